@@ -1,0 +1,187 @@
+/* libparsy_cuda — C ABI of the B200 (sm_100a) executor for ParSy's numeric hot path.
+ *
+ * Two layers:
+ *   1. DROP-IN entry points: the reference's free-function executor signatures, argument for argument
+ *      (SURVEY.md §8(b)).  Every pointer is a HOST pointer owned by the caller; the call uploads, runs
+ *      the CUDA executor and downloads the result (lValues / x).  Names carry a parsy_cuda_ prefix so
+ *      the library can be linked next to the reference headers; INTEGRATION.md shows the one-line
+ *      forwarding stubs.
+ *   2. RESIDENT handle API: structure and values stay in HBM between calls so that the numeric
+ *      factorization and the triangular sweeps can be timed (and re-run) without PCIe traffic.
+ *
+ * Plain C types only.  No CPU fallback exists: every entry point returns an error if no CUDA device
+ * is usable (PARSY_CUDA_ERR_NO_DEVICE).
+ */
+#ifndef PARSY_CUDA_H
+#define PARSY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
+/* status codes of the handle API                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+#define PARSY_CUDA_OK 0
+#define PARSY_CUDA_ERR_NOT_SPD 1        /* a diagonal block was not positive definite (dpotrf info != 0) */
+#define PARSY_CUDA_ERR_BAD_ARG 2        /* NULL / inconsistent structure arrays                          */
+#define PARSY_CUDA_ERR_BAD_SCHEDULE 3   /* LBC schedule is not a legal topological order                 */
+#define PARSY_CUDA_ERR_NO_DEVICE 4      /* no CUDA device / driver                                       */
+#define PARSY_CUDA_ERR_CUDA 5           /* a CUDA runtime call failed (see parsy_cuda_last_error)        */
+#define PARSY_CUDA_ERR_STATE 6          /* call order violated (e.g. solve before factor)                */
+
+const char* parsy_cuda_last_error(void);
+int parsy_cuda_device_count(void);
+/* library version: major*10000 + minor*100 + patch */
+int parsy_cuda_version(void);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* 1. drop-in entry points (host pointers, reference signatures)                                     */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* Replaces  bool cholesky_left_par_05(...)   cholesky/parallel_PB_Cholesky_05.h:27-39
+ * (call sites examples/choleskyTest01.cpp:213-222, examples/triangularTest02.cpp:106-115).
+ *   c,r,values   tril(P A P') in CSC (int pointers);        lC,lR,Li_ptr  BCSC factor structure
+ *   lValues      xsize doubles; the reference requires the caller to zero it (choleskyTest01.cpp:202);
+ *                this implementation zeroes on the device, so the host content on entry is ignored
+ *   blockSet     `super`, supNo+1 first-columns;            aTree  supernodal etree (sParent)
+ *   cT,rT        triu(P A P') pattern — the reference feeds it to ereach_sn (common/Reach.h:112); here the
+ *                descendant lists are derived from the factor structure itself (identical sets), so cT/rT
+ *                may be NULL
+ *   levelPtr/parPtr/partition   the LBC schedule (H-levels x w-partitions); levelSet/nPar unused (NULL/0)
+ *   timing       >= 2 doubles: [0] = seconds in H-levels 0..nLevels-2, [1] = seconds in the last H-level
+ *                (parallel_PB_Cholesky_05.h:266,418), measured with CUDA events on the device
+ *   chunk, threads, super_max, col_max, nodCost  accepted for signature parity, not used
+ * Returns 1 on success, 0 if a diagonal block is not positive definite or on any error
+ * (the reference returns false on dpotrf info != 0, :206-207,252-253). */
+int parsy_cuda_cholesky_left_par_05(int n, int* c, int* r, double* values, size_t* lC, int* lR, size_t* Li_ptr,
+                                    double* lValues, int* blockSet, int supNo, double* timing, int* aTree, int* cT,
+                                    int* rT, int* col2Sup, int nLevels, int* levelPtr, int* levelSet, int nPar,
+                                    int* parPtr, int* partition, int chunk, int threads, int super_max, int col_max,
+                                    double* nodCost);
+
+/* Replaces  bool cholesky_left_sn_07(...)   cholesky/PB_Cholesky.h:16-19  (serial twin driven by a prune set).
+ * prunePtr/pruneSet (descendant lists per supernode) are accepted and validated against the factor
+ * structure; map/contribs scratch arguments are ignored (may be NULL). Runs the same device executor with
+ * a single H-level whose single w-partition is 0..supNo-1. */
+int parsy_cuda_cholesky_left_sn_07(int n, int* c, int* r, double* values, size_t* lC, int* lR, size_t* Li_ptr,
+                                   double* lValues, int* blockSet, int supNo, double* timing, int* prunePtr,
+                                   int* pruneSet, int* map, double* contribs);
+
+/* Replace the supernodal forward solves of triangularSolve/Triangular_BCSC.h (:14, :115, :171, :238).
+ * x is solved in place (host pointer, n doubles).  Return 1, or 0 when Lp/Li/x is NULL (:24,:185) or on error.
+ * All four run the same device sweep; they differ in the schedule they are handed, exactly as the reference:
+ * none (supernode order), etree level sets, LBC schedule, LBC schedule with a peeled last level. */
+int parsy_cuda_blockedLsolve(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr, int* col2sup,
+                             int* sup2col, int supNo, double* x);
+int parsy_cuda_leveledBlockedLsolve(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr, int* col2sup,
+                                    int* sup2col, int supNo, double* x, int levels, int* levelPtr, int* levelSet,
+                                    int chunk);
+int parsy_cuda_H2LeveledBlockedLsolve(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr,
+                                      int* col2sup, int* sup2col, int supNo, double* x, int levels, int* levelPtr,
+                                      int* levelSet, int parts, int* parPtr, int* partition, int chunk);
+int parsy_cuda_H2LeveledBlockedLsolve_Peeled(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr,
+                                             int* col2sup, int* sup2col, int supNo, double* x, int levels,
+                                             int* levelPtr, int* levelSet, int parts, int* parPtr, int* partition,
+                                             int chunk, int threads);
+/* NEW (the reference has no backward sweep): solves L' x = b in place on the same arrays. */
+int parsy_cuda_blockedLtsolve(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr, int* col2sup,
+                              int* sup2col, int supNo, double* x);
+
+/* Replace the column (CSC) forward solves of triangularSolve/Triangular_CSC.h (:14, :50, :76):
+ * Lp/Li/Lx is a CSC lower-triangular matrix with the diagonal first in every column. */
+int parsy_cuda_lsolve(int n, int* Lp, int* Li, double* Lx, double* x);
+int parsy_cuda_lsolvePar(int n, int* Lp, int* Li, double* Lx, double* x, int levels, int* levelPtr, int* levelSet,
+                         int chunk);
+int parsy_cuda_lsolveParH2(int n, int* Lp, int* Li, double* Lx, double* x, int levels, int* levelPtr,
+                           int* levelSet, int parts, int* parPtr, int* partition, int chunk);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* 2. resident handle API                                                                            */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct parsy_cuda_solver parsy_cuda_solver;
+
+/* Options; zero-initialise and override what you need. */
+typedef struct parsy_cuda_options {
+  int device;          /* CUDA device ordinal                                                     */
+  int block_cols;      /* NB: block-column width wide supernodes are factored in (0 = default 128) */
+  int use_graph;       /* 1 = capture the factorization / sweeps into CUDA graphs (default)        */
+  int ignore_hlevels;  /* 1 = schedule by etree dependencies only, not by LBC H-level barriers     */
+  int rank;            /* multi-GPU: this process' rank ...                                        */
+  int world;           /* ... of `world` ranks (0/1 = single GPU)                                  */
+  int reserved[10];
+} parsy_cuda_options;
+
+/* Builds the device-resident symbolic state from the inspector's arrays (all HOST pointers, copied):
+ *   n, c, r           tril(P A P') pattern (values come later)
+ *   lC, lR, Li_ptr    BCSC structure (common/def.h:117-204)
+ *   blockSet, supNo   supernode partition;  aTree = sParent;  col2Sup
+ *   nLevels, levelPtr, parPtr, partition    LBC schedule (cholesky/InspectionLevel_06.h:18)
+ * The derived task lists (descendant pairs with (lb, ndrow1, ndrow3), relative row indices, per-level
+ * batches) are computed here once per structure. */
+int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, const int* r, const size_t* lC, const int* lR,
+                      const size_t* Li_ptr, const int* blockSet, int supNo, const int* aTree, const int* col2Sup,
+                      int nLevels, const int* levelPtr, const int* parPtr, const int* partition,
+                      const parsy_cuda_options* opt);
+void parsy_cuda_destroy(parsy_cuda_solver* s);
+
+/* A values: nnz(A) doubles in the order of c/r. Host -> device. */
+int parsy_cuda_set_values(parsy_cuda_solver* s, const double* values);
+/* Numeric factorization on the device: zero L, scatter A, run every H-level. Asynchronous on the solver's
+ * stream; parsy_cuda_sync() or any download waits for it. */
+int parsy_cuda_factor(parsy_cuda_solver* s);
+/* Waits for the stream; returns PARSY_CUDA_ERR_NOT_SPD if the last factorization hit a bad pivot. */
+int parsy_cuda_sync(parsy_cuda_solver* s);
+/* Device factor -> host lValues (xsize doubles), layout identical to the reference's valL. */
+int parsy_cuda_get_factor(parsy_cuda_solver* s, double* lValues);
+/* Host lValues -> device (lets the solves run on a factor produced elsewhere). */
+int parsy_cuda_set_factor(parsy_cuda_solver* s, const double* lValues);
+
+/* Triangular sweeps on the resident factor; rhs lives on the device. */
+#define PARSY_CUDA_SOLVE_FWD 1  /* L y = b   */
+#define PARSY_CUDA_SOLVE_BWD 2  /* L' x = y  */
+int parsy_cuda_set_rhs(parsy_cuda_solver* s, const double* b);      /* host n doubles -> device */
+int parsy_cuda_get_rhs(parsy_cuda_solver* s, double* x);            /* device -> host           */
+int parsy_cuda_solve(parsy_cuda_solver* s, int which);              /* FWD, BWD or FWD|BWD      */
+
+/* Device-side timing of the last parsy_cuda_factor call (CUDA events):
+ * out[0] = all H-levels but the last, out[1] = last H-level, out[2] = assembly (zero + scatter A), seconds. */
+int parsy_cuda_factor_times(parsy_cuda_solver* s, double* out3);
+
+/* Introspection used by bench.py / tests (counts are exact, computed by the planner). */
+typedef struct parsy_cuda_stats {
+  int64_t n, nsuper, xsize, ssize, nnzA;
+  int64_t n_pairs;            /* (supernode, descendant) update pairs, = sum of ereach_sn sizes   */
+  int64_t n_pairs_small;      /* pairs run by the warp-cooperative FMA kernel                      */
+  int64_t n_pairs_tiled;      /* pairs run by the DMMA tile kernel                                 */
+  int64_t n_steps;            /* dependency steps (kernel-batch boundaries)                        */
+  int64_t n_block_cols;       /* block columns of wide supernodes                                  */
+  int64_t rel_entries;        /* relative-index entries resident on the device                     */
+  int64_t launches_factor;    /* kernel launches per factorization                                 */
+  int64_t launches_fwd, launches_bwd;
+  double flops_potrf, flops_trsm, flops_update;   /* executed supernodal flops (F_sn)             */
+  double bytes_solve;         /* algorithmic bytes of one sweep                  */
+  int64_t device_bytes;       /* HBM held by the handle                                            */
+  int64_t reserved[8];
+} parsy_cuda_stats;
+int parsy_cuda_get_stats(parsy_cuda_solver* s, parsy_cuda_stats* out);
+
+/* Raw device pointers for callers that keep data on the GPU (e.g. bench.py with torch tensors). */
+double* parsy_cuda_device_factor(parsy_cuda_solver* s);   /* xsize doubles */
+double* parsy_cuda_device_rhs(parsy_cuda_solver* s);      /* n doubles     */
+double* parsy_cuda_device_values(parsy_cuda_solver* s);   /* nnzA doubles  */
+void* parsy_cuda_stream(parsy_cuda_solver* s);            /* cudaStream_t  */
+
+/* Multi-GPU: exchange hooks. With world > 1 each rank factors the subtrees it owns; before the shared
+ * top of the tree every rank needs the panels of the others. The library exposes the ownership map and
+ * the panel ranges so the host (torch.distributed / NCCL) moves them; see DESIGN.md (e). */
+int parsy_cuda_owned_ranges(parsy_cuda_solver* s, int rank, int64_t* begin_end_pairs, int max_pairs);
+int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase);   /* 0 = owned subtrees, 1 = shared top */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARSY_CUDA_H */

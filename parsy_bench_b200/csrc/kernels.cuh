@@ -1,0 +1,611 @@
+// Device kernels of the B200 executor (sm_100a).  FP64 throughout.
+//
+//   k_gemm_tiles     DMMA (mma.sync.m8n8k4.f64) tile kernel: SYRK/GEMM update with fused scatter-subtract
+//                    epilogue (K3+K4+K5 of SURVEY.md §2c) and TRSM through the inverse diagonal block (K7).
+//   k_update_small   warp-cooperative FMA update for narrow pairs (K <= 32, ndrow1 <= 32).
+//   k_factor_small   one warp per narrow supernode: POTRF + TRSM fused (K6+K7).
+//   k_potrf_block    one CTA per block column: POTRF of the <=128-wide diagonal block in shared memory
+//                    + its inverse (feeds the DMMA TRSM and the diagonal solves of the sweeps).
+//   k_fwd_* / k_bwd_*  supernodal forward / backward sweeps (K8-K10).
+//   k_build_rel / k_build_apos / k_assemble   structure-time helpers and the A -> L scatter (K1).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "plan.h"
+
+namespace parsy {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 8 : 0;   // src-size 0 => zero-fill, nothing is read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// D(8x8) += A(8x4, row) * B(4x8, col); lane holds A[lane>>2][lane&3], B[lane&3][lane>>2],
+// C[lane>>2][(lane&3)*2 + {0,1}].  SASS: DMMA.8x8x4 (the only native FP64 tensor shape on sm_100a).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMMA tile kernel
+// ------------------------------------------------------------------------------------------------
+template <int TM_, int TN_, int WM_, int WN_, int KC_, int STAGES_>
+struct GemmCfg {
+  static constexpr int TM = TM_, TN = TN_, WM = WM_, WN = WN_, KC = KC_, STAGES = STAGES_;
+  static constexpr int WARPS_M = TM / WM, WARPS_N = TN / WN, THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int LDA = TM + 4, LDB = TN + 4;   // (LD mod 16) == 4 -> conflict-free fragment loads
+  static constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_DOUBLES * 8 + (TM + TN) * 4;
+  static constexpr int FM = WM / 8, FN = WN / 8;
+};
+using Cfg128 = GemmCfg<128, 128, 64, 32, 8, 4>;
+using Cfg64 = GemmCfg<64, 64, 32, 32, 8, 4>;
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS) k_gemm_tiles(const GemmTask* __restrict__ tasks, int ntasks,
+                                                            double* __restrict__ lv, const double* __restrict__ linv,
+                                                            const int* __restrict__ rel) {
+  extern __shared__ __align__(16) double smem[];
+  int* srel = reinterpret_cast<int*>(smem + C::STAGES * C::STAGE_DOUBLES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bid = blockIdx.x;
+  // locate the task that owns this tile (tile0 is an exclusive prefix over the launch)
+  int lo = 0, hi = ntasks - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tasks[mid].tile0 <= bid) lo = mid; else hi = mid - 1;
+  }
+  const GemmTask T = tasks[lo];
+  int t = bid - T.tile0;
+  const int MT = (T.M + C::TM - 1) / C::TM;
+  int mi, ni;
+  if (T.flags & GF_LOWER) {        // lower trapezoid of tiles: column ni holds row tiles ni..MT-1
+    ni = 0;
+    int cnt = MT;
+    while (t >= cnt) { t -= cnt; ++ni; cnt = MT - ni; }
+    mi = ni + t;
+  } else {
+    mi = t % MT; ni = t / MT;
+  }
+  const int m0 = mi * C::TM, n0 = ni * C::TN;
+  const int mrows = min(C::TM, T.M - m0), nrows = min(C::TN, T.N - n0);
+  const double* __restrict__ A = lv + T.a_off + m0;
+  const double* __restrict__ B = ((T.flags & GF_B_LINV) ? linv : lv) + T.b_off + n0;
+  const int K = T.K, lda = T.lda, ldb = T.ldb;
+
+  for (int i = tid; i < C::TM + C::TN; i += C::THREADS) {
+    const bool isrow = i < C::TM;
+    const int loc = isrow ? i : i - C::TM;
+    const int idx = isrow ? m0 + loc : n0 + loc;
+    const bool valid = isrow ? (loc < mrows) : (loc < nrows);
+    int v = idx;
+    if (T.rel_off >= 0) v = valid ? rel[T.rel_off + idx] : 0;
+    srel[i] = v;
+  }
+
+  auto load_chunk = [&](int kc, int stage) {
+    double* As = smem + stage * C::STAGE_DOUBLES;
+    double* Bs = As + C::KC * C::LDA;
+    const int k0 = kc * C::KC;
+#pragma unroll
+    for (int e = tid; e < C::KC * C::TM; e += C::THREADS) {
+      const int kk = e / C::TM, i = e % C::TM;
+      const bool p = (i < mrows) && (k0 + kk < K);
+      const double* src = p ? (A + (int64_t)(k0 + kk) * lda + i) : lv;
+      cp_async8(&As[kk * C::LDA + i], src, p);
+    }
+#pragma unroll
+    for (int e = tid; e < C::KC * C::TN; e += C::THREADS) {
+      const int kk = e / C::TN, j = e % C::TN;
+      const bool p = (j < nrows) && (k0 + kk < K);
+      const double* src = p ? (B + (int64_t)(k0 + kk) * ldb + j) : lv;
+      cp_async8(&Bs[kk * C::LDB + j], src, p);
+    }
+  };
+
+  const int nchunks = (K + C::KC - 1) / C::KC;
+#pragma unroll
+  for (int s = 0; s < C::STAGES - 1; ++s) {
+    if (s < nchunks) load_chunk(s, s);
+    cp_async_commit();
+  }
+  double acc[C::FM][C::FN][2];
+#pragma unroll
+  for (int im = 0; im < C::FM; ++im)
+#pragma unroll
+    for (int in = 0; in < C::FN; ++in) acc[im][in][0] = acc[im][in][1] = 0.0;
+
+  const int wm0 = (warp % C::WARPS_M) * C::WM, wn0 = (warp / C::WARPS_M) * C::WN;
+  const int fr = lane >> 2, fk = lane & 3;
+  // skip warps whose whole sub-tile is out of range or strictly above the diagonal
+  bool warp_active = (wm0 < mrows) && (wn0 < nrows);
+  if ((T.flags & GF_LOWER) && (m0 + wm0 + C::WM - 1 < n0 + wn0)) warp_active = false;
+
+  for (int kc = 0; kc < nchunks; ++kc) {
+    cp_async_wait<C::STAGES - 2>();
+    __syncthreads();
+    const int nx = kc + C::STAGES - 1;
+    if (nx < nchunks) load_chunk(nx, nx % C::STAGES);
+    cp_async_commit();
+    if (warp_active) {
+      const double* As = smem + (kc % C::STAGES) * C::STAGE_DOUBLES;
+      const double* Bs = As + C::KC * C::LDA;
+#pragma unroll
+      for (int k4 = 0; k4 < C::KC; k4 += 4) {
+        double a[C::FM], b[C::FN];
+#pragma unroll
+        for (int im = 0; im < C::FM; ++im) a[im] = As[(k4 + fk) * C::LDA + wm0 + im * 8 + fr];
+#pragma unroll
+        for (int in = 0; in < C::FN; ++in) b[in] = Bs[(k4 + fk) * C::LDB + wn0 + in * 8 + fr];
+#pragma unroll
+        for (int im = 0; im < C::FM; ++im)
+#pragma unroll
+          for (int in = 0; in < C::FN; ++in) dmma884(acc[im][in][0], acc[im][in][1], a[im], b[in]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (!warp_active) return;
+
+  // epilogue: scatter through the relative indices
+  const bool lower = T.flags & GF_LOWER, atomic = T.flags & GF_ATOMIC, overwrite = T.flags & GF_OVERWRITE;
+  double* __restrict__ Cb = lv + T.c_off;
+  const int64_t ldc = T.ldc;
+#pragma unroll
+  for (int in = 0; in < C::FN; ++in) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = wn0 + in * 8 + fk * 2 + e;
+      if (j >= nrows) continue;
+      const int64_t coff = (int64_t)srel[C::TM + j] * ldc;
+#pragma unroll
+      for (int im = 0; im < C::FM; ++im) {
+        const int i = wm0 + im * 8 + fr;
+        if (i >= mrows) continue;
+        if (lower && (m0 + i < n0 + j)) continue;
+        double* dst = Cb + coff + srel[i];
+        const double v = acc[im][in][e];
+        if (overwrite) *dst = v;
+        else if (atomic) atomicAdd(dst, -v);
+        else *dst -= v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small pairs: one warp per (pair, <=256-row chunk); K <= 32, N <= 32
+// ------------------------------------------------------------------------------------------------
+template <int KT>
+__device__ __forceinline__ void small_update_rows(const GemmTask& T, int row0, int nrows, int lane, const double* Bs,
+                                                  const int* srelc, double* __restrict__ lv,
+                                                  const int* __restrict__ rel) {
+  const double* __restrict__ src = lv + T.a_off;
+  for (int i = row0 + lane; i < row0 + nrows; i += 32) {
+    double a[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) a[k] = (k < T.K) ? src[(int64_t)k * T.lda + i] : 0.0;
+    const int tr = rel[T.rel_off + i];
+    const int jmax = min(T.N, i + 1);
+    double* __restrict__ Cb = lv + T.c_off + tr;
+    for (int j = 0; j < jmax; ++j) {
+      double dot = 0.0;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) dot = fma(a[k], Bs[k * 33 + j], dot);
+      atomicAdd(Cb + (int64_t)srelc[j] * T.ldc, -dot);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_update_small(const SmallTask* __restrict__ st, int count,
+                                                       const GemmTask* __restrict__ tasks, double* __restrict__ lv,
+                                                       const int* __restrict__ rel) {
+  __shared__ double sB[4][32 * 33];
+  __shared__ int sRelc[4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 4 + warp;
+  if (wid >= count) return;
+  const SmallTask S = st[wid];
+  const GemmTask T = tasks[S.pair];
+  double* Bs = sB[warp];
+  const double* __restrict__ src = lv + T.a_off;
+  for (int k = 0; k < T.K; ++k)
+    if (lane < T.N) Bs[k * 33 + lane] = src[(int64_t)k * T.lda + lane];
+  if (lane < T.N) sRelc[warp][lane] = rel[T.rel_off + lane];
+  __syncwarp();
+  if (T.K <= 4) small_update_rows<4>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
+  else if (T.K <= 16) small_update_rows<16>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
+  else small_update_rows<32>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
+}
+
+// ------------------------------------------------------------------------------------------------
+// narrow supernodes: one warp each, POTRF (MyBLAS.h:10-25 semantics) + TRSM (MyBLAS.h:27-35) fused
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_factor_small(const int* __restrict__ list, int count,
+                                                       const SupInfo* __restrict__ sup, double* __restrict__ lv,
+                                                       int* __restrict__ info) {
+  __shared__ double sD[4][32 * 33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 4 + warp;
+  if (wid >= count) return;
+  const SupInfo I = sup[list[wid]];
+  const int w = I.w, r = I.r;
+  double* __restrict__ P = lv + I.valptr;
+  double* S = sD[warp];
+  for (int c = 0; c < w; ++c)
+    if (lane < w) S[c * 33 + lane] = P[(int64_t)c * r + lane];
+  __syncwarp();
+  for (int c = 0; c < w; ++c) {
+    double acc = S[c * 33 + lane];
+    for (int k = 0; k < c; ++k) acc = fma(-S[k * 33 + lane], S[k * 33 + c], acc);
+    const double piv = __shfl_sync(0xffffffffu, acc, c);
+    if (!(piv > 0.0) && lane == 0) atomicCAS(info, 0, I.col0 + c + 1);
+    const double l = sqrt(piv);
+    const double v = (lane == c) ? l : acc / l;
+    if (lane >= c && lane < w) S[c * 33 + lane] = v;
+    __syncwarp();
+  }
+  for (int c = 0; c < w; ++c)
+    if (lane >= c && lane < w) P[(int64_t)c * r + lane] = S[c * 33 + lane];
+  // rows below the diagonal block: x * L11' = a, one lane per row
+  for (int i = w + lane; i < r; i += 32) {
+    double x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c < w) {
+        double a = P[(int64_t)c * r + i];
+#pragma unroll
+        for (int k = 0; k < c; ++k) a = fma(-x[k], S[k * 33 + c], a);
+        x[c] = a / S[c * 33 + c];
+        P[(int64_t)c * r + i] = x[c];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block columns: POTRF of the diagonal block + inverse of the factor (one CTA each)
+// shared layout: S(i,c) at c*LD+i, LD = 129; the strict upper triangle holds inv(L) transposed.
+// ------------------------------------------------------------------------------------------------
+constexpr int POTRF_LD = NB_MAX + 1;
+constexpr int POTRF_THREADS = 256;
+constexpr size_t POTRF_SMEM = (size_t)NB_MAX * POTRF_LD * 8 + NB_MAX * 8;
+
+// inverse X = inv(L) of the nb x nb lower factor held in S: thread c owns column c; X(i,c), i > c, is kept at
+// the transposed slot S(c,i) (strict upper triangle), the diagonal 1/L(c,c) in rd.
+__device__ __forceinline__ void invert_lower_in_smem(double* S, const double* rd, int nb, int tid) {
+  constexpr int LD = POTRF_LD;
+  if (tid < nb) {
+    const int c = tid;
+    for (int i = 0; i < nb; ++i) {
+      // all threads walk the same (i,k): L(i,k) is a broadcast read
+      double acc = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) {
+        const double xk = (k > c) ? S[k * LD + c] : ((k == c) ? rd[c] : 0.0);
+        acc = fma(-S[k * LD + i], xk, acc);
+      }
+      if (i > c) S[i * LD + c] = acc * rd[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(POTRF_THREADS) k_potrf_block(const BlockTask* __restrict__ bt,
+                                                                const SupInfo* __restrict__ sup,
+                                                                double* __restrict__ lv, double* __restrict__ linv,
+                                                                int* __restrict__ info) {
+  extern __shared__ __align__(16) double smem[];
+  double* rd = smem;            // reciprocal diagonal
+  double* S = smem + NB_MAX;
+  const BlockTask B = bt[blockIdx.x];
+  const SupInfo I = sup[B.sup];
+  const int nb = B.nb, r = I.r, tid = threadIdx.x;
+  double* __restrict__ P = lv + I.valptr + (int64_t)B.j0 * r + B.j0;   // (j0, j0) of the panel
+  constexpr int LD = POTRF_LD;
+  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
+    const int c = e / nb, i = e % nb;
+    if (i >= c) S[c * LD + i] = P[(int64_t)c * r + i];
+  }
+  __syncthreads();
+  // right-looking Cholesky, one column at a time (MyBLAS.h:10-25 semantics)
+  for (int c = 0; c < nb; ++c) {
+    const double piv = S[c * LD + c];
+    if (tid == 0 && !(piv > 0.0)) atomicCAS(info, 0, I.col0 + B.j0 + c + 1);
+    const double l = sqrt(piv);
+    __syncthreads();
+    for (int i = c + tid; i < nb; i += POTRF_THREADS) S[c * LD + i] = (i == c) ? l : S[c * LD + i] / l;
+    if (tid == 0) rd[c] = 1.0 / l;
+    __syncthreads();
+    // trailing rank-1 update of the lower triangle: columns k > c, rows i >= k
+    const int rem = nb - c - 1;
+    for (int e = tid; e < rem * rem; e += POTRF_THREADS) {
+      const int kk = e / rem, ii = e % rem;
+      if (ii >= kk) {
+        const int k = c + 1 + kk, i = c + 1 + ii;
+        S[k * LD + i] = fma(-S[c * LD + i], S[c * LD + k], S[k * LD + i]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
+    const int c = e / nb, i = e % nb;
+    if (i >= c) P[(int64_t)c * r + i] = S[c * LD + i];
+  }
+  invert_lower_in_smem(S, rd, nb, tid);
+  __syncthreads();
+  double* __restrict__ X = linv + (int64_t)B.slot * NB_MAX * NB_MAX;
+  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
+    const int c = e / nb, i = e % nb;
+    X[c * NB_MAX + i] = (i > c) ? S[i * LD + c] : ((i == c) ? rd[c] : 0.0);
+  }
+}
+
+// inverse diagonal blocks for a factor that was produced elsewhere (parsy_cuda_set_factor, drop-in solves)
+__global__ void __launch_bounds__(POTRF_THREADS) k_invert_block(const BlockTask* __restrict__ bt,
+                                                                 const SupInfo* __restrict__ sup,
+                                                                 const double* __restrict__ lv,
+                                                                 double* __restrict__ linv) {
+  extern __shared__ __align__(16) double smem[];
+  double* rd = smem;
+  double* S = smem + NB_MAX;
+  const BlockTask B = bt[blockIdx.x];
+  const SupInfo I = sup[B.sup];
+  const int nb = B.nb, r = I.r, tid = threadIdx.x;
+  const double* __restrict__ P = lv + I.valptr + (int64_t)B.j0 * r + B.j0;
+  constexpr int LD = POTRF_LD;
+  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
+    const int c = e / nb, i = e % nb;
+    if (i >= c) S[c * LD + i] = P[(int64_t)c * r + i];
+    if (i == c) rd[c] = 1.0 / P[(int64_t)c * r + i];
+  }
+  __syncthreads();
+  invert_lower_in_smem(S, rd, nb, tid);
+  __syncthreads();
+  double* __restrict__ X = linv + (int64_t)B.slot * NB_MAX * NB_MAX;
+  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
+    const int c = e / nb, i = e % nb;
+    X[c * NB_MAX + i] = (i > c) ? S[i * LD + c] : ((i == c) ? rd[c] : 0.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// structure-time helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_row(const int* __restrict__ rows, int len, int key) {
+  int lo = 0, hi = len - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (rows[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// rel[e]: local row (in the target supernode's row list) of every row lb.. of the descendant, per pair
+__global__ void k_build_rel(int64_t total, int npairs, const int64_t* __restrict__ prefix,
+                            const int* __restrict__ psrc, const int* __restrict__ ptgt, const int* __restrict__ plb,
+                            const SupInfo* __restrict__ sup, const int* __restrict__ lR, int* __restrict__ rel) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = npairs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (prefix[mid] <= e) lo = mid; else hi = mid - 1;
+    }
+    const int i = (int)(e - prefix[lo]);
+    const SupInfo D = sup[psrc[lo]], T = sup[ptgt[lo]];
+    const int row = lR[D.rowptr + plb[lo] + i];
+    int v;
+    if (row < T.col0 + T.w) v = row - T.col0;
+    else v = T.w + find_row(lR + T.rowptr + T.w, T.r - T.w, row);
+    rel[e] = v;
+  }
+}
+
+// a_pos[p]: offset in lValues of A entry p (column j, row r[p]) — the `map` of parallel_PB_Cholesky_05.h:100-112
+__global__ void k_build_apos(int64_t nnz, int n, const int* __restrict__ c, const int* __restrict__ r,
+                             const int* __restrict__ col2sup, const SupInfo* __restrict__ sup,
+                             const int* __restrict__ lR, int64_t* __restrict__ apos) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (c[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    const int j = lo;
+    const SupInfo I = sup[col2sup[j]];
+    const int row = r[p];
+    int pos;
+    if (row < I.col0 + I.w) pos = row - I.col0;
+    else pos = I.w + find_row(lR + I.rowptr + I.w, I.r - I.w, row);
+    apos[p] = I.valptr + (int64_t)(j - I.col0) * I.r + pos;
+  }
+}
+
+__global__ void k_assemble(int64_t nnz, const int64_t* __restrict__ apos, const double* __restrict__ vals,
+                           double* __restrict__ lv) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
+    lv[apos[p]] = vals[p];
+}
+
+// ------------------------------------------------------------------------------------------------
+// triangular sweeps
+// ------------------------------------------------------------------------------------------------
+// forward, narrow supernodes: x_s = L11^-1 y_s ; y[rows below] -= L21 x_s          (Triangular_BCSC.h:206-224)
+__global__ void __launch_bounds__(128) k_fwd_small(const int* __restrict__ list, int count,
+                                                    const SupInfo* __restrict__ sup, const int* __restrict__ lR,
+                                                    const double* __restrict__ lv, double* __restrict__ y,
+                                                    double* __restrict__ xs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 4 + warp;
+  if (wid >= count) return;
+  const SupInfo I = sup[list[wid]];
+  const int w = I.w, r = I.r;
+  const double* __restrict__ P = lv + I.valptr;
+  double xv = (lane < w) ? y[I.col0 + lane] : 0.0;
+  for (int c = 0; c < w; ++c) {
+    const double lcol = (lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 1.0;   // column c of L11
+    const double xc = __shfl_sync(0xffffffffu, xv, c) / __shfl_sync(0xffffffffu, lcol, c);
+    if (lane == c) xv = xc;
+    else if (lane > c && lane < w) xv = fma(-lcol, xc, xv);
+  }
+  if (lane < w) xs[I.col0 + lane] = xv;
+  const int* __restrict__ rows = lR + I.rowptr;
+  for (int i0 = w; i0 < r; i0 += 32) {
+    const int i = i0 + lane;
+    double t = 0.0;
+    for (int c = 0; c < w; ++c) {
+      const double xc = __shfl_sync(0xffffffffu, xv, c);
+      if (i < r) t = fma(P[(int64_t)c * r + i], xc, t);
+    }
+    if (i < r) atomicAdd(&y[rows[i]], -t);
+  }
+}
+
+// forward, block columns: every CTA recomputes x_b = inv(L_bb) y_b (nb x nb GEMV from the inverse store),
+// tile 0 publishes it to xs, and each CTA applies its 64-row slice of L21 to y.
+constexpr int SOLVE_ROWS = 64;
+__global__ void __launch_bounds__(256) k_fwd_block(const BlockTask* __restrict__ bt, int ntasks,
+                                                    const SupInfo* __restrict__ sup, const int* __restrict__ lR,
+                                                    const double* __restrict__ lv, const double* __restrict__ linv,
+                                                    double* __restrict__ y, double* __restrict__ xs) {
+  __shared__ double sy[NB_MAX], sx[NB_MAX], spart[4][SOLVE_ROWS];
+  const int tid = threadIdx.x, bid = blockIdx.x;
+  int lo = 0, hi = ntasks - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (bt[mid].tile0 <= bid) lo = mid; else hi = mid - 1;
+  }
+  const BlockTask B = bt[lo];
+  const SupInfo I = sup[B.sup];
+  const int tile = bid - B.tile0, nb = B.nb, r = I.r;
+  const int cbase = I.col0 + B.j0;
+  if (tid < nb) sy[tid] = y[cbase + tid];
+  __syncthreads();
+  const double* __restrict__ X = linv + (int64_t)B.slot * NB_MAX * NB_MAX;
+  if (tid < nb) {
+    double acc = 0.0;
+    for (int k = 0; k <= tid; ++k) acc = fma(X[k * NB_MAX + tid], sy[k], acc);
+    sx[tid] = acc;
+    if (tile == 0) xs[cbase + tid] = acc;
+  }
+  __syncthreads();
+  const int rbeg = B.j0 + nb + tile * SOLVE_ROWS;       // local row in the supernode
+  const int nr = min(SOLVE_ROWS, r - rbeg);
+  if (nr <= 0) return;
+  const int ri = tid & 63, cg = tid >> 6;
+  const double* __restrict__ P = lv + I.valptr + (int64_t)B.j0 * r + rbeg;
+  double t = 0.0;
+  if (ri < nr)
+    for (int c = cg; c < nb; c += 4) t = fma(P[(int64_t)c * r + ri], sx[c], t);
+  spart[cg][ri] = t;
+  __syncthreads();
+  if (tid < nr) {
+    const double s = spart[0][tid] + spart[1][tid] + spart[2][tid] + spart[3][tid];
+    atomicAdd(&y[lR[I.rowptr + rbeg + tid]], -s);
+  }
+}
+
+// backward, narrow supernodes: x_s = L11^-T (y_s - L21' x[rows below])
+__global__ void __launch_bounds__(128) k_bwd_small(const int* __restrict__ list, int count,
+                                                    const SupInfo* __restrict__ sup, const int* __restrict__ lR,
+                                                    const double* __restrict__ lv, double* __restrict__ x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 4 + warp;
+  if (wid >= count) return;
+  const SupInfo I = sup[list[wid]];
+  const int w = I.w, r = I.r;
+  const double* __restrict__ P = lv + I.valptr;
+  const int* __restrict__ rows = lR + I.rowptr;
+  double mine = (lane < w) ? x[I.col0 + lane] : 0.0;   // lane c holds y_c
+  // t_c = sum_i L(i,c) x[rows[i]]: lanes stride the rows, shuffle-reduce per column
+  for (int c = 0; c < w; ++c) {
+    double part = 0.0;
+    for (int i = w + lane; i < r; i += 32) part = fma(P[(int64_t)c * r + i], x[rows[i]], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == c) mine -= part;
+  }
+  // L11' x = mine, backward substitution; lane j holds x_j
+  for (int c = w - 1; c >= 0; --c) {
+    const double lcol = (lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 0.0;   // L(lane, c)
+    double part = (lane > c && lane < w) ? lcol * mine : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const double d = __shfl_sync(0xffffffffu, lcol, c);
+    if (lane == c) mine = (mine - part) / d;
+  }
+  if (lane < w) x[I.col0 + lane] = mine;
+}
+
+// backward, block columns, phase A: x_b -= L21_b' x[rows below] (64-row slices, atomics into x_b)
+__global__ void __launch_bounds__(256) k_bwd_block_gemv(const BlockTask* __restrict__ bt, int ntasks,
+                                                         const SupInfo* __restrict__ sup, const int* __restrict__ lR,
+                                                         const double* __restrict__ lv, double* __restrict__ x) {
+  __shared__ double sx[SOLVE_ROWS];
+  const int tid = threadIdx.x, bid = blockIdx.x, lane = tid & 31, warp = tid >> 5;
+  int lo = 0, hi = ntasks - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (bt[mid].tile0 <= bid) lo = mid; else hi = mid - 1;
+  }
+  const BlockTask B = bt[lo];
+  const SupInfo I = sup[B.sup];
+  const int tile = bid - B.tile0, nb = B.nb, r = I.r;
+  const int rbeg = B.j0 + nb + tile * SOLVE_ROWS;
+  const int nr = min(SOLVE_ROWS, r - rbeg);
+  if (nr <= 0) return;
+  if (tid < nr) sx[tid] = x[lR[I.rowptr + rbeg + tid]];
+  __syncthreads();
+  const double* __restrict__ P = lv + I.valptr + (int64_t)B.j0 * r + rbeg;
+  // each warp takes columns warp, warp+8, ...; lanes stride the 64 rows; shuffle-reduce
+  for (int c = warp; c < nb; c += 8) {
+    double part = 0.0;
+    for (int i = lane; i < nr; i += 32) part = fma(P[(int64_t)c * r + i], sx[i], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) atomicAdd(&x[I.col0 + B.j0 + c], -part);
+  }
+}
+
+// backward, block columns, phase B: x_b = inv(L_bb)' x_b
+__global__ void __launch_bounds__(128) k_bwd_block_diag(const BlockTask* __restrict__ bt,
+                                                         const SupInfo* __restrict__ sup,
+                                                         const double* __restrict__ linv, double* __restrict__ x) {
+  __shared__ double sy[NB_MAX];
+  const BlockTask B = bt[blockIdx.x];
+  const SupInfo I = sup[B.sup];
+  const int tid = threadIdx.x, nb = B.nb, cbase = I.col0 + B.j0;
+  if (tid < nb) sy[tid] = x[cbase + tid];
+  __syncthreads();
+  const double* __restrict__ X = linv + (int64_t)B.slot * NB_MAX * NB_MAX;
+  if (tid < nb) {
+    // (X' y)_c = sum_{k >= c} X(k,c) y_k ; column c of X is contiguous
+    double acc = 0.0;
+    for (int k = tid; k < nb; ++k) acc = fma(X[tid * NB_MAX + k], sy[k], acc);
+    x[cbase + tid] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column (CSC) forward solve, one level per launch: warp per column            (Triangular_CSC.h:50-71)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_csc_level(const int* __restrict__ cols, int count, const int* __restrict__ Lp,
+                            const int* __restrict__ Li, const double* __restrict__ Lx, double* __restrict__ x) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= count) return;
+  const int j = cols[warp];
+  const int p0 = Lp[j], p1 = Lp[j + 1];
+  const double xj = x[j] / Lx[p0];
+  for (int p = p0 + 1 + lane; p < p1; p += 32) atomicAdd(&x[Li[p]], -Lx[p] * xj);
+  __syncwarp();
+  if (lane == 0) x[j] = xj;
+}
+
+}  // namespace parsy

@@ -1,0 +1,258 @@
+// Planner: turns the inspector's arrays + LBC schedule into per-step kernel batches. See plan.h.
+#include "plan.h"
+#include "../../include/parsy_cuda.h"
+#include <algorithm>
+#include <cstring>
+
+namespace parsy {
+
+void enumerate_pairs(std::vector<PairDesc>& out, int supNo, const int* blockSet, const size_t* Li_ptr, const int* lR,
+                     const int* col2Sup) {
+  // For descendant d, every maximal run of its off-diagonal rows that falls into the columns of one
+  // supernode t is one update pair (t, d).  The reference finds the same [lb, ub] by a linear scan for each
+  // d returned by ereach_sn (parallel_PB_Cholesky_05.h:137-152); rows are sorted, so runs are contiguous.
+  out.clear();
+  for (int d = 0; d < supNo; ++d) {
+    const int col0 = blockSet[d], w = blockSet[d + 1] - col0;
+    const size_t rp = Li_ptr[col0];
+    const int r = (int)(Li_ptr[blockSet[d + 1]] - rp);
+    int i = w;
+    while (i < r) {
+      const int t = col2Sup[lR[rp + i]];
+      int e = i + 1;
+      while (e < r && col2Sup[lR[rp + e]] == t) ++e;
+      out.push_back(PairDesc{t, d, i, e - i, r - i});
+      i = e;
+    }
+  }
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int lower_tiles(int M, int N, int T) {   // tiles (mi, ni) of a T x T grid with mi >= ni
+  const int MT = cdiv(M, T), NT = cdiv(N, T);
+  return NT * MT - NT * (NT - 1) / 2;
+}
+
+int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo,
+               const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+               const int* partition, const PlanOptions& opt) {
+  if (n < 0 || supNo < 0 || !lC || !lR || !Li_ptr || !blockSet || !col2Sup || !levelPtr || !parPtr ||
+      !partition || nLevels < 0) {
+    P.error = "NULL or negative argument";
+    return PARSY_CUDA_ERR_BAD_ARG;
+  }
+  const int NB = opt.nb <= 0 ? 128 : opt.nb;
+  if (NB > NB_MAX || NB < 8 || (NB % 8) != 0) { P.error = "block_cols must be a multiple of 8 in [8,128]"; return PARSY_CUDA_ERR_BAD_ARG; }
+  P.n = n; P.nsuper = supNo; P.nlevels = nLevels; P.nb = NB;
+  P.sup.resize(supNo);
+  if (supNo > 0 && (blockSet[0] != 0 || blockSet[supNo] != n)) { P.error = "blockSet does not cover 0..n"; return PARSY_CUDA_ERR_BAD_ARG; }
+  int64_t xs = 0, ss = 0;
+  for (int s = 0; s < supNo; ++s) {
+    SupInfo& I = P.sup[s];
+    I.col0 = blockSet[s]; I.w = blockSet[s + 1] - blockSet[s];
+    if (I.w <= 0) { P.error = "empty supernode"; return PARSY_CUDA_ERR_BAD_ARG; }
+    I.rowptr = (int64_t)Li_ptr[I.col0];
+    I.r = (int)(Li_ptr[blockSet[s + 1]] - Li_ptr[I.col0]);
+    I.valptr = (int64_t)lC[I.col0];
+    if (I.r < I.w) { P.error = "supernode with fewer rows than columns"; return PARSY_CUDA_ERR_BAD_ARG; }
+    I.flags = (I.w <= SMALL_W && I.r <= SMALL_R) ? 1 : 0;
+    xs = std::max<int64_t>(xs, I.valptr + (int64_t)I.w * I.r);
+    ss = std::max<int64_t>(ss, I.rowptr + I.r);
+    const double w = I.w, r = I.r;
+    P.flops_potrf += w * w * w / 3.0;
+    P.flops_trsm += w * w * (r - w);
+    P.bytes_solve += 8.0 * (w * (w + 1) / 2 + w * (r - w));
+  }
+  P.xsize = xs; P.ssize = ss;
+  P.bytes_solve += 4.0 * (double)ss + 16.0 * (double)n;
+
+  // ---- schedule: validate, then assign dependency steps --------------------------------------------
+  std::vector<int32_t> hl(supNo, -1), part(supNo, -1), pos(supNo, -1);
+  std::vector<int32_t> order; order.reserve(supNo);
+  for (int H = 0; H < nLevels; ++H)
+    for (int j1 = levelPtr[H]; j1 < levelPtr[H + 1]; ++j1)
+      for (int k1 = parPtr[j1]; k1 < parPtr[j1 + 1]; ++k1) {
+        const int s = partition[k1];
+        if (s < 0 || s >= supNo || hl[s] >= 0) { P.error = "schedule lists a supernode twice or out of range"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
+        hl[s] = H; part[s] = j1; pos[s] = (int)order.size(); order.push_back(s);
+      }
+  if ((int)order.size() != supNo) { P.error = "schedule does not cover every supernode"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
+  // every update pair (target, descendant) must run the descendant first: an earlier H-level, or earlier in
+  // the same w-partition (SURVEY.md Appendix E legality condition)
+  enumerate_pairs(P.pairs, supNo, blockSet, Li_ptr, lR, col2Sup);
+  P.n_pairs = (int64_t)P.pairs.size();
+  std::vector<int64_t> src_ptr(supNo + 1, 0);
+  for (const PairDesc& q : P.pairs) {
+    if (q.tgt <= q.src || q.tgt >= supNo) { P.error = "row structure is not lower triangular"; return PARSY_CUDA_ERR_BAD_ARG; }
+    const bool ok = hl[q.src] < hl[q.tgt] || (hl[q.src] == hl[q.tgt] && part[q.src] == part[q.tgt] && pos[q.src] < pos[q.tgt]);
+    if (!ok) { P.error = "schedule runs a supernode before one of its descendants"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
+    src_ptr[q.src + 1]++;
+  }
+  for (int s = 0; s < supNo; ++s) src_ptr[s + 1] += src_ptr[s];
+  std::vector<int32_t> nblk(supNo), step0(supNo, 0), need(supNo, 0);
+  for (int s = 0; s < supNo; ++s) nblk[s] = P.sup[s].flags ? 1 : cdiv(P.sup[s].w, NB);
+  P.hlevel_first_step.assign(nLevels + 1, 0);
+  int nsteps = 0;
+  {
+    int idx = 0;
+    for (int H = 0; H < nLevels; ++H) {
+      const int base = opt.ignore_hlevels ? 0 : nsteps;
+      P.hlevel_first_step[H] = nsteps;
+      int cnt = 0;
+      for (int j1 = levelPtr[H]; j1 < levelPtr[H + 1]; ++j1) cnt += parPtr[j1 + 1] - parPtr[j1];
+      for (int q = 0; q < cnt; ++q, ++idx) {
+        const int s = order[idx];
+        step0[s] = std::max(base, need[s]);
+        const int last = step0[s] + nblk[s] - 1;
+        nsteps = std::max(nsteps, last + 1);
+        for (int64_t e = src_ptr[s]; e < src_ptr[s + 1]; ++e) need[P.pairs[e].tgt] = std::max(need[P.pairs[e].tgt], last + 1);
+      }
+    }
+    P.hlevel_first_step[nLevels] = nsteps;
+  }
+
+  // ---- update pairs ---------------------------------------------------------------------------------
+  for (const PairDesc& q : P.pairs) {
+    const double k = P.sup[q.src].w, nd1 = q.nd1, nd3 = q.m - q.nd1;
+    P.flops_update += nd1 * nd1 * k + 2.0 * nd3 * nd1 * k;
+  }
+  // pairs are emitted grouped by source d ascending; the step of a pair is the last step of its source
+  // (the whole width of d is applied in one task, K = width(d)).
+
+  // ---- bucket everything by step ----------------------------------------------------------------------
+  // Two passes to keep memory bounded: count, then fill flat arrays.
+  P.steps.assign(nsteps, Step());
+  for (int H = 0; H < nLevels; ++H)
+    for (int st = P.hlevel_first_step[H]; st < P.hlevel_first_step[H + 1]; ++st) P.steps[st].hlevel = H;
+  if (opt.ignore_hlevels) for (auto& s : P.steps) s.hlevel = 0;
+
+  std::vector<int32_t> c_small(nsteps, 0), c_blk(nsteps, 0), c_trsm(nsteps, 0), c_128(nsteps, 0), c_64(nsteps, 0),
+      c_us(nsteps, 0), c_st(nsteps, 0);
+  auto is_small_pair = [&](int K, int N) { return K <= 32 && N <= 32; };
+  auto use128 = [&](int M, int N) { return N > 64 && (int64_t)M * N >= 2 * 128 * 128; };
+  auto small_chunks = [&](int M) { return cdiv(M, 256); };
+
+  for (int s = 0; s < supNo; ++s) {
+    const SupInfo& I = P.sup[s];
+    if (I.flags) { c_small[step0[s]]++; continue; }
+    for (int b = 0; b < nblk[s]; ++b) {
+      const int st = step0[s] + b, j0 = b * NB, nb = std::min(NB, I.w - j0);
+      c_blk[st]++;
+      if (I.r - j0 - nb > 0) c_trsm[st]++;
+      if (j0 + nb < I.w) { if (use128(I.r - j0 - nb, I.w - j0 - nb)) c_128[st]++; else c_64[st]++; }
+    }
+  }
+  for (const PairDesc& q : P.pairs) {
+    const int st = step0[q.src] + nblk[q.src] - 1, K = P.sup[q.src].w;
+    if (is_small_pair(K, q.nd1)) { c_us[st]++; c_st[st] += small_chunks(q.m); }
+    else if (use128(q.m, q.nd1)) c_128[st]++;
+    else c_64[st]++;
+  }
+  // offsets
+  std::vector<int64_t> o_small(nsteps + 1, 0), o_blk(nsteps + 1, 0), o_gemm(nsteps + 1, 0), o_st(nsteps + 1, 0);
+  for (int st = 0; st < nsteps; ++st) {
+    o_small[st + 1] = o_small[st] + c_small[st];
+    o_blk[st + 1] = o_blk[st] + c_blk[st];
+    o_gemm[st + 1] = o_gemm[st] + c_trsm[st] + c_128[st] + c_64[st] + c_us[st];
+    o_st[st + 1] = o_st[st] + c_st[st];
+  }
+  if (o_gemm[nsteps] > INT32_MAX || o_st[nsteps] > INT32_MAX) { P.error = "task list too large"; return PARSY_CUDA_ERR_BAD_ARG; }
+  P.small_list.resize(o_small[nsteps]);
+  P.block_tasks.resize(o_blk[nsteps]);
+  P.gemm_tasks.resize(o_gemm[nsteps]);
+  P.small_tasks.resize(o_st[nsteps]);
+  std::vector<int32_t> f_small(nsteps, 0), f_blk(nsteps, 0), f_trsm(nsteps, 0), f_128(nsteps, 0), f_64(nsteps, 0),
+      f_us(nsteps, 0), f_st(nsteps, 0);
+  for (int st = 0; st < nsteps; ++st) {
+    Step& S = P.steps[st];
+    S.small_sup = Range{(int32_t)o_small[st], (int32_t)o_small[st + 1]};
+    S.blocks = Range{(int32_t)o_blk[st], (int32_t)o_blk[st + 1]};
+    int32_t g = (int32_t)o_gemm[st];
+    S.trsm = Range{g, g + c_trsm[st]}; g += c_trsm[st];
+    S.upd128 = Range{g, g + c_128[st]}; g += c_128[st];
+    S.upd64 = Range{g, g + c_64[st]}; g += c_64[st];
+    // the small pairs' GemmTasks follow; they are addressed through small_tasks
+    S.small_upd = Range{(int32_t)o_st[st], (int32_t)o_st[st + 1]};
+  }
+  auto gemm_small_base = [&](int st) { return (int32_t)o_gemm[st] + c_trsm[st] + c_128[st] + c_64[st]; };
+
+  int32_t slot = 0;
+  for (int s = 0; s < supNo; ++s) {
+    const SupInfo& I = P.sup[s];
+    if (I.flags) { P.small_list[o_small[step0[s]] + f_small[step0[s]]++] = s; continue; }
+    for (int b = 0; b < nblk[s]; ++b) {
+      const int st = step0[s] + b, j0 = b * NB, nb = std::min(NB, I.w - j0);
+      Step& S = P.steps[st];
+      BlockTask bt; memset(&bt, 0, sizeof(bt));
+      bt.sup = s; bt.j0 = j0; bt.nb = nb; bt.slot = slot;
+      P.block_tasks[o_blk[st] + f_blk[st]++] = bt;
+      S.max_nb = std::max(S.max_nb, nb);
+      const int Mb = I.r - j0 - nb;
+      if (Mb > 0) {
+        GemmTask t; memset(&t, 0, sizeof(t));
+        t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = (int64_t)slot * NB_MAX * NB_MAX; t.c_off = t.a_off;
+        t.rel_off = -1; t.lda = I.r; t.ldb = NB_MAX; t.ldc = I.r; t.M = Mb; t.N = nb; t.K = nb;
+        t.flags = GF_OVERWRITE | GF_B_LINV;
+        P.gemm_tasks[S.trsm.begin + f_trsm[st]++] = t;
+      }
+      if (j0 + nb < I.w) {
+        GemmTask t; memset(&t, 0, sizeof(t));
+        t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = t.a_off;
+        t.c_off = I.valptr + (int64_t)(j0 + nb) * I.r + j0 + nb;
+        t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = Mb; t.N = I.w - j0 - nb; t.K = nb; t.flags = GF_LOWER;
+        if (use128(t.M, t.N)) P.gemm_tasks[S.upd128.begin + f_128[st]++] = t;
+        else P.gemm_tasks[S.upd64.begin + f_64[st]++] = t;
+      }
+      ++slot;
+    }
+  }
+  P.n_slots = slot; P.n_block_cols = slot;
+
+  // real pairs (+ relative-index bookkeeping)
+  P.rel_prefix.assign(P.pairs.size() + 1, 0);
+  P.rel_pair_src.resize(P.pairs.size()); P.rel_pair_tgt.resize(P.pairs.size()); P.rel_pair_lb.resize(P.pairs.size());
+  int64_t rel = 0;
+  for (size_t pi = 0; pi < P.pairs.size(); ++pi) {
+    const PairDesc& q = P.pairs[pi];
+    const SupInfo& D = P.sup[q.src]; const SupInfo& T = P.sup[q.tgt];
+    const int st = step0[q.src] + nblk[q.src] - 1;
+    Step& S = P.steps[st];
+    GemmTask t; memset(&t, 0, sizeof(t));
+    t.a_off = D.valptr + q.lb; t.b_off = t.a_off; t.c_off = T.valptr; t.rel_off = rel;
+    t.lda = t.ldb = D.r; t.ldc = T.r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
+    P.rel_prefix[pi] = rel; P.rel_pair_src[pi] = q.src; P.rel_pair_tgt[pi] = q.tgt; P.rel_pair_lb[pi] = q.lb;
+    rel += q.m;
+    if (is_small_pair(t.K, t.N)) {
+      const int32_t gi = gemm_small_base(st) + f_us[st]++;
+      P.gemm_tasks[gi] = t;
+      for (int r0 = 0; r0 < t.M; r0 += 256) {
+        SmallTask stt; stt.pair = gi; stt.row0 = r0; stt.nrows = std::min(256, t.M - r0); stt.pad = 0;
+        P.small_tasks[o_st[st] + f_st[st]++] = stt;
+      }
+      P.n_pairs_small++;
+    } else if (use128(t.M, t.N)) { P.gemm_tasks[S.upd128.begin + f_128[st]++] = t; P.n_pairs_tiled++; }
+    else { P.gemm_tasks[S.upd64.begin + f_64[st]++] = t; P.n_pairs_tiled++; }
+  }
+  P.rel_prefix[P.pairs.size()] = rel;
+  P.rel_entries = rel;
+
+  // tile prefixes per launch segment
+  for (int st = 0; st < nsteps; ++st) {
+    Step& S = P.steps[st];
+    int32_t acc = 0;
+    for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, 128); }
+    S.trsm_tiles = acc; acc = 0;
+    for (int i = S.upd128.begin; i < S.upd128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128); }
+    S.upd128_tiles = acc; acc = 0;
+    for (int i = S.upd64.begin; i < S.upd64.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 64); }
+    S.upd64_tiles = acc; acc = 0;
+    for (int i = S.blocks.begin; i < S.blocks.end; ++i) {
+      BlockTask& b = P.block_tasks[i];
+      b.tile0 = acc; acc += std::max(1, cdiv(P.sup[b.sup].r - b.j0 - b.nb, 64));
+    }
+    S.solve_tiles = acc;
+  }
+  return PARSY_CUDA_OK;
+}
+
+}  // namespace parsy

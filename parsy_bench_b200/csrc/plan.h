@@ -1,0 +1,134 @@
+// Host-side derived task lists for the device executor ("inspector-executor" split).
+//
+// Input  : the reference inspector's arrays exactly as cholesky_left_par_05 receives them
+//          (cholesky/parallel_PB_Cholesky_05.h:27-39; layout SURVEY.md Appendix A).
+// Output : per dependency step, the batches the CUDA kernels consume:
+//            * small supernodes (width <= SMALL_W) factored by one warp each,
+//            * block columns (<= NB wide) of the remaining supernodes: POTRF + TRSM tasks,
+//            * update pairs (target supernode, descendant) with (lb, ndrow1, nSupRs) — what the reference
+//              finds by scanning the descendant's rows (:137-152) for every supernode returned by ereach_sn
+//              (common/Reach.h:112) — split into DMMA tile tasks and warp-FMA tasks.
+// Nothing here touches numeric values.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <vector>
+#include <string>
+
+namespace parsy {
+
+constexpr int SMALL_W = 32;       // widest supernode handled by the warp-cooperative path
+constexpr int SMALL_R = 1024;     // ... and its largest row count
+constexpr int NB_MAX = 128;       // largest block-column width (POTRF tile held in shared memory)
+
+enum GemmFlags : int32_t {
+  GF_LOWER = 1,      // only elements with row >= col (pair-local) are applied (SYRK part of the trapezoid)
+  GF_ATOMIC = 2,     // target shared with other tasks of the launch: red.global.add.f64
+  GF_OVERWRITE = 4,  // C = A*B' (TRSM through the inverse of the diagonal block), else C -= A*B'
+  GF_B_LINV = 8,     // B operand lives in the inverse-diagonal-block store, not in the factor
+};
+
+// One GEMM-shaped task: C[rel(i), rel(j)] (-)= sum_k A[i,k] * B[j,k], i < M, j < N, k < K.
+struct GemmTask {
+  int64_t a_off;     // offset of A(0,0) in lValues
+  int64_t b_off;     // offset of B(0,0) in lValues (or in the Linv store with GF_B_LINV)
+  int64_t c_off;     // offset of the target panel's (0,0)
+  int64_t rel_off;   // offset into the relative-index array, -1 = identity map
+  int32_t lda, ldb, ldc;
+  int32_t M, N, K;
+  int32_t flags;
+  int32_t tile0;     // first tile of this task within its launch
+};
+static_assert(sizeof(GemmTask) == 64, "GemmTask layout");
+
+// Row chunk of a small pair, one warp each.
+struct SmallTask {
+  int32_t pair;      // index into the GemmTask array
+  int32_t row0;      // first pair-local row of the chunk
+  int32_t nrows;
+  int32_t pad;
+};
+
+struct SupInfo {
+  int64_t rowptr;    // Li_ptr[col0]: start of the row list in lR
+  int64_t valptr;    // lC[col0]: start of the panel in lValues
+  int32_t col0, w, r;
+  int32_t flags;     // 1 = small path
+};
+static_assert(sizeof(SupInfo) == 32, "SupInfo layout");
+
+struct BlockTask {
+  int32_t sup;       // supernode
+  int32_t j0;        // first local column of the block column
+  int32_t nb;        // its width (<= NB)
+  int32_t slot;      // index of its inverse-diagonal-block slot
+  int32_t tile0;     // solve kernels: first row tile of this task within the launch
+  int32_t pad[3];
+};
+static_assert(sizeof(BlockTask) == 32, "BlockTask layout");
+
+// Pair before classification (also used by the tests to compare against ereach_sn).
+struct PairDesc {
+  int32_t tgt, src;  // supernodes
+  int32_t lb;        // first row (index in src's row list) that falls inside tgt's columns
+  int32_t nd1;       // number of src rows inside tgt's columns           (ndrow1)
+  int32_t m;         // rows from lb to the end of src                     (nSupRs = ndrow1 + ndrow3)
+};
+
+struct Range { int32_t begin = 0, end = 0; int32_t size() const { return end - begin; } };
+
+struct Step {
+  int32_t hlevel;
+  Range small_sup;   // into small_list
+  Range blocks;      // into block_tasks
+  Range trsm;        // into gemm_tasks (T128, GF_OVERWRITE|GF_B_LINV)
+  int32_t trsm_tiles = 0;
+  Range upd128;      // into gemm_tasks
+  int32_t upd128_tiles = 0;
+  Range upd64;
+  int32_t upd64_tiles = 0;
+  Range small_upd;   // into small_tasks
+  int32_t solve_tiles = 0;   // row tiles of the block tasks (forward / backward sweeps)
+  int32_t max_nb = 0;        // widest block column in this step
+};
+
+struct PlanOptions {
+  int nb = 128;
+  bool ignore_hlevels = false;
+};
+
+struct Plan {
+  int32_t n = 0, nsuper = 0, nlevels = 0;
+  int64_t xsize = 0, ssize = 0, nnzA = 0;
+  int nb = 128;
+  std::vector<SupInfo> sup;
+  std::vector<int32_t> small_list;
+  std::vector<BlockTask> block_tasks;
+  std::vector<GemmTask> gemm_tasks;
+  std::vector<SmallTask> small_tasks;
+  std::vector<Step> steps;
+  std::vector<int32_t> hlevel_first_step;   // nlevels+1
+  // relative indices: rel_src_row[e] = global row index to look up, rel_tgt[e] = target supernode;
+  // filled on the device from (pair prefix) — here only the per-pair prefix and descriptors
+  std::vector<PairDesc> pairs;              // all pairs, in GemmTask order for the first pairs.size() real pairs
+  std::vector<int64_t> rel_prefix;          // per real pair with a map: start in the rel array (size npairs+1)
+  std::vector<int32_t> rel_pair_src;        // per rel-pair: source supernode
+  std::vector<int32_t> rel_pair_tgt;        // per rel-pair: target supernode
+  std::vector<int32_t> rel_pair_lb;         // per rel-pair: lb
+  int64_t rel_entries = 0;
+  int32_t n_slots = 0;
+  int64_t n_pairs = 0, n_pairs_small = 0, n_pairs_tiled = 0, n_block_cols = 0;
+  double flops_potrf = 0, flops_trsm = 0, flops_update = 0, bytes_solve = 0;
+  std::string error;
+};
+
+// Returns 0 on success, PARSY_CUDA_ERR_* otherwise (message in plan.error).
+int build_plan(Plan& plan, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
+               int supNo, const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+               const int* partition, const PlanOptions& opt);
+
+// Descendant pairs only (no schedule needed): used by tests against ereach_sn and by the prune-set entry point.
+void enumerate_pairs(std::vector<PairDesc>& out, int supNo, const int* blockSet, const size_t* Li_ptr, const int* lR,
+                     const int* col2Sup);
+
+}  // namespace parsy

@@ -1,0 +1,626 @@
+// libparsy_cuda: resident solver object + C ABI (include/parsy_cuda.h).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/parsy_cuda.h"
+#include "plan.h"
+#include "kernels.cuh"
+
+using namespace parsy;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+struct parsy_cuda_solver {
+  Plan plan;
+  int device = 0;
+  bool use_graph = true;
+  bool has_A = false, factored = false, has_values = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // device arrays
+  SupInfo* d_sup = nullptr;
+  int* d_lR = nullptr;
+  int* d_small_list = nullptr;
+  BlockTask* d_blocks = nullptr;
+  GemmTask* d_gemm = nullptr;
+  SmallTask* d_small_tasks = nullptr;
+  int* d_rel = nullptr;
+  int64_t* d_apos = nullptr;
+  double* d_vals = nullptr;
+  double* d_lv = nullptr;
+  double* d_linv = nullptr;
+  double* d_rhs = nullptr;
+  double* d_xs = nullptr;
+  int* d_info = nullptr;
+  int64_t device_bytes = 0;
+  cudaGraphExec_t g_levels = nullptr, g_last = nullptr, g_fwd = nullptr, g_bwd = nullptr;
+  int64_t launches_factor = 0, launches_fwd = 0, launches_bwd = 0;
+  double times[3] = {0, 0, 0};
+  bool timed = false;
+};
+
+template <class T> static int dev_alloc(parsy_cuda_solver* s, T** p, size_t count) {
+  *p = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CU(cudaMalloc((void**)p, bytes));
+  s->device_bytes += (int64_t)bytes;
+  return 0;
+}
+template <class T> static int dev_upload(parsy_cuda_solver* s, T** p, const T* h, size_t count) {
+  int rc = dev_alloc(s, p, count);
+  if (rc) return rc;
+  if (count) CU(cudaMemcpy(*p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int ensure_kernel_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg128::SMEM));
+  CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg64::SMEM));
+  CU(cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+  done = true;
+  return 0;
+}
+
+static inline int cdivi(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- launch sequences -----------------------------------------------------------------------------
+static int64_t enqueue_factor_steps(parsy_cuda_solver* s, int step_begin, int step_end) {
+  int64_t launches = 0;
+  const Plan& P = s->plan;
+  cudaStream_t st = s->stream;
+  for (int i = step_begin; i < step_end; ++i) {
+    const Step& S = P.steps[i];
+    if (S.small_sup.size()) {
+      k_factor_small<<<cdivi(S.small_sup.size(), 4), 128, 0, st>>>(s->d_small_list + S.small_sup.begin,
+                                                                   S.small_sup.size(), s->d_sup, s->d_lv, s->d_info);
+      ++launches;
+    }
+    if (S.blocks.size()) {
+      const size_t smem = (size_t)(NB_MAX + S.max_nb * POTRF_LD) * 8;
+      k_potrf_block<<<S.blocks.size(), POTRF_THREADS, smem, st>>>(s->d_blocks + S.blocks.begin, s->d_sup, s->d_lv,
+                                                                  s->d_linv, s->d_info);
+      ++launches;
+    }
+    if (S.trsm_tiles) {
+      k_gemm_tiles<Cfg128><<<S.trsm_tiles, Cfg128::THREADS, Cfg128::SMEM, st>>>(s->d_gemm + S.trsm.begin, S.trsm.size(),
+                                                                                s->d_lv, s->d_linv, s->d_rel);
+      ++launches;
+    }
+    if (S.upd128_tiles) {
+      k_gemm_tiles<Cfg128><<<S.upd128_tiles, Cfg128::THREADS, Cfg128::SMEM, st>>>(s->d_gemm + S.upd128.begin,
+                                                                                  S.upd128.size(), s->d_lv, s->d_linv,
+                                                                                  s->d_rel);
+      ++launches;
+    }
+    if (S.upd64_tiles) {
+      k_gemm_tiles<Cfg64><<<S.upd64_tiles, Cfg64::THREADS, Cfg64::SMEM, st>>>(s->d_gemm + S.upd64.begin, S.upd64.size(),
+                                                                              s->d_lv, s->d_linv, s->d_rel);
+      ++launches;
+    }
+    if (S.small_upd.size()) {
+      k_update_small<<<cdivi(S.small_upd.size(), 4), 128, 0, st>>>(s->d_small_tasks + S.small_upd.begin,
+                                                                   S.small_upd.size(), s->d_gemm, s->d_lv, s->d_rel);
+      ++launches;
+    }
+  }
+  return launches;
+}
+
+static int64_t enqueue_fwd(parsy_cuda_solver* s) {
+  int64_t launches = 0;
+  const Plan& P = s->plan;
+  cudaStream_t st = s->stream;
+  for (size_t i = 0; i < P.steps.size(); ++i) {
+    const Step& S = P.steps[i];
+    if (S.small_sup.size()) {
+      k_fwd_small<<<cdivi(S.small_sup.size(), 4), 128, 0, st>>>(s->d_small_list + S.small_sup.begin, S.small_sup.size(),
+                                                                s->d_sup, s->d_lR, s->d_lv, s->d_rhs, s->d_xs);
+      ++launches;
+    }
+    if (S.blocks.size()) {
+      k_fwd_block<<<S.solve_tiles, 256, 0, st>>>(s->d_blocks + S.blocks.begin, S.blocks.size(), s->d_sup, s->d_lR,
+                                                 s->d_lv, s->d_linv, s->d_rhs, s->d_xs);
+      ++launches;
+    }
+  }
+  cudaMemcpyAsync(s->d_rhs, s->d_xs, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToDevice, st);
+  return launches;
+}
+
+static int64_t enqueue_bwd(parsy_cuda_solver* s) {
+  int64_t launches = 0;
+  const Plan& P = s->plan;
+  cudaStream_t st = s->stream;
+  for (int i = (int)P.steps.size() - 1; i >= 0; --i) {
+    const Step& S = P.steps[i];
+    if (S.blocks.size()) {
+      k_bwd_block_gemv<<<S.solve_tiles, 256, 0, st>>>(s->d_blocks + S.blocks.begin, S.blocks.size(), s->d_sup, s->d_lR,
+                                                      s->d_lv, s->d_rhs);
+      k_bwd_block_diag<<<S.blocks.size(), 128, 0, st>>>(s->d_blocks + S.blocks.begin, s->d_sup, s->d_linv, s->d_rhs);
+      launches += 2;
+    }
+    if (S.small_sup.size()) {
+      k_bwd_small<<<cdivi(S.small_sup.size(), 4), 128, 0, st>>>(s->d_small_list + S.small_sup.begin, S.small_sup.size(),
+                                                                s->d_sup, s->d_lR, s->d_lv, s->d_rhs);
+      ++launches;
+    }
+  }
+  return launches;
+}
+
+template <class F> static int capture(parsy_cuda_solver* s, cudaGraphExec_t* out, int64_t* launches, F enqueue) {
+  cudaGraph_t g = nullptr;
+  CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+  *launches = enqueue();
+  CU(cudaStreamEndCapture(s->stream, &g));
+  CU(cudaGetLastError());
+  if (*launches > 0) CU(cudaGraphInstantiate(out, g, 0));
+  CU(cudaGraphDestroy(g));
+  return 0;
+}
+
+// ---- C ABI: misc ------------------------------------------------------------------------------------
+extern "C" const char* parsy_cuda_last_error(void) { return g_err.c_str(); }
+extern "C" int parsy_cuda_version(void) { return 100; }
+extern "C" int parsy_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ---- C ABI: handle ----------------------------------------------------------------------------------
+extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->g_levels) cudaGraphExecDestroy(s->g_levels);
+  if (s->g_last) cudaGraphExecDestroy(s->g_last);
+  if (s->g_fwd) cudaGraphExecDestroy(s->g_fwd);
+  if (s->g_bwd) cudaGraphExecDestroy(s->g_bwd);
+  void* ptrs[] = {s->d_sup, s->d_lR, s->d_small_list, s->d_blocks, s->d_gemm, s->d_small_tasks, s->d_rel, s->d_apos,
+                  s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, const int* r, const size_t* lC,
+                                 const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo, const int* aTree,
+                                 const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                                 const int* partition, const parsy_cuda_options* opt) {
+  if (!out) return fail(PARSY_CUDA_ERR_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  if (parsy_cuda_device_count() <= 0) return fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
+  parsy_cuda_options o;
+  memset(&o, 0, sizeof(o));
+  o.use_graph = 1;
+  if (opt) o = *opt;
+  if (o.device < 0 || o.device >= parsy_cuda_device_count()) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad device ordinal");
+  CU(cudaSetDevice(o.device));
+  int rc = ensure_kernel_attrs();
+  if (rc) return rc;
+
+  parsy_cuda_solver* s = new parsy_cuda_solver();
+  s->device = o.device;
+  s->use_graph = o.use_graph != 0;
+  PlanOptions po;
+  po.nb = o.block_cols;
+  po.ignore_hlevels = o.ignore_hlevels != 0;
+  // a missing schedule means "supernode order": one H-level with a single w-partition 0..supNo-1
+  std::vector<int> tl, tp, tq;
+  if (!levelPtr || !parPtr || !partition) {
+    tl = {0, 1}; tp = {0, supNo}; tq.resize(supNo);
+    for (int i = 0; i < supNo; ++i) tq[i] = i;
+    nLevels = 1; levelPtr = tl.data(); parPtr = tp.data(); partition = tq.data();
+  }
+  rc = build_plan(s->plan, n, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition, po);
+  if (rc) { g_err = s->plan.error; delete s; return rc; }
+  Plan& P = s->plan;
+#define TRY(x) do { rc = (x); if (rc) { parsy_cuda_destroy(s); return rc; } } while (0)
+#define TRYCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { parsy_cuda_destroy(s); return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  TRYCU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  for (auto& e : s->ev) TRYCU(cudaEventCreate(&e));
+  TRY(dev_upload(s, &s->d_sup, P.sup.data(), P.sup.size()));
+  TRY(dev_upload(s, &s->d_lR, lR, (size_t)P.ssize));
+  TRY(dev_upload(s, &s->d_small_list, P.small_list.data(), P.small_list.size()));
+  TRY(dev_upload(s, &s->d_blocks, P.block_tasks.data(), P.block_tasks.size()));
+  TRY(dev_upload(s, &s->d_gemm, P.gemm_tasks.data(), P.gemm_tasks.size()));
+  TRY(dev_upload(s, &s->d_small_tasks, P.small_tasks.data(), P.small_tasks.size()));
+  TRY(dev_alloc(s, &s->d_lv, (size_t)P.xsize));
+  TRY(dev_alloc(s, &s->d_linv, (size_t)P.n_slots * NB_MAX * NB_MAX));
+  TRY(dev_alloc(s, &s->d_rhs, (size_t)n));
+  TRY(dev_alloc(s, &s->d_xs, (size_t)n));
+  TRY(dev_alloc(s, &s->d_info, 1));
+  TRYCU(cudaMemset(s->d_info, 0, sizeof(int)));
+  TRYCU(cudaMemset(s->d_linv, 0, std::max<size_t>((size_t)P.n_slots * NB_MAX * NB_MAX, 1) * 8));
+  // relative indices (device-side binary searches, once per structure)
+  TRY(dev_alloc(s, &s->d_rel, (size_t)P.rel_entries));
+  if (P.rel_entries > 0) {
+    int64_t* d_prefix = nullptr; int *d_src = nullptr, *d_tgt = nullptr, *d_lb = nullptr;
+    const size_t np = P.pairs.size();
+    TRYCU(cudaMalloc(&d_prefix, (np + 1) * 8)); TRYCU(cudaMalloc(&d_src, np * 4)); TRYCU(cudaMalloc(&d_tgt, np * 4));
+    TRYCU(cudaMalloc(&d_lb, np * 4));
+    TRYCU(cudaMemcpy(d_prefix, P.rel_prefix.data(), (np + 1) * 8, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(d_src, P.rel_pair_src.data(), np * 4, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(d_tgt, P.rel_pair_tgt.data(), np * 4, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(d_lb, P.rel_pair_lb.data(), np * 4, cudaMemcpyHostToDevice));
+    const int grid = (int)std::min<int64_t>((P.rel_entries + 255) / 256, 148 * 32);
+    k_build_rel<<<grid, 256, 0, s->stream>>>(P.rel_entries, (int)np, d_prefix, d_src, d_tgt, d_lb, s->d_sup, s->d_lR,
+                                             s->d_rel);
+    TRYCU(cudaStreamSynchronize(s->stream));
+    cudaFree(d_prefix); cudaFree(d_src); cudaFree(d_tgt); cudaFree(d_lb);
+  }
+  // host copies of the per-pair bookkeeping are no longer needed
+  std::vector<int64_t>().swap(P.rel_prefix); std::vector<int32_t>().swap(P.rel_pair_src);
+  std::vector<int32_t>().swap(P.rel_pair_tgt); std::vector<int32_t>().swap(P.rel_pair_lb);
+  std::vector<PairDesc>().swap(P.pairs);
+  if (c && r) {
+    const int64_t nnz = c[n];
+    P.nnzA = nnz;
+    int *d_c = nullptr, *d_r = nullptr, *d_c2s = nullptr;
+    TRYCU(cudaMalloc(&d_c, (size_t)(n + 1) * 4)); TRYCU(cudaMalloc(&d_r, std::max<size_t>(nnz, 1) * 4));
+    TRYCU(cudaMalloc(&d_c2s, std::max<size_t>(n, 1) * 4));
+    TRYCU(cudaMemcpy(d_c, c, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(d_r, r, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    TRYCU(cudaMemcpy(d_c2s, col2Sup, (size_t)n * 4, cudaMemcpyHostToDevice));
+    TRY(dev_alloc(s, &s->d_apos, (size_t)nnz));
+    TRY(dev_alloc(s, &s->d_vals, (size_t)nnz));
+    if (nnz > 0) {
+      const int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 32);
+      k_build_apos<<<grid, 256, 0, s->stream>>>(nnz, n, d_c, d_r, d_c2s, s->d_sup, s->d_lR, s->d_apos);
+    }
+    TRYCU(cudaStreamSynchronize(s->stream));
+    cudaFree(d_c); cudaFree(d_r); cudaFree(d_c2s);
+    s->has_A = true;
+  }
+  // CUDA graphs: all H-levels but the last / the last H-level / forward sweep / backward sweep
+  const int nst = (int)P.steps.size();
+  const int last_begin = P.nlevels > 0 ? P.hlevel_first_step[P.nlevels - 1] : 0;
+  if (s->use_graph) {
+    int64_t l0 = 0, l1 = 0;
+    TRY(capture(s, &s->g_levels, &l0, [&] { return enqueue_factor_steps(s, 0, last_begin); }));
+    TRY(capture(s, &s->g_last, &l1, [&] { return enqueue_factor_steps(s, last_begin, nst); }));
+    s->launches_factor = l0 + l1 + (s->has_A ? 1 : 0);
+    TRY(capture(s, &s->g_fwd, &s->launches_fwd, [&] { return enqueue_fwd(s); }));
+    TRY(capture(s, &s->g_bwd, &s->launches_bwd, [&] { return enqueue_bwd(s); }));
+  }
+  TRYCU(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return PARSY_CUDA_OK;
+#undef TRY
+#undef TRYCU
+}
+
+extern "C" int parsy_cuda_set_values(parsy_cuda_solver* s, const double* values) {
+  if (!s || !values) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  if (!s->has_A) return fail(PARSY_CUDA_ERR_STATE, "handle was created without the pattern of A");
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpyAsync(s->d_vals, values, sizeof(double) * (size_t)s->plan.nnzA, cudaMemcpyHostToDevice, s->stream));
+  s->has_values = true;
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_factor(parsy_cuda_solver* s) {
+  if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  if (!s->has_A || !s->has_values) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
+  CU(cudaSetDevice(s->device));
+  const Plan& P = s->plan;
+  cudaStream_t st = s->stream;
+  CU(cudaEventRecord(s->ev[0], st));
+  CU(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
+  CU(cudaMemsetAsync(s->d_lv, 0, sizeof(double) * (size_t)P.xsize, st));   // the reference's caller zeroes valL
+  if (P.nnzA > 0) {
+    const int grid = (int)std::min<int64_t>((P.nnzA + 255) / 256, 148 * 16);
+    k_assemble<<<grid, 256, 0, st>>>(P.nnzA, s->d_apos, s->d_vals, s->d_lv);
+  }
+  CU(cudaEventRecord(s->ev[1], st));
+  const int nst = (int)P.steps.size();
+  const int last_begin = P.nlevels > 0 ? P.hlevel_first_step[P.nlevels - 1] : 0;
+  if (s->use_graph) {
+    if (s->g_levels) CU(cudaGraphLaunch(s->g_levels, st));
+    CU(cudaEventRecord(s->ev[2], st));
+    if (s->g_last) CU(cudaGraphLaunch(s->g_last, st));
+  } else {
+    int64_t l = enqueue_factor_steps(s, 0, last_begin);
+    CU(cudaEventRecord(s->ev[2], st));
+    l += enqueue_factor_steps(s, last_begin, nst);
+    s->launches_factor = l + 1;
+  }
+  CU(cudaEventRecord(s->ev[3], st));
+  CU(cudaGetLastError());
+  s->factored = true;
+  s->timed = true;
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_sync(parsy_cuda_solver* s) {
+  if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaGetLastError());
+  int info = 0;
+  CU(cudaMemcpy(&info, s->d_info, sizeof(int), cudaMemcpyDeviceToHost));
+  if (info != 0) return fail(PARSY_CUDA_ERR_NOT_SPD, "matrix is not positive definite at column " + std::to_string(info - 1));
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_get_factor(parsy_cuda_solver* s, double* lValues) {
+  if (!s || !lValues) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpyAsync(lValues, s->d_lv, sizeof(double) * (size_t)s->plan.xsize, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_set_factor(parsy_cuda_solver* s, const double* lValues) {
+  if (!s || !lValues) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(s->device));
+  const Plan& P = s->plan;
+  CU(cudaMemcpyAsync(s->d_lv, lValues, sizeof(double) * (size_t)P.xsize, cudaMemcpyHostToDevice, s->stream));
+  if (!P.block_tasks.empty()) {
+    static bool attr = false;
+    if (!attr) { CU(cudaFuncSetAttribute(k_invert_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM)); attr = true; }
+    k_invert_block<<<(int)P.block_tasks.size(), POTRF_THREADS, POTRF_SMEM, s->stream>>>(s->d_blocks, s->d_sup, s->d_lv,
+                                                                                      s->d_linv);
+  }
+  CU(cudaGetLastError());
+  s->factored = true;
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_set_rhs(parsy_cuda_solver* s, const double* b) {
+  if (!s || !b) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpyAsync(s->d_rhs, b, sizeof(double) * (size_t)s->plan.n, cudaMemcpyHostToDevice, s->stream));
+  return PARSY_CUDA_OK;
+}
+extern "C" int parsy_cuda_get_rhs(parsy_cuda_solver* s, double* x) {
+  if (!s || !x) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpyAsync(x, s->d_rhs, sizeof(double) * (size_t)s->plan.n, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_solve(parsy_cuda_solver* s, int which) {
+  if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  if (!s->factored) return fail(PARSY_CUDA_ERR_STATE, "solve before factor / set_factor");
+  if (!(which & (PARSY_CUDA_SOLVE_FWD | PARSY_CUDA_SOLVE_BWD))) return fail(PARSY_CUDA_ERR_BAD_ARG, "which must be FWD, BWD or both");
+  CU(cudaSetDevice(s->device));
+  if (which & PARSY_CUDA_SOLVE_FWD) {
+    if (s->use_graph) { if (s->g_fwd) CU(cudaGraphLaunch(s->g_fwd, s->stream)); }
+    else s->launches_fwd = enqueue_fwd(s);
+  }
+  if (which & PARSY_CUDA_SOLVE_BWD) {
+    if (s->use_graph) { if (s->g_bwd) CU(cudaGraphLaunch(s->g_bwd, s->stream)); }
+    else s->launches_bwd = enqueue_bwd(s);
+  }
+  CU(cudaGetLastError());
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_factor_times(parsy_cuda_solver* s, double* out3) {
+  if (!s || !out3) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  if (!s->timed) return fail(PARSY_CUDA_ERR_STATE, "no factorization has run");
+  CU(cudaSetDevice(s->device));
+  CU(cudaEventSynchronize(s->ev[3]));
+  float a = 0, b = 0, c = 0;
+  CU(cudaEventElapsedTime(&c, s->ev[0], s->ev[1]));
+  CU(cudaEventElapsedTime(&a, s->ev[1], s->ev[2]));
+  CU(cudaEventElapsedTime(&b, s->ev[2], s->ev[3]));
+  out3[0] = a * 1e-3; out3[1] = b * 1e-3; out3[2] = c * 1e-3;
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_get_stats(parsy_cuda_solver* s, parsy_cuda_stats* o) {
+  if (!s || !o) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  memset(o, 0, sizeof(*o));
+  const Plan& P = s->plan;
+  o->n = P.n; o->nsuper = P.nsuper; o->xsize = P.xsize; o->ssize = P.ssize; o->nnzA = P.nnzA;
+  o->n_pairs = P.n_pairs; o->n_pairs_small = P.n_pairs_small; o->n_pairs_tiled = P.n_pairs_tiled;
+  o->n_steps = (int64_t)P.steps.size(); o->n_block_cols = P.n_block_cols; o->rel_entries = P.rel_entries;
+  o->launches_factor = s->launches_factor; o->launches_fwd = s->launches_fwd; o->launches_bwd = s->launches_bwd;
+  o->flops_potrf = P.flops_potrf; o->flops_trsm = P.flops_trsm; o->flops_update = P.flops_update;
+  o->bytes_solve = P.bytes_solve; o->device_bytes = s->device_bytes;
+  return PARSY_CUDA_OK;
+}
+
+extern "C" double* parsy_cuda_device_factor(parsy_cuda_solver* s) { return s ? s->d_lv : nullptr; }
+extern "C" double* parsy_cuda_device_rhs(parsy_cuda_solver* s) { return s ? s->d_rhs : nullptr; }
+extern "C" double* parsy_cuda_device_values(parsy_cuda_solver* s) { return s ? s->d_vals : nullptr; }
+extern "C" void* parsy_cuda_stream(parsy_cuda_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+// ---- C ABI: drop-in entry points ------------------------------------------------------------------------
+extern "C" int parsy_cuda_cholesky_left_par_05(int n, int* c, int* r, double* values, size_t* lC, int* lR,
+                                               size_t* Li_ptr, double* lValues, int* blockSet, int supNo,
+                                               double* timing, int* aTree, int* cT, int* rT, int* col2Sup, int nLevels,
+                                               int* levelPtr, int* levelSet, int nPar, int* parPtr, int* partition,
+                                               int chunk, int threads, int super_max, int col_max, double* nodCost) {
+  (void)cT; (void)rT; (void)levelSet; (void)nPar; (void)chunk; (void)threads; (void)super_max; (void)col_max; (void)nodCost;
+  if (!c || !r || !values || !lValues) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  parsy_cuda_solver* s = nullptr;
+  int rc = parsy_cuda_create(&s, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr,
+                             partition, nullptr);
+  if (rc) return 0;
+  rc = parsy_cuda_set_values(s, values);
+  if (!rc) rc = parsy_cuda_factor(s);
+  if (!rc) rc = parsy_cuda_sync(s);
+  if (!rc) rc = parsy_cuda_get_factor(s, lValues);
+  if (!rc && timing) {
+    double t[3];
+    if (!parsy_cuda_factor_times(s, t)) { timing[0] = t[0] + t[2]; timing[1] = t[1]; }
+  }
+  const std::string keep = g_err;
+  parsy_cuda_destroy(s);
+  g_err = keep;
+  return rc == PARSY_CUDA_OK ? 1 : 0;
+}
+
+extern "C" int parsy_cuda_cholesky_left_sn_07(int n, int* c, int* r, double* values, size_t* lC, int* lR,
+                                              size_t* Li_ptr, double* lValues, int* blockSet, int supNo, double* timing,
+                                              int* prunePtr, int* pruneSet, int* map, double* contribs) {
+  (void)map; (void)contribs;
+  if (!c || !r || !values || !lValues || !blockSet) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  // col2sup is not an argument of the serial twin: rebuild it from blockSet
+  std::vector<int> c2s((size_t)std::max(n, 0));
+  for (int s = 0; s < supNo; ++s) for (int j = blockSet[s]; j < blockSet[s + 1]; ++j) c2s[j] = s;
+  if (prunePtr && pruneSet) {
+    // the prune set must list exactly the descendants the structure implies (PB_Cholesky.h:61)
+    std::vector<PairDesc> pairs;
+    enumerate_pairs(pairs, supNo, blockSet, Li_ptr, lR, c2s.data());
+    std::vector<int64_t> cnt(supNo, 0);
+    for (auto& q : pairs) cnt[q.tgt]++;
+    for (int s = 0; s < supNo; ++s)
+      if (prunePtr[s + 1] - prunePtr[s] != cnt[s]) { fail(PARSY_CUDA_ERR_BAD_ARG, "prune set disagrees with the factor structure"); return 0; }
+  }
+  return parsy_cuda_cholesky_left_par_05(n, c, r, values, lC, lR, Li_ptr, lValues, blockSet, supNo, timing, nullptr,
+                                         nullptr, nullptr, c2s.data(), 0, nullptr, nullptr, 0, nullptr, nullptr, 1, 1, 0,
+                                         0, nullptr);
+}
+
+static int dropin_solve(int n, size_t* Lp, int* Li, double* Lx, size_t* Li_ptr, int* col2sup, int* sup2col, int supNo,
+                        double* x, int nLevels, const int* levelPtr, const int* parPtr, const int* partition, int which) {
+  if (!Lp || !Li || !x) return 0;   // Triangular_BCSC.h:24,185
+  if (!Lx || !Li_ptr || !col2sup || !sup2col) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  parsy_cuda_solver* s = nullptr;
+  int rc = parsy_cuda_create(&s, n, nullptr, nullptr, Lp, Li, Li_ptr, sup2col, supNo, nullptr, col2sup, nLevels,
+                             levelPtr, parPtr, partition, nullptr);
+  if (rc) return 0;
+  rc = parsy_cuda_set_factor(s, Lx);
+  if (!rc) rc = parsy_cuda_set_rhs(s, x);
+  if (!rc) rc = parsy_cuda_solve(s, which);
+  if (!rc) rc = parsy_cuda_get_rhs(s, x);
+  const std::string keep = g_err;
+  parsy_cuda_destroy(s);
+  g_err = keep;
+  return rc == PARSY_CUDA_OK ? 1 : 0;
+}
+
+extern "C" int parsy_cuda_blockedLsolve(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr, int* col2sup,
+                                        int* sup2col, int supNo, double* x) {
+  (void)NNZ;
+  return dropin_solve(n, Lp, Li, Lx, Li_ptr, col2sup, sup2col, supNo, x, 0, nullptr, nullptr, nullptr, PARSY_CUDA_SOLVE_FWD);
+}
+extern "C" int parsy_cuda_blockedLtsolve(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr, int* col2sup,
+                                         int* sup2col, int supNo, double* x) {
+  (void)NNZ;
+  return dropin_solve(n, Lp, Li, Lx, Li_ptr, col2sup, sup2col, supNo, x, 0, nullptr, nullptr, nullptr, PARSY_CUDA_SOLVE_BWD);
+}
+extern "C" int parsy_cuda_leveledBlockedLsolve(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr,
+                                               int* col2sup, int* sup2col, int supNo, double* x, int levels,
+                                               int* levelPtr, int* levelSet, int chunk) {
+  (void)NNZ; (void)chunk;
+  if (!levelPtr || !levelSet) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL level set"); return 0; }
+  // an etree level set is an LBC schedule whose w-partitions hold one supernode each
+  std::vector<int> parPtr((size_t)supNo + 1);
+  for (int i = 0; i <= supNo; ++i) parPtr[i] = i;
+  return dropin_solve(n, Lp, Li, Lx, Li_ptr, col2sup, sup2col, supNo, x, levels, levelPtr, parPtr.data(), levelSet,
+                      PARSY_CUDA_SOLVE_FWD);
+}
+extern "C" int parsy_cuda_H2LeveledBlockedLsolve(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr,
+                                                 int* col2sup, int* sup2col, int supNo, double* x, int levels,
+                                                 int* levelPtr, int* levelSet, int parts, int* parPtr, int* partition,
+                                                 int chunk) {
+  (void)NNZ; (void)chunk; (void)levelSet; (void)parts;
+  if (!levelPtr || !parPtr || !partition) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL schedule"); return 0; }
+  return dropin_solve(n, Lp, Li, Lx, Li_ptr, col2sup, sup2col, supNo, x, levels, levelPtr, parPtr, partition,
+                      PARSY_CUDA_SOLVE_FWD);
+}
+extern "C" int parsy_cuda_H2LeveledBlockedLsolve_Peeled(int n, size_t* Lp, int* Li, double* Lx, int NNZ, size_t* Li_ptr,
+                                                        int* col2sup, int* sup2col, int supNo, double* x, int levels,
+                                                        int* levelPtr, int* levelSet, int parts, int* parPtr,
+                                                        int* partition, int chunk, int threads) {
+  (void)threads;
+  return parsy_cuda_H2LeveledBlockedLsolve(n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x, levels, levelPtr,
+                                           levelSet, parts, parPtr, partition, chunk);
+}
+
+// ---- CSC column solves ----------------------------------------------------------------------------------
+static int csc_solve(int n, int* Lp, int* Li, double* Lx, double* x, const std::vector<int>& lptr,
+                     const std::vector<int>& lset) {
+  if (parsy_cuda_device_count() <= 0) { fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)"); return 0; }
+  const size_t nnz = (size_t)Lp[n];
+  int *dp = nullptr, *di = nullptr, *dset = nullptr; double *dx = nullptr, *dv = nullptr;
+  auto cleanup = [&] { cudaFree(dp); cudaFree(di); cudaFree(dset); cudaFree(dx); cudaFree(dv); };
+#define C2(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return 0; } } while (0)
+  C2(cudaMalloc(&dp, (size_t)(n + 1) * 4)); C2(cudaMalloc(&di, std::max<size_t>(nnz, 1) * 4));
+  C2(cudaMalloc(&dset, std::max<size_t>(n, 1) * 4)); C2(cudaMalloc(&dx, std::max<size_t>(n, 1) * 8));
+  C2(cudaMalloc(&dv, std::max<size_t>(nnz, 1) * 8));
+  C2(cudaMemcpy(dp, Lp, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
+  C2(cudaMemcpy(di, Li, nnz * 4, cudaMemcpyHostToDevice));
+  C2(cudaMemcpy(dv, Lx, nnz * 8, cudaMemcpyHostToDevice));
+  C2(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+  C2(cudaMemcpy(dset, lset.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+  for (size_t l = 0; l + 1 < lptr.size(); ++l) {
+    const int cnt = lptr[l + 1] - lptr[l];
+    if (cnt > 0) k_csc_level<<<cdivi((int64_t)cnt * 32, 256), 256>>>(dset + lptr[l], cnt, dp, di, dv, dx);
+  }
+  C2(cudaGetLastError());
+  C2(cudaMemcpy(x, dx, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  cleanup();
+#undef C2
+  return 1;
+}
+
+// dependency levels of the columns of a lower-triangular CSC matrix (what the reference's level-set
+// inspector would produce); used when the caller passes no schedule (lsolve, Triangular_CSC.h:14)
+static void csc_levels(int n, const int* Lp, const int* Li, std::vector<int>& lptr, std::vector<int>& lset) {
+  std::vector<int> lev((size_t)n, 0);
+  int nl = 0;
+  for (int j = 0; j < n; ++j) {
+    for (int p = Lp[j] + 1; p < Lp[j + 1]; ++p) lev[Li[p]] = std::max(lev[Li[p]], lev[j] + 1);
+    nl = std::max(nl, lev[j] + 1);
+  }
+  lptr.assign((size_t)nl + 1, 0);
+  for (int j = 0; j < n; ++j) lptr[lev[j] + 1]++;
+  for (int l = 0; l < nl; ++l) lptr[l + 1] += lptr[l];
+  lset.resize((size_t)n);
+  std::vector<int> fill(lptr.begin(), lptr.end() - 1);
+  for (int j = 0; j < n; ++j) lset[fill[lev[j]]++] = j;
+}
+
+extern "C" int parsy_cuda_lsolve(int n, int* Lp, int* Li, double* Lx, double* x) {
+  if (!Lp || !Li || !x) return 0;   // Triangular_CSC.h:16
+  if (!Lx) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  std::vector<int> lptr, lset;
+  csc_levels(n, Lp, Li, lptr, lset);
+  return csc_solve(n, Lp, Li, Lx, x, lptr, lset);
+}
+extern "C" int parsy_cuda_lsolvePar(int n, int* Lp, int* Li, double* Lx, double* x, int levels, int* levelPtr,
+                                    int* levelSet, int chunk) {
+  (void)chunk;
+  if (!Lp || !Li || !x) return 0;
+  if (!Lx || !levelPtr || !levelSet) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  std::vector<int> lptr(levelPtr, levelPtr + levels + 1), lset(levelSet, levelSet + n);
+  return csc_solve(n, Lp, Li, Lx, x, lptr, lset);
+}
+extern "C" int parsy_cuda_lsolveParH2(int n, int* Lp, int* Li, double* Lx, double* x, int levels, int* levelPtr,
+                                      int* levelSet, int parts, int* parPtr, int* partition, int chunk) {
+  (void)chunk; (void)levelSet; (void)parts; (void)levels; (void)levelPtr; (void)parPtr; (void)partition;
+  // Columns inside one w-partition depend on each other (Triangular_CSC.h:84-96 runs them sequentially),
+  // so the device sweep orders by the column dependency levels, which refine any legal LBC schedule.
+  return parsy_cuda_lsolve(n, Lp, Li, Lx, x);
+}
+
+// ---- multi-GPU hooks -------------------------------------------------------------------
+extern "C" int parsy_cuda_owned_ranges(parsy_cuda_solver* s, int rank, int64_t* begin_end_pairs, int max_pairs) {
+  (void)s; (void)rank; (void)begin_end_pairs; (void)max_pairs;
+  return fail(PARSY_CUDA_ERR_STATE, "multi-GPU sharding not built in this round");
+}
+extern "C" int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase) {
+  (void)s; (void)phase;
+  return fail(PARSY_CUDA_ERR_STATE, "multi-GPU sharding not built in this round");
+}

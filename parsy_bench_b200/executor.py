@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's executor interface over libparsy_cuda (ctypes).
+
+The free functions keep the reference's names, argument order and return conventions
+(``cholesky_left_par_05`` cholesky/parallel_PB_Cholesky_05.h:27-39; ``blockedLsolve`` …
+triangularSolve/Triangular_BCSC.h:14,115,171,238; ``lsolve`` … triangularSolve/Triangular_CSC.h:14,50,76)
+and take numpy arrays where the reference takes raw pointers.  :class:`Solver` wraps the resident handle API.
+Nothing here computes on the CPU: every call goes through the C ABI into CUDA kernels.
+"""
+import ctypes
+from ctypes import c_int, c_void_p, c_double, c_size_t, POINTER, byref
+
+import numpy as np
+
+from ._lib import lib, last_error, Options, Stats
+
+SOLVE_FWD, SOLVE_BWD = 1, 2
+OK, ERR_NOT_SPD, ERR_BAD_ARG, ERR_BAD_SCHEDULE, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = range(7)
+
+
+class ParsyCudaError(RuntimeError):
+    def __init__(self, code, where):
+        super().__init__(f"{where}: error {code}: {last_error()}")
+        self.code = code
+
+
+def _arr(a, dtype, name, allow_none=False):
+    if a is None:
+        if allow_none:
+            return None, None
+        raise ValueError(f"{name} is None")
+    b = np.ascontiguousarray(a, dtype=dtype)
+    return b, b.ctypes.data_as(c_void_p)
+
+
+def _i32(a, name, allow_none=False):
+    return _arr(a, np.int32, name, allow_none)
+
+
+def _u64(a, name, allow_none=False):
+    return _arr(a, np.uint64, name, allow_none)
+
+
+def _f64_inplace(a, name):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable):
+        raise ValueError(f"{name} must be a writable contiguous float64 array (it is updated in place)")
+    return a.ctypes.data_as(c_void_p)
+
+
+def device_count() -> int:
+    return int(lib().parsy_cuda_device_count())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# drop-in free functions (host arrays in, host arrays out)
+# ---------------------------------------------------------------------------------------------------------
+def cholesky_left_par_05(n, c, r, values, lC, lR, Li_ptr, lValues, blockSet, supNo, timing, aTree, cT, rT, col2Sup,
+                         nLevels, levelPtr, levelSet, nPar, parPtr, partition, chunk=1, threads=1, super_max=0,
+                         col_max=0, nodCost=None) -> bool:
+    """LBC-scheduled supernodal Cholesky; fills ``lValues`` (xsize float64) in place. Returns True/False like the
+    reference (False iff a diagonal block is not positive definite, parallel_PB_Cholesky_05.h:206-207)."""
+    L = lib()
+    keep = []
+
+    def P(x):
+        keep.append(x[0])
+        return x[1]
+
+    f = L.parsy_cuda_cholesky_left_par_05
+    f.restype = c_int
+    f.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                  c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    tptr = None if timing is None else _f64_inplace(timing, "timing")
+    rc = f(int(n), P(_i32(c, "c")), P(_i32(r, "r")), P(_arr(values, np.float64, "values")), P(_u64(lC, "lC")),
+           P(_i32(lR, "lR")), P(_u64(Li_ptr, "Li_ptr")), _f64_inplace(lValues, "lValues"), P(_i32(blockSet, "blockSet")),
+           int(supNo), tptr, P(_i32(aTree, "aTree", True)), P(_i32(cT, "cT", True)), P(_i32(rT, "rT", True)),
+           P(_i32(col2Sup, "col2Sup")), int(nLevels), P(_i32(levelPtr, "levelPtr")), None, int(nPar),
+           P(_i32(parPtr, "parPtr")), P(_i32(partition, "partition")), int(chunk), int(threads), int(super_max),
+           int(col_max), None)
+    return bool(rc)
+
+
+def cholesky_left_sn_07(n, c, r, values, lC, lR, Li_ptr, lValues, blockSet, supNo, timing, prunePtr, pruneSet,
+                        map=None, contribs=None) -> bool:  # noqa: A002 - reference argument name
+    """Serial twin driven by a prune set (cholesky/PB_Cholesky.h:16-19)."""
+    L = lib()
+    keep = []
+
+    def P(x):
+        keep.append(x[0])
+        return x[1]
+
+    f = L.parsy_cuda_cholesky_left_sn_07
+    f.restype = c_int
+    f.argtypes = [c_int] + [c_void_p] * 8 + [c_int] + [c_void_p] * 5
+    tptr = None if timing is None else _f64_inplace(timing, "timing")
+    rc = f(int(n), P(_i32(c, "c")), P(_i32(r, "r")), P(_arr(values, np.float64, "values")), P(_u64(lC, "lC")),
+           P(_i32(lR, "lR")), P(_u64(Li_ptr, "Li_ptr")), _f64_inplace(lValues, "lValues"), P(_i32(blockSet, "blockSet")),
+           int(supNo), tptr, P(_i32(prunePtr, "prunePtr", True)), P(_i32(pruneSet, "pruneSet", True)), None, None)
+    return bool(rc)
+
+
+def _solve_common(fname, n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x, extra_types=(), extra=()):
+    L = lib()
+    if Lp is None or Li is None or x is None:
+        return 0  # Triangular_BCSC.h:24
+    keep = []
+
+    def P(v):
+        keep.append(v[0])
+        return v[1]
+
+    f = getattr(L, fname)
+    f.restype = c_int
+    f.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p] + \
+        list(extra_types)
+    args = [int(n), P(_u64(Lp, "Lp")), P(_i32(Li, "Li")), P(_arr(Lx, np.float64, "Lx")), int(NNZ) & 0x7FFFFFFF,
+            P(_u64(Li_ptr, "Li_ptr")), P(_i32(col2sup, "col2sup")), P(_i32(sup2col, "sup2col")), int(supNo),
+            _f64_inplace(x, "x")]
+    for v in extra:
+        if isinstance(v, tuple):
+            args.append(P(v))
+        else:
+            args.append(v)
+    return int(f(*args))
+
+
+def blockedLsolve(n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x) -> int:
+    """Supernodal forward solve L x = b in place on ``x`` (Triangular_BCSC.h:14)."""
+    return _solve_common("parsy_cuda_blockedLsolve", n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x)
+
+
+def blockedLtsolve(n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x) -> int:
+    """NEW: supernodal backward solve L' x = b in place (the reference has none)."""
+    return _solve_common("parsy_cuda_blockedLtsolve", n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x)
+
+
+def leveledBlockedLsolve(n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x, levels, levelPtr, levelSet,
+                         chunk=1) -> int:
+    """Level-set supernodal forward solve (Triangular_BCSC.h:115)."""
+    return _solve_common("parsy_cuda_leveledBlockedLsolve", n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x,
+                         [c_int, c_void_p, c_void_p, c_int],
+                         [int(levels), _i32(levelPtr, "levelPtr"), _i32(levelSet, "levelSet"), int(chunk)])
+
+
+def H2LeveledBlockedLsolve(n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x, levels, levelPtr, levelSet, parts,
+                           parPtr, partition, chunk=1) -> int:
+    """LBC-scheduled supernodal forward solve (Triangular_BCSC.h:171)."""
+    return _solve_common("parsy_cuda_H2LeveledBlockedLsolve", n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x,
+                         [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int],
+                         [int(levels), _i32(levelPtr, "levelPtr"), None, int(parts), _i32(parPtr, "parPtr"),
+                          _i32(partition, "partition"), int(chunk)])
+
+
+def H2LeveledBlockedLsolve_Peeled(n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col, supNo, x, levels, levelPtr, levelSet,
+                                  parts, parPtr, partition, chunk=1, threads=1) -> int:
+    """LBC-scheduled forward solve with the last level peeled (Triangular_BCSC.h:238)."""
+    return _solve_common("parsy_cuda_H2LeveledBlockedLsolve_Peeled", n, Lp, Li, Lx, NNZ, Li_ptr, col2sup, sup2col,
+                         supNo, x, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int],
+                         [int(levels), _i32(levelPtr, "levelPtr"), None, int(parts), _i32(parPtr, "parPtr"),
+                          _i32(partition, "partition"), int(chunk), int(threads)])
+
+
+def _csc_common(fname, n, Lp, Li, Lx, x, extra_types=(), extra=()):
+    L = lib()
+    if Lp is None or Li is None or x is None:
+        return 0  # Triangular_CSC.h:16
+    keep = []
+
+    def P(v):
+        keep.append(v[0])
+        return v[1]
+
+    f = getattr(L, fname)
+    f.restype = c_int
+    f.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + list(extra_types)
+    args = [int(n), P(_i32(Lp, "Lp")), P(_i32(Li, "Li")), P(_arr(Lx, np.float64, "Lx")), _f64_inplace(x, "x")]
+    for v in extra:
+        args.append(P(v) if isinstance(v, tuple) else v)
+    return int(f(*args))
+
+
+def lsolve(n, Lp, Li, Lx, x) -> int:
+    """Column forward solve on a CSC lower-triangular matrix, diagonal first (Triangular_CSC.h:14)."""
+    return _csc_common("parsy_cuda_lsolve", n, Lp, Li, Lx, x)
+
+
+def lsolvePar(n, Lp, Li, Lx, x, levels, levelPtr, levelSet, chunk=1) -> int:
+    """Level-set column forward solve (Triangular_CSC.h:50)."""
+    return _csc_common("parsy_cuda_lsolvePar", n, Lp, Li, Lx, x, [c_int, c_void_p, c_void_p, c_int],
+                       [int(levels), _i32(levelPtr, "levelPtr"), _i32(levelSet, "levelSet"), int(chunk)])
+
+
+def lsolveParH2(n, Lp, Li, Lx, x, levels, levelPtr, levelSet, parts, parPtr, partition, chunk=1) -> int:
+    """LBC column forward solve (Triangular_CSC.h:76)."""
+    return _csc_common("parsy_cuda_lsolveParH2", n, Lp, Li, Lx, x,
+                       [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int],
+                       [int(levels), _i32(levelPtr, "levelPtr", True), None, int(parts), _i32(parPtr, "parPtr", True),
+                        _i32(partition, "partition", True), int(chunk)])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# resident handle
+# ---------------------------------------------------------------------------------------------------------
+class Solver:
+    """Device-resident symbolic state + factor. Arrays are the inspector's outputs."""
+
+    def __init__(self, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
+                 device=0, block_cols=0, use_graph=True, ignore_hlevels=False):
+        L = lib()
+        self._L = L
+        self._h = c_void_p()
+        opt = Options()
+        opt.device, opt.block_cols, opt.use_graph, opt.ignore_hlevels = int(device), int(block_cols), int(use_graph), \
+            int(ignore_hlevels)
+        f = L.parsy_cuda_create
+        f.restype = c_int
+        f.argtypes = [POINTER(c_void_p), c_int] + [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + \
+            [c_void_p] * 3 + [POINTER(Options)]
+        keep = [_i32(c, "c", True), _i32(r, "r", True), _u64(lC, "lC"), _i32(lR, "lR"), _u64(Li_ptr, "Li_ptr"),
+                _i32(blockSet, "blockSet"), _i32(aTree, "aTree", True), _i32(col2Sup, "col2Sup"),
+                _i32(levelPtr, "levelPtr", True), _i32(parPtr, "parPtr", True), _i32(partition, "partition", True)]
+        p = [k[1] for k in keep]
+        rc = f(byref(self._h), int(n), p[0], p[1], p[2], p[3], p[4], p[5], int(supNo), p[6], p[7], int(nLevels), p[8],
+               p[9], p[10], byref(opt))
+        if rc != OK:
+            self._h = c_void_p()
+            raise ParsyCudaError(rc, "parsy_cuda_create")
+        self.n = int(n)
+        st = self.stats()
+        self.xsize, self.nnzA = st["xsize"], st["nnzA"]
+
+    def _call(self, name, *args, ok=(OK,)):
+        f = getattr(self._L, name)
+        f.restype = c_int
+        f.argtypes = [c_void_p] + [c_void_p if not isinstance(a, int) else c_int for a in args]
+        rc = f(self._h, *args)
+        if rc not in ok:
+            raise ParsyCudaError(rc, name)
+        return rc
+
+    def set_values(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if v.size != self.nnzA:
+            raise ValueError("values has the wrong length")
+        self._call("parsy_cuda_set_values", v.ctypes.data_as(c_void_p))
+        self._call("parsy_cuda_sync", ok=(OK, ERR_NOT_SPD))  # host buffer may be released after return
+
+    def factor(self):
+        self._call("parsy_cuda_factor")
+
+    def sync(self) -> bool:
+        """Waits for the device; returns False if the last factorization met a non-positive pivot."""
+        return self._call("parsy_cuda_sync", ok=(OK, ERR_NOT_SPD)) == OK
+
+    def get_factor(self, out=None):
+        if out is None:
+            out = np.empty(self.xsize, np.float64)
+        self._call("parsy_cuda_get_factor", _f64_inplace(out, "out"))
+        return out
+
+    def set_factor(self, lValues):
+        v = np.ascontiguousarray(lValues, dtype=np.float64)
+        if v.size != self.xsize:
+            raise ValueError("lValues has the wrong length")
+        self._call("parsy_cuda_set_factor", v.ctypes.data_as(c_void_p))
+        self._call("parsy_cuda_sync", ok=(OK, ERR_NOT_SPD))
+
+    def set_rhs(self, b):
+        v = np.ascontiguousarray(b, dtype=np.float64)
+        if v.size != self.n:
+            raise ValueError("rhs has the wrong length")
+        self._call("parsy_cuda_set_rhs", v.ctypes.data_as(c_void_p))
+        self._call("parsy_cuda_sync", ok=(OK, ERR_NOT_SPD))
+
+    def get_rhs(self, out=None):
+        if out is None:
+            out = np.empty(self.n, np.float64)
+        self._call("parsy_cuda_get_rhs", _f64_inplace(out, "out"))
+        return out
+
+    def solve(self, which=SOLVE_FWD | SOLVE_BWD):
+        self._call("parsy_cuda_solve", int(which))
+
+    def factor_times(self):
+        t = np.zeros(3, np.float64)
+        self._call("parsy_cuda_factor_times", t.ctypes.data_as(c_void_p))
+        return {"levels": t[0], "last_level": t[1], "assemble": t[2]}
+
+    def stats(self):
+        st = Stats()
+        f = self._L.parsy_cuda_get_stats
+        f.restype = c_int
+        f.argtypes = [c_void_p, POINTER(Stats)]
+        rc = f(self._h, byref(st))
+        if rc != OK:
+            raise ParsyCudaError(rc, "parsy_cuda_get_stats")
+        return st.as_dict()
+
+    def device_pointers(self):
+        L = self._L
+        out = {}
+        for k in ("factor", "rhs", "values", ):
+            f = getattr(L, f"parsy_cuda_device_{k}")
+            f.restype = c_void_p
+            f.argtypes = [c_void_p]
+            out[k] = f(self._h)
+        f = L.parsy_cuda_stream
+        f.restype = c_void_p
+        f.argtypes = [c_void_p]
+        out["stream"] = f(self._h)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            f = self._L.parsy_cuda_destroy
+            f.restype = None
+            f.argtypes = [c_void_p]
+            f(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
