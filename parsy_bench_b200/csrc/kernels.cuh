@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(C::THREADS) k_gemm_tiles(const GemmTask* __res
   const int wm0 = (warp % C::WARPS_M) * C::WM, wn0 = (warp / C::WARPS_M) * C::WN;
   const int fr = lane >> 2, fk = lane & 3;
   // skip warps whose whole sub-tile is out of range or strictly above the diagonal
+  const bool binv = T.flags & GF_B_LINV;
   bool warp_active = (wm0 < mrows) && (wn0 < nrows);
   if ((T.flags & GF_LOWER) && (m0 + wm0 + C::WM - 1 < n0 + wn0)) warp_active = false;
 
@@ -135,7 +136,10 @@ __global__ void __launch_bounds__(C::THREADS) k_gemm_tiles(const GemmTask* __res
     const int nx = kc + C::STAGES - 1;
     if (nx < nchunks) load_chunk(nx, nx % C::STAGES);
     cp_async_commit();
-    if (warp_active) {
+    // TRSM through the inverse: B(j,k) = inv(L)(j,k) vanishes for k > j, so a warp whose columns all lie
+    // below this k-chunk has nothing to add
+    const bool chunk_active = warp_active && !(binv && (wn0 + C::WN <= kc * C::KC));
+    if (chunk_active) {
       const double* As = smem + (kc % C::STAGES) * C::STAGE_DOUBLES;
       const double* Bs = As + C::KC * C::LDA;
 #pragma unroll
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(C::THREADS) k_gemm_tiles(const GemmTask* __res
   if (!warp_active) return;
 
   // epilogue: scatter through the relative indices
-  const bool lower = T.flags & GF_LOWER, atomic = T.flags & GF_ATOMIC, overwrite = T.flags & GF_OVERWRITE;
+  const bool lower = T.flags & GF_LOWER, overwrite = T.flags & GF_OVERWRITE;
   double* __restrict__ Cb = lv + T.c_off;
   const int64_t ldc = T.ldc;
 #pragma unroll
@@ -175,8 +179,7 @@ __global__ void __launch_bounds__(C::THREADS) k_gemm_tiles(const GemmTask* __res
         double* dst = Cb + coff + srel[i];
         const double v = acc[im][in][e];
         if (overwrite) *dst = v;
-        else if (atomic) atomicAdd(dst, -v);
-        else *dst -= v;
+        else atomicAdd(dst, -v);   // red.global.add.f64: fire-and-forget, also for exclusive targets
       }
     }
   }
@@ -273,28 +276,223 @@ __global__ void __launch_bounds__(128) k_factor_small(const int* __restrict__ li
 }
 
 // ------------------------------------------------------------------------------------------------
-// block columns: POTRF of the diagonal block + inverse of the factor (one CTA each)
-// shared layout: S(i,c) at c*LD+i, LD = 129; the strict upper triangle holds inv(L) transposed.
+// block columns: POTRF of the <=128-wide diagonal block + inverse of its factor, one CTA each.
+//
+// Shared memory: S(i,c) at c*PLD+i (PLD = 132, conflict-free DMMA fragment loads). The block is padded with
+// an identity to a multiple of 16 (nbp).  Cholesky is right-looking over 16-column macro panels, each made of
+// two 8-column micro panels that every row-thread factors redundantly in registers (no intra-panel
+// synchronisation: 8 rsqrt chains per micro panel), followed by a DMMA rank-16 trailing update.
+// The inverse X = inv(L) is a block-row forward substitution with 16x16 blocks on DMMA:
+//   X(I,J) = -D_I * sum_{K=J..I-1} L(I,K) X(K,J),  D_I = inv(L_II)
+// with X(I,J), J < I, parked in the (unused) upper block (J,I) of S and the D_I in a side buffer.
 // ------------------------------------------------------------------------------------------------
-constexpr int POTRF_LD = NB_MAX + 1;
+constexpr int PLD = 132;
+constexpr int XDLD = 20;
 constexpr int POTRF_THREADS = 256;
-constexpr size_t POTRF_SMEM = (size_t)NB_MAX * POTRF_LD * 8 + NB_MAX * 8;
+constexpr int POTRF_S = NB_MAX * PLD;                 // doubles
+constexpr int POTRF_XD = (NB_MAX / 16) * 16 * XDLD;   // diagonal inverse blocks
+constexpr int POTRF_T = NB_MAX * XDLD;                // 16 x 128 temporary, column-major with ld XDLD
+constexpr size_t POTRF_SMEM = (size_t)(POTRF_S + NB_MAX + POTRF_XD + POTRF_T) * 8;
+constexpr int POTRF_LD = PLD;
 
-// inverse X = inv(L) of the nb x nb lower factor held in S: thread c owns column c; X(i,c), i > c, is kept at
-// the transposed slot S(c,i) (strict upper triangle), the diagonal 1/L(c,c) in rd.
-__device__ __forceinline__ void invert_lower_in_smem(double* S, const double* rd, int nb, int tid) {
-  constexpr int LD = POTRF_LD;
-  if (tid < nb) {
-    const int c = tid;
-    for (int i = 0; i < nb; ++i) {
-      // all threads walk the same (i,k): L(i,k) is a broadcast read
-      double acc = (i == c) ? 1.0 : 0.0;
-      for (int k = 0; k < i; ++k) {
-        const double xk = (k > c) ? S[k * LD + c] : ((k == c) ? rd[c] : 0.0);
-        acc = fma(-S[k * LD + i], xk, acc);
-      }
-      if (i > c) S[i * LD + c] = acc * rd[i];
+// micro panel: columns [p0, p0+8), thread t owns row p0+t
+__device__ __forceinline__ void potrf_micro8(double* S, double* rd, int p0, int nbp, int tid, int* info, int colbase,
+                                             int nb) {
+  const int i = p0 + tid;
+  const bool active = i < nbp;
+  double d[8][8], x[8], rr[8];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int m = 0; m <= k; ++m) d[k][m] = S[(p0 + m) * PLD + p0 + k];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] = S[(p0 + c) * PLD + i];
+  }
+  __syncthreads();   // every thread has its copy of the diagonal block before its rows are overwritten
+  if (!active) return;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const double piv = d[c][c];
+    if (tid == 0 && !(piv > 0.0) && p0 + c < nb) atomicCAS(info, 0, colbase + p0 + c + 1);
+    const double r = rsqrt(piv);
+    rr[c] = r;
+    d[c][c] = piv * r;
+#pragma unroll
+    for (int k = c + 1; k < 8; ++k) d[k][c] *= r;
+#pragma unroll
+    for (int k = c + 1; k < 8; ++k)
+#pragma unroll
+      for (int m = c + 1; m <= k; ++m) d[k][m] = fma(-d[k][c], d[m][c], d[k][m]);
+  }
+  // own row against the factored diagonal block: x * L_dd' = a
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    double v = x[c];
+#pragma unroll
+    for (int m = 0; m < c; ++m) v = fma(-x[m], d[c][m], v);
+    x[c] = v * rr[c];
+  }
+  // rows inside the diagonal block reproduce L_dd itself (x[c] == d[t][c] for c <= t)
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (i > p0 + c) S[(p0 + c) * PLD + i] = x[c];
+    else if (i == p0 + c) S[(p0 + c) * PLD + i] = d[c][c];
+  if (tid == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) rd[p0 + c] = rr[c];
+  }
+}
+
+// rank-8 update of columns [p0+8, p0+16) by the micro panel [p0, p0+8); thread t owns row p0+8+t
+__device__ __forceinline__ void potrf_mid8(double* S, int p0, int nbp, int tid) {
+  const int i = p0 + 8 + tid;
+  if (i >= nbp) return;
+  double x[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) x[c] = S[(p0 + c) * PLD + i];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (i >= p0 + 8 + k) {
+      double v = S[(p0 + 8 + k) * PLD + i];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v = fma(-x[c], S[(p0 + c) * PLD + p0 + 8 + k], v);
+      S[(p0 + 8 + k) * PLD + i] = v;
     }
+  }
+}
+
+// DMMA trailing update: S(i,k) -= sum_{c<16} S(i,p0+c) S(k,p0+c) for i >= k >= q0 = p0+16, 16x16 tiles per warp
+__device__ __forceinline__ void potrf_trailing16(double* S, int p0, int nbp, int warp, int lane) {
+  const int q0 = p0 + 16;
+  const int T16 = (nbp - q0) >> 4;
+  const int ntiles = T16 * (T16 + 1) / 2;
+  const int fr = lane >> 2, fk = lane & 3;
+  for (int tile = warp; tile < ntiles; tile += POTRF_THREADS / 32) {
+    int ti = 0, rem = tile;
+    while (rem > ti) { rem -= ti + 1; ++ti; }
+    const int tj = rem;
+    const int r0 = q0 + ti * 16, c0 = q0 + tj * 16;
+    const bool diag = ti == tj;
+    double c[2][2][2];
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+      for (int fj = 0; fj < 2; ++fj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) c[fi][fj][e] = S[(c0 + fj * 8 + fk * 2 + e) * PLD + r0 + fi * 8 + fr];
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      double a[2], b[2];
+#pragma unroll
+      for (int fi = 0; fi < 2; ++fi) a[fi] = -S[(p0 + k4 + fk) * PLD + r0 + fi * 8 + fr];
+#pragma unroll
+      for (int fj = 0; fj < 2; ++fj) b[fj] = S[(p0 + k4 + fk) * PLD + c0 + fj * 8 + fr];
+#pragma unroll
+      for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+        for (int fj = 0; fj < 2; ++fj) dmma884(c[fi][fj][0], c[fi][fj][1], a[fi], b[fj]);
+    }
+#pragma unroll
+    for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+      for (int fj = 0; fj < 2; ++fj) {
+        if (diag && fi == 0 && fj == 1) continue;   // strictly above the diagonal
+#pragma unroll
+        for (int e = 0; e < 2; ++e) S[(c0 + fj * 8 + fk * 2 + e) * PLD + r0 + fi * 8 + fr] = c[fi][fj][e];
+      }
+  }
+}
+
+// Cholesky of the padded nbp x nbp block held in S (lower part); fills rd = 1/diag(L)
+__device__ __forceinline__ void potrf_in_smem(double* S, double* rd, int nb, int nbp, int tid, int* info, int colbase) {
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int p0 = 0; p0 < nbp; p0 += 16) {
+    potrf_micro8(S, rd, p0, nbp, tid, info, colbase, nb);
+    __syncthreads();
+    potrf_mid8(S, p0, nbp, tid);
+    __syncthreads();
+    potrf_micro8(S, rd, p0 + 8, nbp, tid, info, colbase, nb);
+    __syncthreads();
+    if (p0 + 16 < nbp) {
+      potrf_trailing16(S, p0, nbp, warp, lane);
+      __syncthreads();
+    }
+  }
+}
+
+// X = inv(L): leaves X(I,J), J < I, in the upper block (J,I) of S and the diagonal blocks D_I in XD
+__device__ __forceinline__ void invert_in_smem(double* S, const double* rd, double* XD, double* Tt, int nbp, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fk = lane & 3;
+  const int nI = nbp >> 4;
+  // D_I = inv(L_II): 16 threads per block, thread c solves L_II x = e_c
+  if (tid < nI * 16) {
+    const int I = tid >> 4, c = tid & 15, o = I * 16;
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      double v = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) v = fma(-S[(o + k) * PLD + o + i], x[k], v);
+      x[i] = v * rd[o + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) XD[I * 16 * XDLD + c * XDLD + i] = x[i];   // zero above the diagonal (i < c)
+  }
+  __syncthreads();
+  for (int I = 1; I < nI; ++I) {
+    const int ntile = 4 * I;   // 2 row fragments x 2I column fragments of the 16 x 16I block row
+    // phase A: T = sum_{K<I} L(I,K) X(K, 0..16I)
+    for (int tt = warp; tt < ntile; tt += POTRF_THREADS / 32) {
+      const int fi = tt & 1, fj = tt >> 1, J = fj >> 1, cj = (fj & 1) * 8;
+      double c0 = 0.0, c1 = 0.0;
+      for (int K = J; K < I; ++K) {
+#pragma unroll
+        for (int k4 = 0; k4 < 16; k4 += 4) {
+          const double a = S[(K * 16 + k4 + fk) * PLD + I * 16 + fi * 8 + fr];
+          const double b = (K == J) ? XD[J * 16 * XDLD + (cj + fr) * XDLD + k4 + fk]
+                                    : S[(K * 16 + cj + fr) * PLD + J * 16 + k4 + fk];
+          dmma884(c0, c1, a, b);
+        }
+      }
+      Tt[(fj * 8 + fk * 2) * XDLD + fi * 8 + fr] = c0;
+      Tt[(fj * 8 + fk * 2 + 1) * XDLD + fi * 8 + fr] = c1;
+    }
+    __syncthreads();
+    // phase B: X(I, 0..16I) = -D_I T
+    for (int tt = warp; tt < ntile; tt += POTRF_THREADS / 32) {
+      const int fi = tt & 1, fj = tt >> 1, J = fj >> 1, cj = (fj & 1) * 8;
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int k4 = 0; k4 < 16; k4 += 4) {
+        const double a = -XD[I * 16 * XDLD + (k4 + fk) * XDLD + fi * 8 + fr];
+        const double b = Tt[(fj * 8 + fr) * XDLD + k4 + fk];
+        dmma884(c0, c1, a, b);
+      }
+      S[(I * 16 + cj + fk * 2) * PLD + J * 16 + fi * 8 + fr] = c0;
+      S[(I * 16 + cj + fk * 2 + 1) * PLD + J * 16 + fi * 8 + fr] = c1;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void store_inverse(const double* S, const double* XD, double* __restrict__ X, int nb,
+                                              int tid) {
+  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
+    const int c = e / nb, i = e - c * nb;
+    const int I = i >> 4, J = c >> 4;
+    double v = 0.0;
+    if (I == J) v = XD[I * 16 * XDLD + (c & 15) * XDLD + (i & 15)];
+    else if (I > J) v = S[(I * 16 + (c & 15)) * PLD + J * 16 + (i & 15)];
+    X[c * NB_MAX + i] = v;
+  }
+}
+
+__device__ __forceinline__ void load_padded_block(double* S, const double* __restrict__ P, int64_t r, int nb, int nbp,
+                                                  int tid) {
+  for (int e = tid; e < nbp * nbp; e += POTRF_THREADS) {
+    const int c = e / nbp, i = e - c * nbp;
+    if (i >= c) S[c * PLD + i] = (i < nb && c < nb) ? P[(int64_t)c * r + i] : ((i == c) ? 1.0 : 0.0);
   }
 }
 
@@ -303,49 +501,24 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_block(const BlockTask* 
                                                                 double* __restrict__ lv, double* __restrict__ linv,
                                                                 int* __restrict__ info) {
   extern __shared__ __align__(16) double smem[];
-  double* rd = smem;            // reciprocal diagonal
-  double* S = smem + NB_MAX;
+  double* S = smem;
+  double* rd = S + POTRF_S;
+  double* XD = rd + NB_MAX;
+  double* Tt = XD + POTRF_XD;
   const BlockTask B = bt[blockIdx.x];
   const SupInfo I = sup[B.sup];
-  const int nb = B.nb, r = I.r, tid = threadIdx.x;
+  const int nb = B.nb, nbp = (nb + 15) & ~15, tid = threadIdx.x;
+  const int64_t r = I.r;
   double* __restrict__ P = lv + I.valptr + (int64_t)B.j0 * r + B.j0;   // (j0, j0) of the panel
-  constexpr int LD = POTRF_LD;
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int c = e / nb, i = e % nb;
-    if (i >= c) S[c * LD + i] = P[(int64_t)c * r + i];
-  }
+  load_padded_block(S, P, r, nb, nbp, tid);
   __syncthreads();
-  // right-looking Cholesky, one column at a time (MyBLAS.h:10-25 semantics)
-  for (int c = 0; c < nb; ++c) {
-    const double piv = S[c * LD + c];
-    if (tid == 0 && !(piv > 0.0)) atomicCAS(info, 0, I.col0 + B.j0 + c + 1);
-    const double l = sqrt(piv);
-    __syncthreads();
-    for (int i = c + tid; i < nb; i += POTRF_THREADS) S[c * LD + i] = (i == c) ? l : S[c * LD + i] / l;
-    if (tid == 0) rd[c] = 1.0 / l;
-    __syncthreads();
-    // trailing rank-1 update of the lower triangle: columns k > c, rows i >= k
-    const int rem = nb - c - 1;
-    for (int e = tid; e < rem * rem; e += POTRF_THREADS) {
-      const int kk = e / rem, ii = e % rem;
-      if (ii >= kk) {
-        const int k = c + 1 + kk, i = c + 1 + ii;
-        S[k * LD + i] = fma(-S[c * LD + i], S[c * LD + k], S[k * LD + i]);
-      }
-    }
-    __syncthreads();
-  }
+  potrf_in_smem(S, rd, nb, nbp, tid, info, I.col0 + B.j0);
   for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int c = e / nb, i = e % nb;
-    if (i >= c) P[(int64_t)c * r + i] = S[c * LD + i];
+    const int c = e / nb, i = e - c * nb;
+    if (i >= c) P[(int64_t)c * r + i] = S[c * PLD + i];
   }
-  invert_lower_in_smem(S, rd, nb, tid);
-  __syncthreads();
-  double* __restrict__ X = linv + (int64_t)B.slot * NB_MAX * NB_MAX;
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int c = e / nb, i = e % nb;
-    X[c * NB_MAX + i] = (i > c) ? S[i * LD + c] : ((i == c) ? rd[c] : 0.0);
-  }
+  invert_in_smem(S, rd, XD, Tt, nbp, tid);
+  store_inverse(S, XD, linv + (int64_t)B.slot * NB_MAX * NB_MAX, nb, tid);
 }
 
 // inverse diagonal blocks for a factor that was produced elsewhere (parsy_cuda_set_factor, drop-in solves)
@@ -354,26 +527,21 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_invert_block(const BlockTask*
                                                                  const double* __restrict__ lv,
                                                                  double* __restrict__ linv) {
   extern __shared__ __align__(16) double smem[];
-  double* rd = smem;
-  double* S = smem + NB_MAX;
+  double* S = smem;
+  double* rd = S + POTRF_S;
+  double* XD = rd + NB_MAX;
+  double* Tt = XD + POTRF_XD;
   const BlockTask B = bt[blockIdx.x];
   const SupInfo I = sup[B.sup];
-  const int nb = B.nb, r = I.r, tid = threadIdx.x;
+  const int nb = B.nb, nbp = (nb + 15) & ~15, tid = threadIdx.x;
+  const int64_t r = I.r;
   const double* __restrict__ P = lv + I.valptr + (int64_t)B.j0 * r + B.j0;
-  constexpr int LD = POTRF_LD;
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int c = e / nb, i = e % nb;
-    if (i >= c) S[c * LD + i] = P[(int64_t)c * r + i];
-    if (i == c) rd[c] = 1.0 / P[(int64_t)c * r + i];
-  }
+  load_padded_block(S, P, r, nb, nbp, tid);
   __syncthreads();
-  invert_lower_in_smem(S, rd, nb, tid);
+  if (tid < nbp) rd[tid] = 1.0 / S[tid * PLD + tid];
   __syncthreads();
-  double* __restrict__ X = linv + (int64_t)B.slot * NB_MAX * NB_MAX;
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int c = e / nb, i = e % nb;
-    X[c * NB_MAX + i] = (i > c) ? S[i * LD + c] : ((i == c) ? rd[c] : 0.0);
-  }
+  invert_in_smem(S, rd, XD, Tt, nbp, tid);
+  store_inverse(S, XD, linv + (int64_t)B.slot * NB_MAX * NB_MAX, nb, tid);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -88,8 +88,7 @@ static int64_t enqueue_factor_steps(parsy_cuda_solver* s, int step_begin, int st
       ++launches;
     }
     if (S.blocks.size()) {
-      const size_t smem = (size_t)(NB_MAX + S.max_nb * POTRF_LD) * 8;
-      k_potrf_block<<<S.blocks.size(), POTRF_THREADS, smem, st>>>(s->d_blocks + S.blocks.begin, s->d_sup, s->d_lv,
+      k_potrf_block<<<S.blocks.size(), POTRF_THREADS, POTRF_SMEM, st>>>(s->d_blocks + S.blocks.begin, s->d_sup, s->d_lv,
                                                                   s->d_linv, s->d_info);
       ++launches;
     }

@@ -24,7 +24,8 @@ S = ex.Solver(n, R.A2_p, R.A2_i, R.p, R.s, R.i_ptr, R.super, ns, R.sParent, R.co
               R.parPtr, R.partition, block_cols=nb)
 print("create: %.3fs" % (time.time() - t0), S.stats())
 S.set_values(R.A2_x)
-for it in range(3):
+FACTOR_ONLY = os.environ.get("FACTOR_ONLY") == "1"
+for it in range(1 if FACTOR_ONLY else 3):
     S.factor()
     ok = S.sync()
     print("factor ok", ok, S.factor_times())
@@ -33,6 +34,8 @@ ref = R.valL
 print("factor rel err:", rel_err(Lx, ref), " fro2:", float(Lx @ Lx), "nan:", int(np.isnan(Lx).sum()))
 bad = np.argmax(np.abs(Lx - ref))
 print("worst abs idx", bad, Lx[bad], ref[bad])
+if FACTOR_ONLY:
+    sys.exit(0)
 # solves on our own factor
 b = R.b_L1.copy()
 S.set_rhs(b)
