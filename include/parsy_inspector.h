@@ -1,0 +1,75 @@
+/* libparsy_inspector — host-side symbolic inspector (C ABI).
+ *
+ * Re-statement of the reference's analyze_p2 (cholesky/LSparsity.h:256-842) and of the two ptranspose calls the
+ * drivers make (examples/choleskyTest01.cpp:190-191): METIS nested dissection, elimination tree, postorders,
+ * column counts, relaxed supernodes, supernodal row patterns and the LBC schedule
+ * (cholesky/InspectionLevel_06.h:18).  Every array it returns must equal the reference's bit for bit
+ * (tests/test_inspector.py compares them against the compiled reference).  Plain host arrays, owned by the
+ * returned object; the executor (include/parsy_cuda.h) consumes them unchanged.
+ */
+#ifndef PARSY_INSPECTOR_H
+#define PARSY_INSPECTOR_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors the fields of BCSC (common/def.h:117-204) the executor reads, plus the schedule and P A P'. */
+typedef struct parsy_symbolic {
+  int n;              /* order of A                                                          */
+  int nsuper;         /* number of supernodes                                                */
+  int64_t nnzA;       /* entries of tril(A)                                                  */
+  int64_t xsize;      /* doubles in the supernodal factor (sum width*rows)                   */
+  int64_t ssize;      /* entries of the concatenated row lists                               */
+  int maxSupWid;      /* widest supernode                                                    */
+  int maxCol;         /* longest supernode (rows)                                            */
+  double flops;       /* sum_j ColCount[j]^2  (cholesky/ColumnCount.h:486-498)               */
+  double t_ordering;  /* seconds in METIS_NodeND                                             */
+  double t_total;     /* seconds in the whole inspector                                      */
+  int* Perm;          /* n: Perm[k] = original index placed at position k                    */
+  int* ColCount;      /* n: column counts of the simplicial factor, post-ordered             */
+  int* Parent;        /* n: column elimination tree, post-ordered                            */
+  int* super;         /* nsuper+1: first column of each supernode            (blockSet)      */
+  int* sParent;       /* nsuper: supernodal etree                            (aTree)         */
+  int* col2Sup;       /* n                                                                  */
+  size_t* pi;         /* nsuper+1: start of each supernode's row list in s                   */
+  int* s;             /* ssize: row lists                                    (lR)            */
+  size_t* p;          /* n+1: offset of every column in the factor           (lC)            */
+  size_t* i_ptr;      /* n+1: start of the row list of the column's supernode (Li_ptr)       */
+  int nLevels;        /* LBC H-levels                                                        */
+  int nParts;         /* total number of w-partitions                                        */
+  int* levelPtr;      /* nLevels+1                                                           */
+  int* parPtr;        /* nParts+1                                                            */
+  int* partition;     /* nsuper                                                              */
+  int* A1_p; int* A1_i;                /* triu(P A P') pattern by columns (cT, rT)           */
+  int* A2_p; int* A2_i; double* A2_x;  /* tril(P A P') by columns, rows ascending (c, r, values) */
+  int64_t* A2_src;    /* nnzA: position in the input arrays of every A2 entry (to re-permute new values) */
+} parsy_symbolic;
+
+/* A = lower-half CSC (rows ascending, diagonal first), as common/Util.h:77 `readMatrix` delivers it.
+ * costParam / levelParam / divRate = innerParts / minLevelDist / divRate of getCoarseLevelSet_6.
+ * userPerm: NULL -> METIS_NodeND with default options on the diagonal-free full graph (LSparsity.h:534-613);
+ *           otherwise a permutation of 0..n-1 used in place of the METIS result.
+ * Returns 0 on success. */
+int parsy_inspect(int n, const int* Ap, const int* Ai, const double* Ax, int costParam, int levelParam, int divRate,
+                  const int* userPerm, parsy_symbolic** out);
+void parsy_symbolic_free(parsy_symbolic* s);
+const char* parsy_inspector_last_error(void);
+
+/* Descendant supernodes of supernode s in topological order, exactly what ereach_sn (common/Reach.h:112-143)
+ * leaves in xi[top..supNo): fills out[0..count) and returns count (or -1 on bad input). Work arrays are internal. */
+int parsy_ereach_sn(const parsy_symbolic* sym, int s, int* out);
+
+/* Supernodal etree level sets as the reference's getLevelSet (common/TreeUtils.h:119) builds them for
+ * leveledBlockedLsolve (examples/triangularTest02.cpp:218): returns the number of levels. */
+int parsy_etree_level_set(int nsuper, const int* sParent, int* levelPtr /*nsuper+1*/, int* levelSet /*nsuper*/);
+
+/* BCSC -> CSC conversion of a supernodal factor (common/Util.h:311 bcsc2csc); Cp has n+1 entries; returns nnz.
+ * Pass Ci = Cx = NULL to only count. */
+int64_t parsy_bcsc2csc(const parsy_symbolic* sym, const double* Lx, int* Cp, int* Ci, double* Cx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
