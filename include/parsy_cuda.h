@@ -169,6 +169,12 @@ typedef struct parsy_cuda_stats {
 } parsy_cuda_stats;
 int parsy_cuda_get_stats(parsy_cuda_solver* s, parsy_cuda_stats* out);
 
+/* HOST-ONLY: runs the planner (schedule validation, descendant pairs, step assignment) without touching a device
+ * and fills the structural fields of `out`; used by the CPU test-suite.  Same return codes as parsy_cuda_create. */
+int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo,
+                          const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                          const int* partition, const parsy_cuda_options* opt, parsy_cuda_stats* out);
+
 /* Raw device pointers for callers that keep data on the GPU (e.g. bench.py with torch tensors). */
 double* parsy_cuda_device_factor(parsy_cuda_solver* s);   /* xsize doubles */
 double* parsy_cuda_device_rhs(parsy_cuda_solver* s);      /* n doubles     */

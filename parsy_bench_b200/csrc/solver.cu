@@ -437,6 +437,31 @@ extern "C" int parsy_cuda_get_stats(parsy_cuda_solver* s, parsy_cuda_stats* o) {
   return PARSY_CUDA_OK;
 }
 
+extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
+                                     int supNo, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                                     const int* partition, const parsy_cuda_options* opt, parsy_cuda_stats* o) {
+  Plan P;
+  PlanOptions po;
+  if (opt) { po.nb = opt->block_cols; po.ignore_hlevels = opt->ignore_hlevels != 0; }
+  std::vector<int> tl, tp, tq;
+  if (!levelPtr || !parPtr || !partition) {
+    tl = {0, 1}; tp = {0, supNo}; tq.resize(std::max(supNo, 0));
+    for (int i = 0; i < supNo; ++i) tq[i] = i;
+    nLevels = 1; levelPtr = tl.data(); parPtr = tp.data(); partition = tq.data();
+  }
+  const int rc = build_plan(P, n, lC, lR, Li_ptr, blockSet, supNo, nullptr, col2Sup, nLevels, levelPtr, parPtr, partition, po);
+  if (rc) return fail(rc, P.error);
+  if (o) {
+    memset(o, 0, sizeof(*o));
+    o->n = P.n; o->nsuper = P.nsuper; o->xsize = P.xsize; o->ssize = P.ssize;
+    o->n_pairs = P.n_pairs; o->n_pairs_small = P.n_pairs_small; o->n_pairs_tiled = P.n_pairs_tiled;
+    o->n_steps = (int64_t)P.steps.size(); o->n_block_cols = P.n_block_cols; o->rel_entries = P.rel_entries;
+    o->flops_potrf = P.flops_potrf; o->flops_trsm = P.flops_trsm; o->flops_update = P.flops_update;
+    o->bytes_solve = P.bytes_solve;
+  }
+  return PARSY_CUDA_OK;
+}
+
 extern "C" double* parsy_cuda_device_factor(parsy_cuda_solver* s) { return s ? s->d_lv : nullptr; }
 extern "C" double* parsy_cuda_device_rhs(parsy_cuda_solver* s) { return s ? s->d_rhs : nullptr; }
 extern "C" double* parsy_cuda_device_values(parsy_cuda_solver* s) { return s ? s->d_vals : nullptr; }

@@ -199,6 +199,25 @@ def lsolveParH2(n, Lp, Li, Lx, x, levels, levelPtr, levelSet, parts, parPtr, par
                         _i32(partition, "partition", True), int(chunk)])
 
 
+def plan_check(n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition, block_cols=0,
+               ignore_hlevels=False):
+    """Host-only planner run (no device needed): returns (status code, stats dict)."""
+    L = lib()
+    opt = Options()
+    opt.block_cols, opt.ignore_hlevels, opt.use_graph = int(block_cols), int(ignore_hlevels), 1
+    st = Stats()
+    f = L.parsy_cuda_plan_check
+    f.restype = c_int
+    f.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                  POINTER(Options), POINTER(Stats)]
+    keep = [_u64(lC, "lC"), _i32(lR, "lR"), _u64(Li_ptr, "Li_ptr"), _i32(blockSet, "blockSet"),
+            _i32(col2Sup, "col2Sup"), _i32(levelPtr, "levelPtr", True), _i32(parPtr, "parPtr", True),
+            _i32(partition, "partition", True)]
+    p = [k[1] for k in keep]
+    rc = f(int(n), p[0], p[1], p[2], p[3], int(supNo), p[4], int(nLevels), p[5], p[6], p[7], byref(opt), byref(st))
+    return rc, st.as_dict()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # resident handle
 # ---------------------------------------------------------------------------------------------------------

@@ -1,0 +1,99 @@
+"""CPU: the C-ABI libraries load and export every symbol their headers declare; host-only logic of the executor
+library (planner, schedule validation, error paths) behaves without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import load_golden
+from parsy_bench_b200 import _lib, executor as ex, inspector
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header, prefix):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(" + prefix + r"\w+)\s*\(", src)))
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = declared("parsy_cuda.h", "parsy_cuda_")
+    assert len(names) >= 30
+    for nme in names:
+        assert hasattr(L, nme), nme
+
+
+def test_inspector_library_exports_every_declared_symbol():
+    L = inspector.lib()
+    for nme in declared("parsy_inspector.h", "parsy_"):
+        assert hasattr(L, nme), nme
+
+
+def test_version_and_error_string():
+    L = _lib.lib()
+    assert L.parsy_cuda_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_plan_check_counts_pairs():
+    G = load_golden("2d5_N30_c8_l1_d2")
+    rc, st = ex.plan_check(G.n, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.col2Sup, len(G.levelPtr) - 1, G.levelPtr,
+                           G.parPtr, G.partition)
+    assert rc == ex.OK
+    assert st["nsuper"] == G.nsuper and st["xsize"] == G.meta["xsize"] and st["ssize"] == G.meta["ssize"]
+    assert st["n_pairs"] == st["n_pairs_small"] + st["n_pairs_tiled"] > 0
+    # executed supernodal flops bound the simplicial count from above (relaxed supernodes store explicit zeros)
+    assert st["flops_potrf"] + st["flops_trsm"] + st["flops_update"] >= G.meta["flops"] * 0.99
+
+
+def test_plan_check_rejects_illegal_schedules():
+    G = load_golden("2d5_N30_c8_l1_d2")
+    nl = len(G.levelPtr) - 1
+    rev = G.partition[::-1].copy()                    # parents before children
+    rc, _ = ex.plan_check(G.n, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.col2Sup, nl, G.levelPtr, G.parPtr, rev)
+    assert rc == ex.ERR_BAD_SCHEDULE
+    dup = G.partition.copy()
+    dup[0] = dup[1]                                    # a supernode listed twice
+    rc, _ = ex.plan_check(G.n, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.col2Sup, nl, G.levelPtr, G.parPtr, dup)
+    assert rc == ex.ERR_BAD_SCHEDULE
+    rc, _ = ex.plan_check(G.n, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.col2Sup, nl, G.levelPtr, G.parPtr,
+                          G.partition, block_cols=100)  # not a multiple of 8
+    assert rc == ex.ERR_BAD_ARG
+
+
+def test_plan_without_schedule_and_block_sizes():
+    G = load_golden("3d27_N6_c4_l0_d2")
+    for nb in (0, 32, 64, 128):
+        rc, st = ex.plan_check(G.n, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.col2Sup, 0, None, None, None,
+                               block_cols=nb)
+        assert rc == ex.OK and st["n_steps"] >= 1
+
+
+def test_etree_levels_are_a_legal_schedule():
+    """leveledBlockedLsolve's schedule = getLevelSet waves with one supernode per w-partition"""
+    G = load_golden("3d7_N7_c8_l1_d2")
+    parPtr = np.arange(G.nsuper + 1, dtype=np.int32)
+    rc, st = ex.plan_check(G.n, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.col2Sup, len(G.etree_levelPtr) - 1,
+                           G.etree_levelPtr, parPtr, G.etree_levelSet)
+    assert rc == ex.OK
+
+
+@pytest.mark.skipif(ex.device_count() > 0, reason="checks the no-device error path")
+def test_no_device_is_an_error_not_a_fallback():
+    G = load_golden("2d5_N12_c8_l1_d2")
+    with pytest.raises(ex.ParsyCudaError) as e:
+        ex.Solver(G.n, G.A2_p, G.A2_i, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.sParent, G.col2Sup,
+                  len(G.levelPtr) - 1, G.levelPtr, G.parPtr, G.partition)
+    assert e.value.code == ex.ERR_NO_DEVICE
+    lv = np.zeros(G.meta["xsize"])
+    ok = ex.cholesky_left_par_05(G.n, G.A2_p, G.A2_i, G.A2_x, G.p, G.s, G.i_ptr, lv, G.super, G.nsuper, None,
+                                 G.sParent, None, None, G.col2Sup, len(G.levelPtr) - 1, G.levelPtr, None, 0,
+                                 G.parPtr, G.partition)
+    assert ok is False and not lv.any()
+    x = np.ones(G.n)
+    assert ex.blockedLsolve(G.n, G.p, G.s, G.valL, 0, G.i_ptr, G.col2Sup, G.super, G.nsuper, x) == 0
+    assert ex.blockedLsolve(G.n, None, G.s, G.valL, 0, G.i_ptr, G.col2Sup, G.super, G.nsuper, x) == 0  # NULL Lp

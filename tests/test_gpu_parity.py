@@ -1,0 +1,234 @@
+"""GPU (-m gpu): parity of the CUDA executor, called through the C ABI, against
+  * the golden vectors the compiled reference produced (tests/golden/),
+  * the oracle's CPU restatement on seeded inputs of moderate size,
+  * size-independent properties at BASELINE.json's full sizes (||L||_F^2 = trace(A), L*1 round trip, residual).
+Tolerances: factor relative 1e-9 elementwise (north star) with the absolute floor 1e-6*max|L| for near-zero
+entries; solves: residual within 10x of the oracle's."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from common import FULL_CASES, load_golden, rel_err, parse_case, full_matrix, View
+from parsy_bench_b200 import executor as ex, inspector, matrices
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import parsy_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def dropin_factor(S, values=None, timing=None):
+    n = len(S.col2Sup)
+    lv = np.full(int(np.asarray(S.p)[n]), np.nan)   # the executor must not depend on the caller zeroing
+    ok = ex.cholesky_left_par_05(n, S.A2_p, S.A2_i, S.A2_x if values is None else values, S.p, S.s, S.i_ptr, lv,
+                                 S.super, S.nsuper, timing, S.sParent, S.A1_p, S.A1_i, S.col2Sup,
+                                 len(S.levelPtr) - 1, S.levelPtr, None, 0, S.parPtr, S.partition, 1, 1, 0, 0)
+    return ok, lv
+
+
+def analyze(kind, N, c=8, l=1, d=2):
+    n, Ap, Ai, Ax = matrices.laplacian(kind, N)
+    return inspector.analyze(n, Ap, Ai, Ax, c, l, d)
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_factor_vs_reference_golden(name):
+    G = load_golden(name)
+    timing = np.zeros(4)
+    ok, lv = dropin_factor(G, timing=timing)
+    assert ok
+    assert rel_err(lv, G.valL) < TOL
+    assert np.array_equal(lv == 0.0, G.valL == 0.0)     # never-written entries stay exactly 0.0
+    assert timing[0] >= 0 and timing[1] > 0
+
+
+@pytest.mark.parametrize("case", [("2d5", 100, 8, 1, 2), ("2d5", 100, 592, 1, 4), ("3d7", 20, 8, 1, 2),
+                                  ("3d27", 16, 8, 1, 2), ("3d27", 20, 148, 0, 4), ("2d5", 257, 37, 2, 2)])
+def test_factor_vs_oracle(case):
+    S = analyze(*case)
+    ok, lv = dropin_factor(S)
+    assert ok
+    ref = orc.cholesky_left_par_05(S)
+    assert rel_err(lv, ref) < TOL
+    assert abs(float(lv @ lv) - float(S.A2_x[S.A2_p[:-1]].sum())) < 1e-10 * S.n * 26
+
+
+def test_serial_twin_with_prune_set():
+    S = analyze("2d5", 40)
+    ptr = [0]
+    pset = []
+    for s in range(S.nsuper):
+        pset.extend(S.ereach_sn(s).tolist())
+        ptr.append(len(pset))
+    lv = np.zeros(S.xsize)
+    ok = ex.cholesky_left_sn_07(S.n, S.A2_p, S.A2_i, S.A2_x, S.p, S.s, S.i_ptr, lv, S.super, S.nsuper, None,
+                                np.array(ptr, np.int32), np.array(pset, np.int32))
+    assert ok and rel_err(lv, orc.cholesky_left_sn(S)) < TOL
+    bad = np.array(ptr, np.int32)
+    bad[-1] += 1
+    assert not ex.cholesky_left_sn_07(S.n, S.A2_p, S.A2_i, S.A2_x, S.p, S.s, S.i_ptr, lv, S.super, S.nsuper, None,
+                                      bad, np.array(pset + [0], np.int32))
+
+
+@pytest.mark.parametrize("nb", [32, 64, 128])
+def test_resident_handle_and_block_sizes(nb):
+    S = analyze("3d27", 14, 16, 0, 2)
+    ref = orc.cholesky_left_par_05(S)
+    H = ex.Solver(S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                  S.levelPtr, S.parPtr, S.partition, block_cols=nb)
+    H.set_values(S.A2_x)
+    for _ in range(2):                     # re-factoring on the same handle re-zeroes and re-assembles
+        H.factor()
+        assert H.sync()
+        assert rel_err(H.get_factor(), ref) < TOL
+    t = H.factor_times()
+    st = H.stats()
+    assert t["last_level"] > 0 and st["launches_factor"] > 0 and st["n_pairs"] == st["n_pairs_small"] + st["n_pairs_tiled"]
+    # no-graph path gives the same factor
+    H2 = ex.Solver(S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                   S.levelPtr, S.parPtr, S.partition, block_cols=nb, use_graph=False, ignore_hlevels=True)
+    H2.set_values(S.A2_x)
+    H2.factor()
+    assert H2.sync() and rel_err(H2.get_factor(), ref) < TOL
+    H.close()
+    H2.close()
+
+
+def test_not_positive_definite_returns_false():
+    G = load_golden("2d5_N30_c8_l1_d2")
+    vals = G.A2_x.copy()
+    vals[G.A2_p[G.n // 2]] = -4.0
+    ok, _ = dropin_factor(G, values=vals)
+    assert ok is False
+    assert orc.cholesky_left_par_05(G, vals) is None     # same verdict as the reference semantics
+
+
+def test_illegal_and_degenerate_schedules():
+    G = load_golden("2d5_N30_c8_l1_d2")
+    bad = View(G)
+    bad["partition"] = G.partition[::-1].copy()
+    ok, _ = dropin_factor(bad)
+    assert ok is False
+    # empty w-partitions are legal (InspectionLevel_06.h:302-319 can emit them)
+    e = View(G)
+    par = G.parPtr.tolist()
+    e["parPtr"] = np.array([0, 0] + par[1:], np.int32)       # an empty partition in front
+    lp = G.levelPtr.copy()
+    lp[1:] += 1
+    e["levelPtr"] = lp
+    ok, lv = dropin_factor(e)
+    assert ok and rel_err(lv, G.valL) < TOL
+    # one H-level, one partition, supernode order (what cholesky_left_sn_07 runs)
+    one = View(G)
+    one["levelPtr"] = np.array([0, 1], np.int32)
+    one["parPtr"] = np.array([0, G.nsuper], np.int32)
+    one["partition"] = np.arange(G.nsuper, dtype=np.int32)
+    ok, lv = dropin_factor(one)
+    assert ok and rel_err(lv, G.valL) < TOL
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_forward_solves_vs_reference_golden(name):
+    G = load_golden(name)
+    n, ns = G.n, G.nsuper
+    nnz = int(G.meta["xsize"])
+    for fn, extra in (
+        (ex.blockedLsolve, ()),
+        (ex.leveledBlockedLsolve, (len(G.etree_levelPtr) - 1, G.etree_levelPtr, G.etree_levelSet, 1)),
+        (ex.H2LeveledBlockedLsolve, (len(G.levelPtr) - 1, G.levelPtr, None, 0, G.parPtr, G.partition, 1)),
+        (ex.H2LeveledBlockedLsolve_Peeled, (len(G.levelPtr) - 1, G.levelPtr, None, 0, G.parPtr, G.partition, 1, 1)),
+    ):
+        x = G.b_L1.copy()
+        assert fn(n, G.p, G.s, G.valL, nnz, G.i_ptr, G.col2Sup, G.super, ns, x, *extra) == 1
+        assert np.max(np.abs(x - 1.0)) < 1e-10 and orc.test_triangular(x)      # known answer x == 1
+        y = 1.0 + np.arange(n) / n
+        assert fn(n, G.p, G.s, G.valL, nnz, G.i_ptr, G.col2Sup, G.super, ns, y, *extra) == 1
+        assert rel_err(y, G.y_ramp) < 1e-11
+    assert ex.blockedLsolve(n, None, G.s, G.valL, nnz, G.i_ptr, G.col2Sup, G.super, ns, G.b_L1.copy()) == 0
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_csc_solves_vs_reference_golden(name):
+    G = load_golden(name)
+    n = G.n
+    ramp = 1.0 + np.arange(n) / n
+    x = ramp.copy()
+    assert ex.lsolve(n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, x) == 1
+    assert rel_err(x, G.y_ramp_csc) < 1e-11
+    # column level sets for lsolvePar: level(i) = 1 + max level of the columns that update i
+    lev = np.zeros(n, np.int64)
+    for j in range(n):
+        rows = G.Lcsc_i[G.Lcsc_p[j] + 1:G.Lcsc_p[j + 1]]
+        if len(rows):
+            lev[rows] = np.maximum(lev[rows], lev[j] + 1)
+    order = np.argsort(lev, kind="stable").astype(np.int32)
+    lptr = np.concatenate([[0], np.cumsum(np.bincount(lev))]).astype(np.int32)
+    x = ramp.copy()
+    assert ex.lsolvePar(n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, x, len(lptr) - 1, lptr, order, 1) == 1
+    assert rel_err(x, G.y_ramp_csc) < 1e-11
+    x = ramp.copy()
+    assert ex.lsolveParH2(n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, x, 0, None, None, 0, None, None, 1) == 1
+    assert rel_err(x, G.y_ramp_csc) < 1e-11
+    assert ex.lsolve(n, None, G.Lcsc_i, G.Lcsc_x, x) == 0
+
+
+@pytest.mark.parametrize("case", [("2d5", 100, 8, 1, 2), ("3d27", 16, 8, 1, 2), ("3d7", 24, 148, 1, 4)])
+def test_full_solve_residual_vs_oracle(case):
+    """forward + NEW backward sweep: ||Ax-b||/||b|| within 10x of the oracle's residual on its own factor"""
+    S = analyze(*case)
+    n = S.n
+    A = full_matrix(S)
+    b = 1.0 + np.arange(n) / n
+    Lref = orc.cholesky_left_par_05(S)
+    xr = orc.blockedLtsolve(S, Lref, orc.blockedLsolve(S, Lref, b))
+    res_ref = np.linalg.norm(A @ xr - b) / np.linalg.norm(b)
+    H = ex.Solver(n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                  S.levelPtr, S.parPtr, S.partition)
+    H.set_values(S.A2_x)
+    H.factor()
+    assert H.sync()
+    H.set_rhs(b)
+    H.solve(ex.SOLVE_FWD)
+    y = H.get_rhs()
+    assert rel_err(y, orc.blockedLsolve(S, Lref, b)) < 1e-9
+    H.solve(ex.SOLVE_BWD)
+    x = H.get_rhs()
+    res = np.linalg.norm(A @ x - b) / np.linalg.norm(b)
+    assert res <= 10 * max(res_ref, np.finfo(float).eps), (res, res_ref)
+    assert rel_err(x, xr) < 1e-8
+    # drop-in backward sweep on the reference-layout arrays
+    z = y.copy()
+    assert ex.blockedLtsolve(n, S.p, S.s, Lref, int(S.xsize), S.i_ptr, S.col2Sup, S.super, S.nsuper, z) == 1
+    assert rel_err(z, xr) < 1e-8
+    H.close()
+
+
+@pytest.mark.parametrize("case", [("2d5", 1000, 8, 1, 2), ("3d27", 64, 8, 1, 2)])
+def test_full_size_properties(case):
+    """BASELINE.json configs 2 and 4 at full size: identities that need no CPU factorization."""
+    S = analyze(*case)
+    n = S.n
+    H = ex.Solver(n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                  S.levelPtr, S.parPtr, S.partition)
+    H.set_values(S.A2_x)
+    H.factor()
+    assert H.sync()
+    L = H.get_factor()
+    trace = float(S.A2_x[S.A2_p[:-1]].sum())
+    assert abs(float(L @ L) - trace) < 1e-10 * trace                 # ||L||_F^2 = trace(A)
+    b = orc.rhs_init_blocked(S, L)                                    # b = L*1 (Util.h:277)
+    H.set_rhs(b)
+    H.solve(ex.SOLVE_FWD)
+    x = H.get_rhs()
+    assert orc.test_triangular(x) and np.max(np.abs(x - 1.0)) < 1e-8  # Util.h:294, much tighter
+    A = full_matrix(S)
+    rhs = 1.0 + np.arange(n) / n
+    H.set_rhs(rhs)
+    H.solve(ex.SOLVE_FWD | ex.SOLVE_BWD)
+    sol = H.get_rhs()
+    assert np.linalg.norm(A @ sol - rhs) / np.linalg.norm(rhs) < 1e-9
+    del L
+    H.close()
