@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(128) k_update_small(const SmallTask* __restric
   const GemmTask T = tasks[S.pair];
   double* Bs = sB[warp];
   const double* __restrict__ src = lv + T.a_off;
-  for (int k = 0; k < T.K; ++k)
-    if (lane < T.N) Bs[k * 33 + lane] = src[(int64_t)k * T.lda + lane];
+  // rows K..KT of Bs are multiplied by a[k] = 0: they must hold zeros, not whatever the SM's shared memory kept
+  const int KT = T.K <= 4 ? 4 : (T.K <= 16 ? 16 : 32);
+  for (int k = 0; k < KT; ++k) Bs[k * 33 + lane] = (k < T.K && lane < T.N) ? src[(int64_t)k * T.lda + lane] : 0.0;
   if (lane < T.N) sRelc[warp][lane] = rel[T.rel_off + lane];
   __syncwarp();
   if (T.K <= 4) small_update_rows<4>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);

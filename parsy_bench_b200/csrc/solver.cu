@@ -245,6 +245,8 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
   TRY(dev_alloc(s, &s->d_info, 1));
   TRYCU(cudaMemset(s->d_info, 0, sizeof(int)));
   TRYCU(cudaMemset(s->d_linv, 0, std::max<size_t>((size_t)P.n_slots * NB_MAX * NB_MAX, 1) * 8));
+  // the blocking uploads above ran on the legacy stream; the solver's stream is non-blocking, so order them explicitly
+  TRYCU(cudaDeviceSynchronize());
   // relative indices (device-side binary searches, once per structure)
   TRY(dev_alloc(s, &s->d_rel, (size_t)P.rel_entries));
   if (P.rel_entries > 0) {
@@ -256,6 +258,7 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
     TRYCU(cudaMemcpy(d_src, P.rel_pair_src.data(), np * 4, cudaMemcpyHostToDevice));
     TRYCU(cudaMemcpy(d_tgt, P.rel_pair_tgt.data(), np * 4, cudaMemcpyHostToDevice));
     TRYCU(cudaMemcpy(d_lb, P.rel_pair_lb.data(), np * 4, cudaMemcpyHostToDevice));
+    TRYCU(cudaDeviceSynchronize());
     const int grid = (int)std::min<int64_t>((P.rel_entries + 255) / 256, 148 * 32);
     k_build_rel<<<grid, 256, 0, s->stream>>>(P.rel_entries, (int)np, d_prefix, d_src, d_tgt, d_lb, s->d_sup, s->d_lR,
                                              s->d_rel);
@@ -277,6 +280,7 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
     TRYCU(cudaMemcpy(d_c2s, col2Sup, (size_t)n * 4, cudaMemcpyHostToDevice));
     TRY(dev_alloc(s, &s->d_apos, (size_t)nnz));
     TRY(dev_alloc(s, &s->d_vals, (size_t)nnz));
+    TRYCU(cudaDeviceSynchronize());
     if (nnz > 0) {
       const int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 32);
       k_build_apos<<<grid, 256, 0, s->stream>>>(nnz, n, d_c, d_r, d_c2s, s->d_sup, s->d_lR, s->d_apos);

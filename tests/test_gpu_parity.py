@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from common import FULL_CASES, load_golden, rel_err, parse_case, full_matrix, View
-from parsy_bench_b200 import executor as ex, inspector, matrices
+from parsy_bench_b200 import executor as ex, inspector, matrices, _lib
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import parsy_oracle as orc  # noqa: E402
@@ -26,6 +26,8 @@ def dropin_factor(S, values=None, timing=None):
     ok = ex.cholesky_left_par_05(n, S.A2_p, S.A2_i, S.A2_x if values is None else values, S.p, S.s, S.i_ptr, lv,
                                  S.super, S.nsuper, timing, S.sParent, S.A1_p, S.A1_i, S.col2Sup,
                                  len(S.levelPtr) - 1, S.levelPtr, None, 0, S.parPtr, S.partition, 1, 1, 0, 0)
+    if not ok:
+        print('cholesky_left_par_05 failed:', _lib.last_error())
     return ok, lv
 
 
