@@ -151,6 +151,12 @@ int parsy_cuda_solve(parsy_cuda_solver* s, int which);              /* FWD, BWD 
  * out[0] = all H-levels but the last, out[1] = last H-level, out[2] = assembly (zero + scatter A), seconds. */
 int parsy_cuda_factor_times(parsy_cuda_solver* s, double* out3);
 
+/* One factorization without CUDA graphs, every kernel launch bracketed by CUDA events on the solver's stream;
+ * returns, per kernel class, the summed device time (ms), the number of launches and the algorithmic flops:
+ * 0 factor_small, 1 potrf_block, 2 TRSM tiles (DMMA), 3 update tiles 128 (DMMA), 4 update tiles 64 (DMMA),
+ * 5 update_small.  This is where bench.py's roofline numbers come from. */
+int parsy_cuda_factor_profiled(parsy_cuda_solver* s, double* class_ms6, int64_t* class_launches6, double* class_flops6);
+
 /* Introspection used by bench.py / tests (counts are exact, computed by the planner). */
 typedef struct parsy_cuda_stats {
   int64_t n, nsuper, xsize, ssize, nnzA;

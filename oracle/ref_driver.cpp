@@ -168,6 +168,9 @@ int main(int argc, char** argv) {
     double tr = 0; for (size_t j = 0; j < n; ++j) tr += Ax[Ap[j]];
     printf(", \"factor_ok\": %d, \"t_factor\": %.6f, \"t_levels\": %.6f, \"t_last\": %.6f, \"fro2\": %.17g, \"trace\": %.17g",
            (int)ok, tf[m], tl0[m], tl1[m], fro, tr);
+    printf(", \"t_factor_all\": [");
+    for (size_t i = 0; i < tf.size(); ++i) printf("%s%.6f", i ? ", " : "", tf[i]);
+    printf("]");
     if (dumpL) dump(dir, "valL.f64", valL, L->xsize);
   }
 
@@ -239,6 +242,9 @@ int main(int argc, char** argv) {
       dump(dir, "y_ramp_csc.f64", x, n);
       delete[] Cp; delete[] Ci; delete[] Cx;
     }
+    printf(", \"t_h2_all\": [");
+    for (size_t i = 0; i < t3.size(); ++i) printf("%s%.6f", i ? ", " : "", t3[i]);
+    printf("]");
     printf(", \"solve_ok\": %d, \"t_blockedLsolve\": %.6f, \"t_leveled\": %.6f, \"t_h2\": %.6f, \"t_h2_peeled\": %.6f, "
            "\"t_lsolve_csc\": %.6f, \"etree_levels\": %d, \"nnzLcsc\": %zu",
            okall, med(t1), med(t2), med(t3), med(t4), tcsc, blevels, nnzC);

@@ -46,7 +46,7 @@ struct GemmCfg {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_DOUBLES * 8 + (TM + TN) * 4;
   static constexpr int FM = WM / 8, FN = WN / 8;
 };
-using Cfg128 = GemmCfg<128, 128, 64, 32, 8, 4>;
+using Cfg128 = GemmCfg<128, 128, 32, 32, 16, 3>;   // 16 warps: 4 per SMSP keep the DMMA pipe fed across LDS/barrier stalls
 using Cfg64 = GemmCfg<64, 64, 32, 32, 8, 4>;
 
 template <class C>
@@ -209,10 +209,11 @@ __device__ __forceinline__ void small_update_rows(const GemmTask& T, int row0, i
   }
 }
 
+template <int KMAX>
 __global__ void __launch_bounds__(128) k_update_small(const SmallTask* __restrict__ st, int count,
                                                        const GemmTask* __restrict__ tasks, double* __restrict__ lv,
                                                        const int* __restrict__ rel) {
-  __shared__ double sB[4][32 * 33];
+  __shared__ double sB[4][KMAX * 33];
   __shared__ int sRelc[4][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wid = blockIdx.x * 4 + warp;
@@ -222,22 +223,25 @@ __global__ void __launch_bounds__(128) k_update_small(const SmallTask* __restric
   double* Bs = sB[warp];
   const double* __restrict__ src = lv + T.a_off;
   // rows K..KT of Bs are multiplied by a[k] = 0: they must hold zeros, not whatever the SM's shared memory kept
-  const int KT = T.K <= 4 ? 4 : (T.K <= 16 ? 16 : 32);
+  const int KT = KMAX <= 4 ? 4 : (T.K <= 4 ? 4 : (T.K <= 16 ? 16 : 32));
   for (int k = 0; k < KT; ++k) Bs[k * 33 + lane] = (k < T.K && lane < T.N) ? src[(int64_t)k * T.lda + lane] : 0.0;
   if (lane < T.N) sRelc[warp][lane] = rel[T.rel_off + lane];
   __syncwarp();
-  if (T.K <= 4) small_update_rows<4>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
-  else if (T.K <= 16) small_update_rows<16>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
-  else small_update_rows<32>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
+  if (KMAX <= 4 || T.K <= 4) small_update_rows<4>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
+  else if (T.K <= 16) small_update_rows<(KMAX < 16 ? KMAX : 16)>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
+  else small_update_rows<KMAX>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
 }
 
 // ------------------------------------------------------------------------------------------------
 // narrow supernodes: one warp each, POTRF (MyBLAS.h:10-25 semantics) + TRSM (MyBLAS.h:27-35) fused
 // ------------------------------------------------------------------------------------------------
+template <int WMAX>
 __global__ void __launch_bounds__(128) k_factor_small(const int* __restrict__ list, int count,
                                                        const SupInfo* __restrict__ sup, double* __restrict__ lv,
                                                        int* __restrict__ info) {
-  __shared__ double sD[4][32 * 33];
+  constexpr int LDS = WMAX + 1;
+  __shared__ double sD[4][WMAX * LDS];
+  __shared__ double sR[4][WMAX];   // reciprocal diagonal
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wid = blockIdx.x * 4 + warp;
   if (wid >= count) return;
@@ -245,31 +249,33 @@ __global__ void __launch_bounds__(128) k_factor_small(const int* __restrict__ li
   const int w = I.w, r = I.r;
   double* __restrict__ P = lv + I.valptr;
   double* S = sD[warp];
+  double* R = sR[warp];
   for (int c = 0; c < w; ++c)
-    if (lane < w) S[c * 33 + lane] = P[(int64_t)c * r + lane];
+    if (lane < w) S[c * LDS + lane] = P[(int64_t)c * r + lane];
   __syncwarp();
   for (int c = 0; c < w; ++c) {
-    double acc = S[c * 33 + lane];
-    for (int k = 0; k < c; ++k) acc = fma(-S[k * 33 + lane], S[k * 33 + c], acc);
+    double acc = (lane < w) ? S[c * LDS + lane] : 0.0;
+    for (int k = 0; k < c; ++k) acc = (lane < w) ? fma(-S[k * LDS + lane], S[k * LDS + c], acc) : acc;
     const double piv = __shfl_sync(0xffffffffu, acc, c);
     if (!(piv > 0.0) && lane == 0) atomicCAS(info, 0, I.col0 + c + 1);
     const double l = sqrt(piv);
     const double v = (lane == c) ? l : acc / l;
-    if (lane >= c && lane < w) S[c * 33 + lane] = v;
+    if (lane >= c && lane < w) S[c * LDS + lane] = v;
+    if (lane == c) R[c] = 1.0 / l;
     __syncwarp();
   }
   for (int c = 0; c < w; ++c)
-    if (lane >= c && lane < w) P[(int64_t)c * r + lane] = S[c * 33 + lane];
+    if (lane >= c && lane < w) P[(int64_t)c * r + lane] = S[c * LDS + lane];
   // rows below the diagonal block: x * L11' = a, one lane per row
   for (int i = w + lane; i < r; i += 32) {
-    double x[32];
+    double x[WMAX];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < WMAX; ++c) {
       if (c < w) {
         double a = P[(int64_t)c * r + i];
 #pragma unroll
-        for (int k = 0; k < c; ++k) a = fma(-x[k], S[k * 33 + c], a);
-        x[c] = a / S[c * 33 + c];
+        for (int k = 0; k < c; ++k) a = fma(-x[k], S[k * LDS + c], a);
+        x[c] = a * R[c];
         P[(int64_t)c * r + i] = x[c];
       }
     }
@@ -296,6 +302,26 @@ constexpr int POTRF_T = NB_MAX * XDLD;                // 16 x 128 temporary, col
 constexpr size_t POTRF_SMEM = (size_t)(POTRF_S + NB_MAX + POTRF_XD + POTRF_T) * 8;
 constexpr int POTRF_LD = PLD;
 
+// 1/sqrt(a) for the pivot chain: FP32 seed (MUFU.RSQ) + two Newton steps in FP64 (6 dependent FP64 ops; error
+// ~1 ulp).  The library rsqrt() carries special-case branches that sit on the factorization's critical path.
+__device__ __forceinline__ double fast_rsqrt(double a) {
+  // scale by an even power of two into [1,4) so the FP32 seed never leaves float range
+  const int hi = __double2hiint(a);
+  const int ex = (((hi >> 20) & 0x7ff) - 1023) & ~1;
+  const double as = __hiloint2double(hi - (ex << 20), __double2loint(a));
+  double y = (double)rsqrtf((float)as);
+  const double h = 0.5 * as;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-h * y, y, 0.5);   // 0.5 - 0.5*a*y^2
+    y = fma(y, e, y);
+  }
+  y = __hiloint2double(__double2hiint(y) - ((ex >> 1) << 20), __double2loint(y));
+  // zero, negative, NaN, Inf, denormal: library path (rare; the test is off the dependent chain)
+  if (!(a > 1e-300 && a < 1e300)) y = rsqrt(a);
+  return y;
+}
+
 // micro panel: columns [p0, p0+8), thread t owns row p0+t
 __device__ __forceinline__ void potrf_micro8(double* S, double* rd, int p0, int nbp, int tid, int* info, int colbase,
                                              int nb) {
@@ -316,7 +342,7 @@ __device__ __forceinline__ void potrf_micro8(double* S, double* rd, int p0, int 
   for (int c = 0; c < 8; ++c) {
     const double piv = d[c][c];
     if (tid == 0 && !(piv > 0.0) && p0 + c < nb) atomicCAS(info, 0, colbase + p0 + c + 1);
-    const double r = rsqrt(piv);
+    const double r = fast_rsqrt(piv);
     rr[c] = r;
     d[c][c] = piv * r;
 #pragma unroll
@@ -477,11 +503,14 @@ __device__ __forceinline__ void invert_in_smem(double* S, const double* rd, doub
   }
 }
 
+// row = tid & 127, two column phases: no integer division, coalesced along rows
 __device__ __forceinline__ void store_inverse(const double* S, const double* XD, double* __restrict__ X, int nb,
                                               int tid) {
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int c = e / nb, i = e - c * nb;
-    const int I = i >> 4, J = c >> 4;
+  const int i = tid & 127, I = i >> 4;
+  if (i >= nb) return;
+#pragma unroll 8
+  for (int c = tid >> 7; c < nb; c += 2) {
+    const int J = c >> 4;
     double v = 0.0;
     if (I == J) v = XD[I * 16 * XDLD + (c & 15) * XDLD + (i & 15)];
     else if (I > J) v = S[(I * 16 + (c & 15)) * PLD + J * 16 + (i & 15)];
@@ -489,11 +518,31 @@ __device__ __forceinline__ void store_inverse(const double* S, const double* XD,
   }
 }
 
+__device__ __forceinline__ void store_factor_block(const double* S, double* __restrict__ P, int64_t r, int nb, int tid) {
+  const int i = tid & 127;
+  if (i >= nb) return;
+#pragma unroll 8
+  for (int c = tid >> 7; c <= i; c += 2) P[(int64_t)c * r + i] = S[c * PLD + i];
+}
+
 __device__ __forceinline__ void load_padded_block(double* S, const double* __restrict__ P, int64_t r, int nb, int nbp,
                                                   int tid) {
-  for (int e = tid; e < nbp * nbp; e += POTRF_THREADS) {
-    const int c = e / nbp, i = e - c * nbp;
-    if (i >= c) S[c * PLD + i] = (i < nb && c < nb) ? P[(int64_t)c * r + i] : ((i == c) ? 1.0 : 0.0);
+  // row = tid & 127, two column phases; batches of 16 independent global loads before the dependent shared stores
+  constexpr int U = 16;
+  const int i = tid & 127;
+  if (i >= nbp) return;
+  for (int c0 = tid >> 7; c0 <= i; c0 += 2 * U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + 2 * u;
+      v[u] = (c <= i && i < nb && c < nb) ? P[(int64_t)c * r + i] : ((i == c) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + 2 * u;
+      if (c <= i) S[c * PLD + i] = v[u];
+    }
   }
 }
 
@@ -514,10 +563,7 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_block(const BlockTask* 
   load_padded_block(S, P, r, nb, nbp, tid);
   __syncthreads();
   potrf_in_smem(S, rd, nb, nbp, tid, info, I.col0 + B.j0);
-  for (int e = tid; e < nb * nb; e += POTRF_THREADS) {
-    const int c = e / nb, i = e - c * nb;
-    if (i >= c) P[(int64_t)c * r + i] = S[c * PLD + i];
-  }
+  store_factor_block(S, P, r, nb, tid);
   invert_in_smem(S, rd, XD, Tt, nbp, tid);
   store_inverse(S, XD, linv + (int64_t)B.slot * NB_MAX * NB_MAX, nb, tid);
 }

@@ -55,7 +55,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     I.r = (int)(Li_ptr[blockSet[s + 1]] - Li_ptr[I.col0]);
     I.valptr = (int64_t)lC[I.col0];
     if (I.r < I.w) { P.error = "supernode with fewer rows than columns"; return PARSY_CUDA_ERR_BAD_ARG; }
-    I.flags = (I.w <= SMALL_W && I.r <= SMALL_R) ? 1 : 0;
+    I.flags = (I.w <= SMALL_W && I.r <= SMALL_R && (int64_t)(I.r - I.w) * I.w * I.w <= SMALL_WORK) ? 1 : 0;
     xs = std::max<int64_t>(xs, I.valptr + (int64_t)I.w * I.r);
     ss = std::max<int64_t>(ss, I.rowptr + I.r);
     const double w = I.w, r = I.r;
@@ -120,88 +120,87 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   // (the whole width of d is applied in one task, K = width(d)).
 
   // ---- bucket everything by step ----------------------------------------------------------------------
-  // Two passes to keep memory bounded: count, then fill flat arrays.
   P.steps.assign(nsteps, Step());
   for (int H = 0; H < nLevels; ++H)
     for (int st = P.hlevel_first_step[H]; st < P.hlevel_first_step[H + 1]; ++st) P.steps[st].hlevel = H;
   if (opt.ignore_hlevels) for (auto& s : P.steps) s.hlevel = 0;
 
-  std::vector<int32_t> c_small(nsteps, 0), c_blk(nsteps, 0), c_trsm(nsteps, 0), c_128(nsteps, 0), c_64(nsteps, 0),
-      c_us(nsteps, 0), c_st(nsteps, 0);
   auto is_small_pair = [&](int K, int N) { return K <= 32 && N <= 32; };
   auto use128 = [&](int M, int N) { return N > 64 && (int64_t)M * N >= 2 * 128 * 128; };
-  auto small_chunks = [&](int M) { return cdiv(M, 256); };
+  auto upd_flops = [](const GemmTask& t) { return (double)t.N * t.N * t.K + 2.0 * (double)(t.M - t.N) * t.N * t.K; };
 
+  // factor-side lists: small supernodes and block columns per step
+  std::vector<int32_t> c_small(nsteps, 0), c_blk(nsteps, 0);
   for (int s = 0; s < supNo; ++s) {
-    const SupInfo& I = P.sup[s];
-    if (I.flags) { c_small[step0[s]]++; continue; }
-    for (int b = 0; b < nblk[s]; ++b) {
-      const int st = step0[s] + b, j0 = b * NB, nb = std::min(NB, I.w - j0);
-      c_blk[st]++;
-      if (I.r - j0 - nb > 0) c_trsm[st]++;
-      if (j0 + nb < I.w) { if (use128(I.r - j0 - nb, I.w - j0 - nb)) c_128[st]++; else c_64[st]++; }
-    }
+    if (P.sup[s].flags) { c_small[step0[s]]++; continue; }
+    for (int b2 = 0; b2 < nblk[s]; ++b2) c_blk[step0[s] + b2]++;
   }
-  for (const PairDesc& q : P.pairs) {
-    const int st = step0[q.src] + nblk[q.src] - 1, K = P.sup[q.src].w;
-    if (is_small_pair(K, q.nd1)) { c_us[st]++; c_st[st] += small_chunks(q.m); }
-    else if (use128(q.m, q.nd1)) c_128[st]++;
-    else c_64[st]++;
-  }
-  // offsets
-  std::vector<int64_t> o_small(nsteps + 1, 0), o_blk(nsteps + 1, 0), o_gemm(nsteps + 1, 0), o_st(nsteps + 1, 0);
-  for (int st = 0; st < nsteps; ++st) {
-    o_small[st + 1] = o_small[st] + c_small[st];
-    o_blk[st + 1] = o_blk[st] + c_blk[st];
-    o_gemm[st + 1] = o_gemm[st] + c_trsm[st] + c_128[st] + c_64[st] + c_us[st];
-    o_st[st + 1] = o_st[st] + c_st[st];
-  }
-  if (o_gemm[nsteps] > INT32_MAX || o_st[nsteps] > INT32_MAX) { P.error = "task list too large"; return PARSY_CUDA_ERR_BAD_ARG; }
+  std::vector<int64_t> o_small(nsteps + 1, 0), o_blk(nsteps + 1, 0);
+  for (int st = 0; st < nsteps; ++st) { o_small[st + 1] = o_small[st] + c_small[st]; o_blk[st + 1] = o_blk[st] + c_blk[st]; }
   P.small_list.resize(o_small[nsteps]);
   P.block_tasks.resize(o_blk[nsteps]);
-  P.gemm_tasks.resize(o_gemm[nsteps]);
-  P.small_tasks.resize(o_st[nsteps]);
-  std::vector<int32_t> f_small(nsteps, 0), f_blk(nsteps, 0), f_trsm(nsteps, 0), f_128(nsteps, 0), f_64(nsteps, 0),
-      f_us(nsteps, 0), f_st(nsteps, 0);
   for (int st = 0; st < nsteps; ++st) {
-    Step& S = P.steps[st];
-    S.small_sup = Range{(int32_t)o_small[st], (int32_t)o_small[st + 1]};
-    S.blocks = Range{(int32_t)o_blk[st], (int32_t)o_blk[st + 1]};
-    int32_t g = (int32_t)o_gemm[st];
-    S.trsm = Range{g, g + c_trsm[st]}; g += c_trsm[st];
-    S.upd128 = Range{g, g + c_128[st]}; g += c_128[st];
-    S.upd64 = Range{g, g + c_64[st]}; g += c_64[st];
-    // the small pairs' GemmTasks follow; they are addressed through small_tasks
-    S.small_upd = Range{(int32_t)o_st[st], (int32_t)o_st[st + 1]};
+    P.steps[st].small_sup = Range{(int32_t)o_small[st], (int32_t)o_small[st + 1]};
+    P.steps[st].blocks = Range{(int32_t)o_blk[st], (int32_t)o_blk[st + 1]};
   }
-  auto gemm_small_base = [&](int st) { return (int32_t)o_gemm[st] + c_trsm[st] + c_128[st] + c_64[st]; };
 
+  // GEMM-shaped tasks, generated with a sort key: step, then class (0 trsm, 1 tiles128, 2 tiles64, 3 small), then
+  // group (0 = "A": the target is factored in the very next step, 1 = "R": the rest; the executor overlaps R with
+  // the next step's POTRF/TRSM on a second stream)
+  struct Gen { GemmTask t; int32_t step; int8_t cls, grp; };
+  std::vector<Gen> gen;
+  gen.reserve(P.pairs.size() + 3 * (size_t)o_blk[nsteps]);
+  auto emit_update = [&](const GemmTask& t, int st, int grp, bool real_pair) {
+    Gen g; g.t = t; g.step = st; g.grp = (int8_t)grp;
+    const double fl = upd_flops(t);
+    if (real_pair && is_small_pair(t.K, t.N)) { g.cls = 3; P.class_flops[5] += fl; P.n_pairs_small++; }
+    else if (use128(t.M, t.N)) { g.cls = 1; P.class_flops[3] += fl; if (real_pair) P.n_pairs_tiled++; }
+    else { g.cls = 2; P.class_flops[4] += fl; if (real_pair) P.n_pairs_tiled++; }
+    gen.push_back(g);
+  };
+
+  std::vector<int32_t> f_small(nsteps, 0), f_blk(nsteps, 0);
   int32_t slot = 0;
   for (int s = 0; s < supNo; ++s) {
     const SupInfo& I = P.sup[s];
-    if (I.flags) { P.small_list[o_small[step0[s]] + f_small[step0[s]]++] = s; continue; }
-    for (int b = 0; b < nblk[s]; ++b) {
-      const int st = step0[s] + b, j0 = b * NB, nb = std::min(NB, I.w - j0);
+    if (I.flags) {
+      P.small_list[o_small[step0[s]] + f_small[step0[s]]++] = s;
+      P.class_flops[0] += (double)I.w * I.w * I.w / 3.0 + (double)I.w * I.w * (I.r - I.w);
+      continue;
+    }
+    for (int b2 = 0; b2 < nblk[s]; ++b2) {
+      const int st = step0[s] + b2, j0 = b2 * NB, nb = std::min(NB, I.w - j0);
       Step& S = P.steps[st];
       BlockTask bt; memset(&bt, 0, sizeof(bt));
       bt.sup = s; bt.j0 = j0; bt.nb = nb; bt.slot = slot;
       P.block_tasks[o_blk[st] + f_blk[st]++] = bt;
+      P.class_flops[1] += (double)nb * nb * nb / 3.0;
       S.max_nb = std::max(S.max_nb, nb);
       const int Mb = I.r - j0 - nb;
       if (Mb > 0) {
-        GemmTask t; memset(&t, 0, sizeof(t));
+        Gen g; memset(&g.t, 0, sizeof(g.t));
+        GemmTask& t = g.t;
         t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = (int64_t)slot * NB_MAX * NB_MAX; t.c_off = t.a_off;
         t.rel_off = -1; t.lda = I.r; t.ldb = NB_MAX; t.ldc = I.r; t.M = Mb; t.N = nb; t.K = nb;
         t.flags = GF_OVERWRITE | GF_B_LINV;
-        P.gemm_tasks[S.trsm.begin + f_trsm[st]++] = t;
+        g.step = st; g.cls = 0; g.grp = 0;
+        gen.push_back(g);
+        P.class_flops[2] += (double)Mb * nb * nb;
       }
-      if (j0 + nb < I.w) {
+      const int Nt = I.w - j0 - nb;   // trailing columns of the same supernode
+      if (Nt > 0) {
+        // columns of the next block column first ("A"), the remainder of the trapezoid separately ("R")
+        const int n1 = std::min(Nt, NB);
         GemmTask t; memset(&t, 0, sizeof(t));
         t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = t.a_off;
         t.c_off = I.valptr + (int64_t)(j0 + nb) * I.r + j0 + nb;
-        t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = Mb; t.N = I.w - j0 - nb; t.K = nb; t.flags = GF_LOWER;
-        if (use128(t.M, t.N)) P.gemm_tasks[S.upd128.begin + f_128[st]++] = t;
-        else P.gemm_tasks[S.upd64.begin + f_64[st]++] = t;
+        t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = Mb; t.N = n1; t.K = nb; t.flags = GF_LOWER;
+        emit_update(t, st, 0, false);
+        if (Nt > n1) {
+          GemmTask u = t;
+          u.a_off += n1; u.b_off += n1; u.c_off += (int64_t)n1 * I.r + n1; u.M = Mb - n1; u.N = Nt - n1;
+          emit_update(u, st, 1, false);
+        }
       }
       ++slot;
     }
@@ -216,39 +215,86 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     const PairDesc& q = P.pairs[pi];
     const SupInfo& D = P.sup[q.src]; const SupInfo& T = P.sup[q.tgt];
     const int st = step0[q.src] + nblk[q.src] - 1;
-    Step& S = P.steps[st];
     GemmTask t; memset(&t, 0, sizeof(t));
     t.a_off = D.valptr + q.lb; t.b_off = t.a_off; t.c_off = T.valptr; t.rel_off = rel;
     t.lda = t.ldb = D.r; t.ldc = T.r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
     P.rel_prefix[pi] = rel; P.rel_pair_src[pi] = q.src; P.rel_pair_tgt[pi] = q.tgt; P.rel_pair_lb[pi] = q.lb;
     rel += q.m;
-    if (is_small_pair(t.K, t.N)) {
-      const int32_t gi = gemm_small_base(st) + f_us[st]++;
-      P.gemm_tasks[gi] = t;
-      for (int r0 = 0; r0 < t.M; r0 += 256) {
-        SmallTask stt; stt.pair = gi; stt.row0 = r0; stt.nrows = std::min(256, t.M - r0); stt.pad = 0;
-        P.small_tasks[o_st[st] + f_st[st]++] = stt;
-      }
-      P.n_pairs_small++;
-    } else if (use128(t.M, t.N)) { P.gemm_tasks[S.upd128.begin + f_128[st]++] = t; P.n_pairs_tiled++; }
-    else { P.gemm_tasks[S.upd64.begin + f_64[st]++] = t; P.n_pairs_tiled++; }
+    emit_update(t, st, step0[q.tgt] == st + 1 ? 0 : 1, true);
   }
   P.rel_prefix[P.pairs.size()] = rel;
   P.rel_entries = rel;
 
+  if (gen.size() > (size_t)INT32_MAX) { P.error = "task list too large"; return PARSY_CUDA_ERR_BAD_ARG; }
+  std::vector<int32_t> ord(gen.size());
+  for (size_t i = 0; i < gen.size(); ++i) ord[i] = (int32_t)i;
+  auto key = [&](int32_t i) { return ((int64_t)gen[i].step << 8) | ((int64_t)gen[i].cls << 4) | gen[i].grp; };
+  std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return key(x) < key(y); });
+  P.gemm_tasks.resize(gen.size());
+  {
+    size_t i = 0;
+    for (int st = 0; st < nsteps; ++st) {
+      Step& S = P.steps[st];
+      auto take = [&](int cls, int grp) {
+        const int32_t b0 = (int32_t)i;
+        while (i < ord.size() && gen[ord[i]].step == st && gen[ord[i]].cls == cls && gen[ord[i]].grp == grp) {
+          P.gemm_tasks[i] = gen[ord[i]].t;
+          ++i;
+        }
+        return Range{b0, (int32_t)i};
+      };
+      S.trsm = take(0, 0);
+      for (int g = 0; g < 2; ++g) S.upd[g].u128 = take(1, g);
+      for (int g = 0; g < 2; ++g) S.upd[g].u64 = take(2, g);
+      for (int g = 0; g < 2; ++g) S.upd[g].small_pairs = take(3, g);
+    }
+  }
+  std::vector<Gen>().swap(gen);
+  // row chunks of the small pairs, narrow (K <= 4) first inside every (step, group)
+  for (int st = 0; st < nsteps; ++st)
+    for (int g = 0; g < 2; ++g) {
+      UpdGroup& U = P.steps[st].upd[g];
+      U.small.begin = (int32_t)P.small_tasks.size();
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int gi = U.small_pairs.begin; gi < U.small_pairs.end; ++gi) {
+          const GemmTask& t = P.gemm_tasks[gi];
+          if ((t.K <= 4) != (pass == 0)) continue;
+          for (int r0 = 0; r0 < t.M; r0 += 256) {
+            SmallTask stt; stt.pair = gi; stt.row0 = r0; stt.nrows = std::min(256, t.M - r0); stt.pad = 0;
+            P.small_tasks.push_back(stt);
+          }
+        }
+        if (pass == 0) U.small_narrow = (int32_t)P.small_tasks.size() - U.small.begin;
+      }
+      U.small.end = (int32_t)P.small_tasks.size();
+    }
+
+  // narrow supernodes first inside every step (the low-register kernel variant takes the leading part of the list)
+  for (int st = 0; st < nsteps; ++st) {
+    Step& S = P.steps[st];
+    std::stable_sort(P.small_list.begin() + S.small_sup.begin, P.small_list.begin() + S.small_sup.end,
+                     [&](int a2, int b2) { return P.sup[a2].w < P.sup[b2].w; });
+    S.small_narrow = 0;
+    for (int i = S.small_sup.begin; i < S.small_sup.end; ++i) if (P.sup[P.small_list[i]].w <= SMALL_W_NARROW) S.small_narrow++;
+  }
   // tile prefixes per launch segment
   for (int st = 0; st < nsteps; ++st) {
     Step& S = P.steps[st];
     int32_t acc = 0;
     for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, 128); }
-    S.trsm_tiles = acc; acc = 0;
-    for (int i = S.upd128.begin; i < S.upd128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128); }
-    S.upd128_tiles = acc; acc = 0;
-    for (int i = S.upd64.begin; i < S.upd64.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 64); }
-    S.upd64_tiles = acc; acc = 0;
+    S.trsm_tiles = acc;
+    for (int g = 0; g < 2; ++g) {
+      UpdGroup& U = S.upd[g];
+      acc = 0;
+      for (int i = U.u128.begin; i < U.u128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128); }
+      U.tiles128 = acc; acc = 0;
+      for (int i = U.u64.begin; i < U.u64.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 64); }
+      U.tiles64 = acc;
+    }
+    acc = 0;
     for (int i = S.blocks.begin; i < S.blocks.end; ++i) {
-      BlockTask& b = P.block_tasks[i];
-      b.tile0 = acc; acc += std::max(1, cdiv(P.sup[b.sup].r - b.j0 - b.nb, 64));
+      BlockTask& bk = P.block_tasks[i];
+      bk.tile0 = acc; acc += std::max(1, cdiv(P.sup[bk.sup].r - bk.j0 - bk.nb, 64));
     }
     S.solve_tiles = acc;
   }

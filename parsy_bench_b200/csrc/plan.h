@@ -19,6 +19,8 @@ namespace parsy {
 
 constexpr int SMALL_W = 32;       // widest supernode handled by the warp-cooperative path
 constexpr int SMALL_R = 1024;     // ... and its largest row count
+constexpr int64_t SMALL_WORK = 100000;   // ... and the bound on (rows below) * width^2 one warp is asked to do
+constexpr int SMALL_W_NARROW = 8;        // supernodes / pairs at most this wide run in the low-register kernels
 constexpr int NB_MAX = 128;       // largest block-column width (POTRF tile held in shared memory)
 
 enum GemmFlags : int32_t {
@@ -77,17 +79,25 @@ struct PairDesc {
 
 struct Range { int32_t begin = 0, end = 0; int32_t size() const { return end - begin; } };
 
+// Update work of one step, split by when its target is needed.
+struct UpdGroup {
+  Range u128;          // gemm_tasks, 128x128 DMMA tiles
+  int32_t tiles128 = 0;
+  Range u64;           // gemm_tasks, 64x64 DMMA tiles
+  int32_t tiles64 = 0;
+  Range small_pairs;   // gemm_tasks of the warp-FMA pairs (addressed through small_tasks)
+  Range small;         // small_tasks (row chunks); the first small_narrow have K <= 4
+  int32_t small_narrow = 0;
+};
+
 struct Step {
-  int32_t hlevel;
-  Range small_sup;   // into small_list
+  int32_t hlevel = 0;
+  Range small_sup;   // into small_list, sorted by width; the first small_narrow have width <= SMALL_W_NARROW
+  int32_t small_narrow = 0;
   Range blocks;      // into block_tasks
   Range trsm;        // into gemm_tasks (T128, GF_OVERWRITE|GF_B_LINV)
   int32_t trsm_tiles = 0;
-  Range upd128;      // into gemm_tasks
-  int32_t upd128_tiles = 0;
-  Range upd64;
-  int32_t upd64_tiles = 0;
-  Range small_upd;   // into small_tasks
+  UpdGroup upd[2];   // [0] targets factored in the next step ("A"), [1] everything else ("R")
   int32_t solve_tiles = 0;   // row tiles of the block tasks (forward / backward sweeps)
   int32_t max_nb = 0;        // widest block column in this step
 };
@@ -119,6 +129,9 @@ struct Plan {
   int32_t n_slots = 0;
   int64_t n_pairs = 0, n_pairs_small = 0, n_pairs_tiled = 0, n_block_cols = 0;
   double flops_potrf = 0, flops_trsm = 0, flops_update = 0, bytes_solve = 0;
+  // algorithmic flops per kernel class: 0 factor_small, 1 potrf_block, 2 trsm tiles, 3 update tiles 128, 4 update
+  // tiles 64, 5 update_small
+  double class_flops[6] = {0, 0, 0, 0, 0, 0};
   std::string error;
 };
 

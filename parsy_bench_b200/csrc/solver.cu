@@ -25,7 +25,9 @@ struct parsy_cuda_solver {
   int device = 0;
   bool use_graph = true;
   bool has_A = false, factored = false, has_values = false;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_F[2] = {nullptr, nullptr}, ev_R[2] = {nullptr, nullptr};
+  bool lookahead = true;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device arrays
   SupInfo* d_sup = nullptr;
@@ -76,44 +78,121 @@ static int ensure_kernel_attrs() {
 static inline int cdivi(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- launch sequences -----------------------------------------------------------------------------
-static int64_t enqueue_factor_steps(parsy_cuda_solver* s, int step_begin, int step_end) {
+// optional per-launch CUDA-event instrumentation (parsy_cuda_factor_profiled)
+struct LaunchProfiler {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cls;
+  cudaStream_t st = nullptr;
+  void begin(int c) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev.push_back(a); ev.push_back(b); cls.push_back(c); cudaEventRecord(a, st); }
+  void end() { cudaEventRecord(ev.back(), st); }
+};
+#define PROF_BEGIN(c) do { if (prof) prof->begin(c); } while (0)
+#define PROF_END() do { if (prof) prof->end(); } while (0)
+
+static int64_t launch_factor_phase(parsy_cuda_solver* s, const Step& S, cudaStream_t st, LaunchProfiler* prof) {
+  int64_t launches = 0;
+  if (S.small_narrow > 0) {
+    PROF_BEGIN(0);
+    k_factor_small<SMALL_W_NARROW><<<cdivi(S.small_narrow, 4), 128, 0, st>>>(s->d_small_list + S.small_sup.begin,
+                                                                             S.small_narrow, s->d_sup, s->d_lv, s->d_info);
+    PROF_END();
+    ++launches;
+  }
+  if (S.small_sup.size() - S.small_narrow > 0) {
+    PROF_BEGIN(0);
+    const int cnt = S.small_sup.size() - S.small_narrow;
+    k_factor_small<SMALL_W><<<cdivi(cnt, 4), 128, 0, st>>>(s->d_small_list + S.small_sup.begin + S.small_narrow, cnt,
+                                                           s->d_sup, s->d_lv, s->d_info);
+    PROF_END();
+    ++launches;
+  }
+  if (S.blocks.size()) {
+    PROF_BEGIN(1);
+    k_potrf_block<<<S.blocks.size(), POTRF_THREADS, POTRF_SMEM, st>>>(s->d_blocks + S.blocks.begin, s->d_sup, s->d_lv,
+                                                                      s->d_linv, s->d_info);
+    PROF_END();
+    ++launches;
+  }
+  if (S.trsm_tiles) {
+    PROF_BEGIN(2);
+    k_gemm_tiles<Cfg128><<<S.trsm_tiles, Cfg128::THREADS, Cfg128::SMEM, st>>>(s->d_gemm + S.trsm.begin, S.trsm.size(),
+                                                                              s->d_lv, s->d_linv, s->d_rel);
+    PROF_END();
+    ++launches;
+  }
+  return launches;
+}
+
+static int64_t launch_update_group(parsy_cuda_solver* s, const UpdGroup& U, cudaStream_t st, LaunchProfiler* prof) {
+  int64_t launches = 0;
+  if (U.tiles128) {
+    PROF_BEGIN(3);
+    k_gemm_tiles<Cfg128><<<U.tiles128, Cfg128::THREADS, Cfg128::SMEM, st>>>(s->d_gemm + U.u128.begin, U.u128.size(),
+                                                                            s->d_lv, s->d_linv, s->d_rel);
+    PROF_END();
+    ++launches;
+  }
+  if (U.tiles64) {
+    PROF_BEGIN(4);
+    k_gemm_tiles<Cfg64><<<U.tiles64, Cfg64::THREADS, Cfg64::SMEM, st>>>(s->d_gemm + U.u64.begin, U.u64.size(), s->d_lv,
+                                                                        s->d_linv, s->d_rel);
+    PROF_END();
+    ++launches;
+  }
+  if (U.small_narrow > 0) {
+    PROF_BEGIN(5);
+    k_update_small<4><<<cdivi(U.small_narrow, 4), 128, 0, st>>>(s->d_small_tasks + U.small.begin, U.small_narrow,
+                                                                s->d_gemm, s->d_lv, s->d_rel);
+    PROF_END();
+    ++launches;
+  }
+  if (U.small.size() - U.small_narrow > 0) {
+    PROF_BEGIN(5);
+    const int cnt = U.small.size() - U.small_narrow;
+    k_update_small<32><<<cdivi(cnt, 4), 128, 0, st>>>(s->d_small_tasks + U.small.begin + U.small_narrow, cnt, s->d_gemm,
+                                                      s->d_lv, s->d_rel);
+    PROF_END();
+    ++launches;
+  }
+  return launches;
+}
+
+// Steps [step_begin, step_end) of the factorization.
+//   single stream (profiling):  F_s, A_s, R_s in order.
+//   two streams (default):      side: F_s, A_s  |  main: R_s
+//     F_s  = factor the supernodes / block columns of step s (POTRF + TRSM)
+//     A_s  = updates from step-s panels into targets factored at step s+1
+//     R_s  = the remaining updates (targets at steps >= s+2) — red.global.add, so they commute with A_{s+1}
+//   F_{s+1} needs A_s (same stream) and R_{s-1} (event); R_s needs F_s (event).  The bulk trailing update R_s thus
+//   overlaps the latency-bound POTRF/TRSM of the next block column (look-ahead of depth one).
+static int64_t enqueue_factor_steps(parsy_cuda_solver* s, int step_begin, int step_end, LaunchProfiler* prof = nullptr) {
   int64_t launches = 0;
   const Plan& P = s->plan;
-  cudaStream_t st = s->stream;
+  cudaStream_t mainst = s->stream;
+  if (step_end <= step_begin) return 0;
+  if (prof || !s->lookahead) {
+    for (int i = step_begin; i < step_end; ++i) {
+      launches += launch_factor_phase(s, P.steps[i], mainst, prof);
+      launches += launch_update_group(s, P.steps[i].upd[0], mainst, prof);
+      launches += launch_update_group(s, P.steps[i].upd[1], mainst, prof);
+    }
+    return launches;
+  }
+  cudaStream_t side = s->stream2;
+  cudaEventRecord(s->ev_fork, mainst);
+  cudaStreamWaitEvent(side, s->ev_fork, 0);
   for (int i = step_begin; i < step_end; ++i) {
     const Step& S = P.steps[i];
-    if (S.small_sup.size()) {
-      k_factor_small<<<cdivi(S.small_sup.size(), 4), 128, 0, st>>>(s->d_small_list + S.small_sup.begin,
-                                                                   S.small_sup.size(), s->d_sup, s->d_lv, s->d_info);
-      ++launches;
-    }
-    if (S.blocks.size()) {
-      k_potrf_block<<<S.blocks.size(), POTRF_THREADS, POTRF_SMEM, st>>>(s->d_blocks + S.blocks.begin, s->d_sup, s->d_lv,
-                                                                  s->d_linv, s->d_info);
-      ++launches;
-    }
-    if (S.trsm_tiles) {
-      k_gemm_tiles<Cfg128><<<S.trsm_tiles, Cfg128::THREADS, Cfg128::SMEM, st>>>(s->d_gemm + S.trsm.begin, S.trsm.size(),
-                                                                                s->d_lv, s->d_linv, s->d_rel);
-      ++launches;
-    }
-    if (S.upd128_tiles) {
-      k_gemm_tiles<Cfg128><<<S.upd128_tiles, Cfg128::THREADS, Cfg128::SMEM, st>>>(s->d_gemm + S.upd128.begin,
-                                                                                  S.upd128.size(), s->d_lv, s->d_linv,
-                                                                                  s->d_rel);
-      ++launches;
-    }
-    if (S.upd64_tiles) {
-      k_gemm_tiles<Cfg64><<<S.upd64_tiles, Cfg64::THREADS, Cfg64::SMEM, st>>>(s->d_gemm + S.upd64.begin, S.upd64.size(),
-                                                                              s->d_lv, s->d_linv, s->d_rel);
-      ++launches;
-    }
-    if (S.small_upd.size()) {
-      k_update_small<<<cdivi(S.small_upd.size(), 4), 128, 0, st>>>(s->d_small_tasks + S.small_upd.begin,
-                                                                   S.small_upd.size(), s->d_gemm, s->d_lv, s->d_rel);
-      ++launches;
-    }
+    if (i - 2 >= step_begin) cudaStreamWaitEvent(side, s->ev_R[(i - 1) & 1], 0);   // F_i needs R_{i-2} (and all before it)
+    launches += launch_factor_phase(s, S, side, nullptr);
+    cudaEventRecord(s->ev_F[i & 1], side);
+    launches += launch_update_group(s, S.upd[0], side, nullptr);
+    cudaStreamWaitEvent(mainst, s->ev_F[i & 1], 0);
+    launches += launch_update_group(s, S.upd[1], mainst, nullptr);
+    cudaEventRecord(s->ev_R[(i + 1) & 1], mainst);   // consumed by F_{i+2}: slot (i+2-1)&1 == (i+1)&1
   }
+  cudaEventRecord(s->ev_join, side);
+  cudaStreamWaitEvent(mainst, s->ev_join, 0);
   return launches;
 }
 
@@ -192,6 +271,8 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
                   s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {s->ev_fork, s->ev_join, s->ev_F[0], s->ev_F[1], s->ev_R[0], s->ev_R[1]}) if (e) cudaEventDestroy(e);
+  if (s->stream2) cudaStreamDestroy(s->stream2);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -231,6 +312,15 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
 #define TRY(x) do { rc = (x); if (rc) { parsy_cuda_destroy(s); return rc; } } while (0)
 #define TRYCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { parsy_cuda_destroy(s); return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
   TRYCU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  {
+    // the latency-critical chain (POTRF/TRSM of the next block column) must win SM slots against the bulk update
+    int lo = 0, hi = 0;
+    TRYCU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TRYCU(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, hi));
+  }
+  for (cudaEvent_t* e : {&s->ev_fork, &s->ev_join, &s->ev_F[0], &s->ev_F[1], &s->ev_R[0], &s->ev_R[1]})
+    TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  s->lookahead = o.reserved[0] == 0;   // reserved[0] = 1 disables the two-stream look-ahead
   for (auto& e : s->ev) TRYCU(cudaEventCreate(&e));
   TRY(dev_upload(s, &s->d_sup, P.sup.data(), P.sup.size()));
   TRY(dev_upload(s, &s->d_lR, lR, (size_t)P.ssize));
@@ -346,6 +436,39 @@ extern "C" int parsy_cuda_factor(parsy_cuda_solver* s) {
   CU(cudaGetLastError());
   s->factored = true;
   s->timed = true;
+  return PARSY_CUDA_OK;
+}
+
+// One factorization without CUDA graphs, every launch bracketed by CUDA events on the solver's stream.
+// class_ms[6] / class_launches[6] / class_flops[6]: 0 factor_small, 1 potrf_block, 2 trsm tiles (DMMA), 3 update
+// tiles 128 (DMMA), 4 update tiles 64 (DMMA), 5 update_small.
+extern "C" int parsy_cuda_factor_profiled(parsy_cuda_solver* s, double* class_ms, int64_t* class_launches,
+                                          double* class_flops) {
+  if (!s || !class_ms || !class_launches || !class_flops) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  if (!s->has_A || !s->has_values) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
+  CU(cudaSetDevice(s->device));
+  const Plan& P = s->plan;
+  cudaStream_t st = s->stream;
+  CU(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
+  CU(cudaMemsetAsync(s->d_lv, 0, sizeof(double) * (size_t)P.xsize, st));
+  if (P.nnzA > 0) {
+    const int grid = (int)std::min<int64_t>((P.nnzA + 255) / 256, 148 * 16);
+    k_assemble<<<grid, 256, 0, st>>>(P.nnzA, s->d_apos, s->d_vals, s->d_lv);
+  }
+  LaunchProfiler prof;
+  prof.st = st;
+  enqueue_factor_steps(s, 0, (int)P.steps.size(), &prof);
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  for (int c = 0; c < 6; ++c) { class_ms[c] = 0; class_launches[c] = 0; class_flops[c] = P.class_flops[c]; }
+  for (size_t i = 0; i < prof.cls.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
+    class_ms[prof.cls[i]] += ms;
+    class_launches[prof.cls[i]]++;
+    cudaEventDestroy(prof.ev[2 * i]); cudaEventDestroy(prof.ev[2 * i + 1]);
+  }
+  s->factored = true;
   return PARSY_CUDA_OK;
 }
 

@@ -306,6 +306,19 @@ class Solver:
         self._call("parsy_cuda_factor_times", t.ctypes.data_as(c_void_p))
         return {"levels": t[0], "last_level": t[1], "assemble": t[2]}
 
+    KERNEL_CLASSES = ("factor_small", "potrf_block", "trsm_tiles_dmma", "update_tiles128_dmma", "update_tiles64_dmma",
+                      "update_small")
+
+    def factor_profiled(self):
+        """One event-instrumented factorization (no graphs): {class: (ms, launches, algorithmic flops)}."""
+        ms = np.zeros(6, np.float64)
+        nl = np.zeros(6, np.int64)
+        fl = np.zeros(6, np.float64)
+        self._call("parsy_cuda_factor_profiled", ms.ctypes.data_as(c_void_p), nl.ctypes.data_as(c_void_p),
+                   fl.ctypes.data_as(c_void_p))
+        return {k: {"ms": float(ms[i]), "launches": int(nl[i]), "flops": float(fl[i])}
+                for i, k in enumerate(self.KERNEL_CLASSES)}
+
     def stats(self):
         st = Stats()
         f = self._L.parsy_cuda_get_stats
