@@ -809,6 +809,246 @@ __global__ void __launch_bounds__(128) k_bwd_block_diag(const BlockTask* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// single-launch dataflow sweeps
+//
+// One launch per sweep. CTAs take tickets (atomic counter) and walk the solve tasks in dependency order, so every
+// producer of a task holds a smaller ticket and is already running: spinning on its counter cannot deadlock.
+// forward : node ready  <=> done[node] == need[node]  (every task that adds into its right-hand side has finished)
+// backward: task ready  <=> solved[u] != 0 for every node u its rows belong to;  the last slice of a block column
+//           to finish its partial L21' x does the diagonal solve and publishes solved[node].
+// Right-hand-side entries are only ever modified by L2 atomics and read with ld.global.cg after an acquire.
+// Everything that does not depend on the right-hand side (the slice of L, the diagonal block of a narrow
+// supernode) is pulled into registers BEFORE the task waits for its inputs: the dependency chain then only
+// carries the arithmetic, not the HBM latency.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until_ge_busy(const int* p, int target) {
+  while (ld_acquire_gpu(p) < target) {}
+}
+
+constexpr int SWEEP_THREADS = 256;
+
+__global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
+    const SolveCta* __restrict__ ctas, const SolveTask* __restrict__ tasks, const int* __restrict__ targets,
+    const int* __restrict__ need, int* __restrict__ done, int* __restrict__ ticket, const SupInfo* __restrict__ sup,
+    const int* __restrict__ lR, const double* __restrict__ lv, const double* __restrict__ linv,
+    double* __restrict__ y, double* __restrict__ xs) {
+  __shared__ int s_cta;
+  __shared__ double sy[NB_MAX], sx[NB_MAX], spart[SWEEP_THREADS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cta = atomicAdd(ticket, 1);
+  __syncthreads();
+  const SolveCta C = ctas[s_cta];
+  if (C.kind == 0) {
+    if (warp >= C.count) return;
+    const SolveTask T = tasks[C.first + warp];
+    const SupInfo I = sup[T.sup];
+    const int w = I.w, r = I.r;
+    const double* __restrict__ P = lv + I.valptr;
+    double lrow[SMALL_W];   // L(lane, c), c <= lane
+#pragma unroll
+    for (int c = 0; c < SMALL_W; ++c) lrow[c] = (c < w && lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 1.0;
+    if (lane == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
+    __syncwarp();
+    double xv = (lane < w) ? __ldcg(&y[I.col0 + lane]) : 0.0;
+#pragma unroll
+    for (int c = 0; c < SMALL_W; ++c) {
+      if (c < w) {
+        const double xc = __shfl_sync(0xffffffffu, xv, c) / __shfl_sync(0xffffffffu, lrow[c], c);
+        if (lane == c) xv = xc;
+        else if (lane > c && lane < w) xv = fma(-lrow[c], xc, xv);
+      }
+    }
+    if (lane < w) xs[I.col0 + lane] = xv;
+    const int* __restrict__ rows = lR + I.rowptr;
+    for (int i0 = w; i0 < r; i0 += 32) {
+      const int i = i0 + lane;
+      double t = 0.0;
+      for (int c = 0; c < w; ++c) {
+        const double xc = __shfl_sync(0xffffffffu, xv, c);
+        if (i < r) t = fma(P[(int64_t)c * r + i], xc, t);
+      }
+      if (i < r) atomicAdd(&y[rows[i]], -t);
+    }
+    __threadfence();
+    __syncwarp();
+    for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) atomicAdd(&done[targets[q]], 1);
+    return;
+  }
+  const SolveTask T = tasks[C.first];
+  const SupInfo I = sup[T.sup];
+  const int nb = T.nb, r = I.r, cbase = I.col0 + T.j0;
+  // slice of L21: row ri, columns cg*32 .. cg*32+31, loaded ahead of the wait
+  const int ri = tid & 63, cg = tid >> 6;
+  double lval[32];
+  int myrow = -1;
+  {
+    const double* __restrict__ P = lv + I.valptr + (int64_t)T.j0 * r + T.row0;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int c = cg * 32 + u;
+      lval[u] = (ri < T.nrows && c < nb) ? P[(int64_t)c * r + ri] : 0.0;
+    }
+    if (cg == 0 && ri < T.nrows) myrow = lR[I.rowptr + T.row0 + ri];
+  }
+  const double* __restrict__ X = linv + (int64_t)T.slot * NB_MAX * NB_MAX;
+  if (tid == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
+  __syncthreads();
+  if (tid < nb) sy[tid] = __ldcg(&y[cbase + tid]);
+  __syncthreads();
+  // x_b = inv(L_bb) y_b, recomputed by every slice (an extra flag hop would sit on the critical path):
+  // row i = tid & 127, the two halves of the block split k
+  const int i = tid & 127, half = tid >> 7;
+  {
+    double acc0 = 0.0, acc1 = 0.0;
+    if (i < nb) {
+      const int kend = min(i + 1, half ? nb : 64);
+      int k = half * 64;
+#pragma unroll 8
+      for (; k + 1 < kend; k += 2) {
+        acc0 = fma(X[k * NB_MAX + i], sy[k], acc0);
+        acc1 = fma(X[(k + 1) * NB_MAX + i], sy[k + 1], acc1);
+      }
+      if (k < kend) acc0 = fma(X[k * NB_MAX + i], sy[k], acc0);
+    }
+    spart[tid] = acc0 + acc1;
+  }
+  __syncthreads();
+  if (tid < NB_MAX) {   // entries past nb are multiplied by zero-filled lval: they must be zeros, not stale smem
+    const double v = (tid < nb) ? spart[tid] + spart[tid + 128] : 0.0;
+    sx[tid] = v;
+    if (T.first && tid < nb) xs[cbase + tid] = v;
+  }
+  __syncthreads();
+  if (T.nrows > 0) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int u = 0; u < 32; u += 2) {
+      t0 = fma(lval[u], sx[(cg * 32 + u) & (NB_MAX - 1)], t0);
+      t1 = fma(lval[u + 1], sx[(cg * 32 + u + 1) & (NB_MAX - 1)], t1);
+    }
+    spart[tid] = t0 + t1;
+    __syncthreads();
+    if (tid < 64 && myrow >= 0) atomicAdd(&y[myrow], -(spart[tid] + spart[tid + 64] + spart[tid + 128] + spart[tid + 192]));
+    __threadfence();
+    __syncthreads();
+    for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) atomicAdd(&done[targets[q]], 1);
+  }
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS) k_bwd_dataflow(
+    const SolveCta* __restrict__ ctas, int nctas, const SolveTask* __restrict__ tasks,
+    const int* __restrict__ targets, const int* __restrict__ ntiles, int* __restrict__ cnt, int* __restrict__ solved,
+    int* __restrict__ ticket, const SupInfo* __restrict__ sup, const int* __restrict__ lR,
+    const double* __restrict__ lv, const double* __restrict__ linv, double* __restrict__ x) {
+  __shared__ int s_cta, s_last;
+  __shared__ double sx[SOLVE_TILE_ROWS], sy[NB_MAX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cta = nctas - 1 - atomicAdd(ticket, 1);
+  __syncthreads();
+  const SolveCta C = ctas[s_cta];
+  if (C.kind == 0) {
+    if (warp >= C.count) return;
+    const SolveTask T = tasks[C.first + warp];
+    const SupInfo I = sup[T.sup];
+    const int w = I.w, r = I.r;
+    const double* __restrict__ P = lv + I.valptr;
+    const int* __restrict__ rows = lR + I.rowptr;
+    double lrow[SMALL_W];   // L(lane, c), c <= lane
+#pragma unroll
+    for (int c = 0; c < SMALL_W; ++c) lrow[c] = (c < w && lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 0.0;
+    for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) spin_until_ge_busy(&solved[targets[q]], 1);
+    __syncwarp();
+    double mine = (lane < w) ? __ldcg(&x[I.col0 + lane]) : 0.0;
+    // t_c = sum_i L(i,c) x[rows[i]]: every lane gathers its rows once, then one shuffle reduction per column
+    for (int i0 = w; i0 < r; i0 += 32) {
+      const int ii = i0 + lane;
+      const double xr = (ii < r) ? __ldcg(&x[rows[ii]]) : 0.0;
+      for (int c = 0; c < w; ++c) {
+        double part = (ii < r) ? P[(int64_t)c * r + ii] * xr : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == c) mine -= part;
+      }
+    }
+#pragma unroll
+    for (int c = SMALL_W - 1; c >= 0; --c) {
+      if (c < w) {
+        double part = (lane > c && lane < w) ? lrow[c] * mine : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const double d = __shfl_sync(0xffffffffu, lrow[c], c);
+        if (lane == c) mine = (mine - part) / d;
+      }
+    }
+    if (lane < w) x[I.col0 + lane] = mine;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(&solved[T.node], 1);
+    return;
+  }
+  const SolveTask T = tasks[C.first];
+  const SupInfo I = sup[T.sup];
+  const int nb = T.nb, r = I.r, cbase = I.col0 + T.j0;
+  // slice of L21 ahead of the wait: warp w owns columns w, w+8, ...; lanes own rows lane, lane+32
+  double lval[16][2];
+  {
+    const double* __restrict__ P = lv + I.valptr + (int64_t)T.j0 * r + T.row0;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = warp + 8 * u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ii = lane + 32 * h;
+        lval[u][h] = (c < nb && ii < T.nrows) ? P[(int64_t)c * r + ii] : 0.0;
+      }
+    }
+  }
+  int myrow = -1;
+  if (tid < T.nrows) myrow = lR[I.rowptr + T.row0 + tid];
+  for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) spin_until_ge_busy(&solved[targets[q]], 1);
+  __syncthreads();
+  if (T.nrows > 0) {
+    if (tid < SOLVE_TILE_ROWS) sx[tid] = (myrow >= 0) ? __ldcg(&x[myrow]) : 0.0;
+    __syncthreads();
+    const double x0 = sx[lane], x1 = sx[lane + 32];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = warp + 8 * u;
+      double part = fma(lval[u][0], x0, lval[u][1] * x1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0 && c < nb) atomicAdd(&x[cbase + c], -part);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&cnt[T.node], 1) == ntiles[T.node] - 1);
+  __syncthreads();
+  if (!s_last) return;
+  // every slice has added its partial: x_b = inv(L_bb)' x_b, one warp per column of the inverse
+  __threadfence();
+  if (tid < nb) sy[tid] = __ldcg(&x[cbase + tid]);
+  __syncthreads();
+  const double* __restrict__ X = linv + (int64_t)T.slot * NB_MAX * NB_MAX;
+  for (int c = warp; c < nb; c += SWEEP_THREADS / 32) {
+    double part = 0.0;
+#pragma unroll 4
+    for (int k = c + lane; k < nb; k += 32) part = fma(X[c * NB_MAX + k], sy[k], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) x[cbase + c] = part;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) atomicExch(&solved[T.node], 1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // column (CSC) forward solve, one level per launch: warp per column            (Triangular_CSC.h:50-71)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_csc_level(const int* __restrict__ cols, int count, const int* __restrict__ Lp,

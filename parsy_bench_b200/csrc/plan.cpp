@@ -298,6 +298,62 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     }
     S.solve_tiles = acc;
   }
+  // ---- dataflow sweeps: nodes, tasks in dependency order, target lists, counters ------------------------------
+  {
+    std::vector<int32_t> node_first(supNo + 1, 0);
+    for (int s = 0; s < supNo; ++s) node_first[s + 1] = node_first[s] + nblk[s];
+    P.n_nodes = node_first[supNo];
+    auto node_of_row = [&](int row) {
+      const int t = col2Sup[row];
+      return P.sup[t].flags ? node_first[t] : node_first[t] + (row - P.sup[t].col0) / NB;
+    };
+    P.node_need.assign(P.n_nodes, 0);
+    P.node_tiles.assign(P.n_nodes, 1);
+    auto add_targets = [&](SolveTask& t, const SupInfo& I) {
+      t.tgt_begin = (int32_t)P.solve_targets.size();
+      int last = -1;
+      for (int i = t.row0; i < t.row0 + t.nrows; ++i) {
+        const int nd = node_of_row(lR[I.rowptr + i]);
+        if (nd != last) { P.solve_targets.push_back(nd); P.node_need[nd]++; last = nd; }
+      }
+      t.tgt_end = (int32_t)P.solve_targets.size();
+    };
+    for (int st = 0; st < nsteps; ++st) {
+      const Step& S = P.steps[st];
+      // narrow supernodes, eight per CTA
+      for (int i0 = S.small_sup.begin; i0 < S.small_sup.end; i0 += 8) {
+        SolveCta c; c.kind = 0; c.first = (int32_t)P.solve_tasks.size(); c.count = std::min(8, S.small_sup.end - i0); c.pad = 0;
+        for (int i = i0; i < i0 + c.count; ++i) {
+          const int s = P.small_list[i];
+          const SupInfo& I = P.sup[s];
+          SolveTask t; memset(&t, 0, sizeof(t));
+          t.sup = s; t.node = node_first[s]; t.j0 = 0; t.nb = I.w; t.slot = -1; t.row0 = I.w; t.nrows = I.r - I.w; t.first = 1;
+          add_targets(t, I);
+          P.solve_tasks.push_back(t);
+        }
+        P.solve_ctas.push_back(c);
+      }
+      for (int i = S.blocks.begin; i < S.blocks.end; ++i) {
+        const BlockTask& b = P.block_tasks[i];
+        const SupInfo& I = P.sup[b.sup];
+        const int below = I.r - b.j0 - b.nb;
+        const int ntile = std::max(1, cdiv(below, SOLVE_TILE_ROWS));
+        const int nd = node_first[b.sup] + b.j0 / NB;
+        P.node_tiles[nd] = ntile;
+        for (int k = 0; k < ntile; ++k) {
+          SolveTask t; memset(&t, 0, sizeof(t));
+          t.sup = b.sup; t.node = nd; t.j0 = b.j0; t.nb = b.nb; t.slot = b.slot;
+          t.row0 = b.j0 + b.nb + k * SOLVE_TILE_ROWS;
+          t.nrows = std::max(0, std::min(SOLVE_TILE_ROWS, I.r - t.row0));
+          t.first = k == 0;
+          add_targets(t, I);
+          SolveCta c; c.kind = 1; c.first = (int32_t)P.solve_tasks.size(); c.count = 1; c.pad = 0;
+          P.solve_tasks.push_back(t);
+          P.solve_ctas.push_back(c);
+        }
+      }
+    }
+  }
   return PARSY_CUDA_OK;
 }
 

@@ -70,6 +70,29 @@ struct BlockTask {
 static_assert(sizeof(BlockTask) == 32, "BlockTask layout");
 
 // Pair before classification (also used by the tests to compare against ereach_sn).
+// ---- single-launch dataflow sweeps -------------------------------------------------------------------
+// A "node" is what gets solved as one unit: a narrow supernode or one block column.  A "solve task" is what one
+// warp (narrow supernode) or one CTA (128-row slice of a block column's rows below the diagonal block) does.
+constexpr int SOLVE_TILE_ROWS = 64;
+struct SolveTask {
+  int32_t sup;        // supernode
+  int32_t node;       // node this task belongs to (the one whose solution it consumes)
+  int32_t j0, nb;     // block column (narrow supernode: 0, width)
+  int32_t slot;       // inverse-diagonal-block slot (-1 for narrow supernodes)
+  int32_t row0;       // first local row of the slice (narrow: width)
+  int32_t nrows;      // rows in the slice (may be 0: a block column with nothing below it)
+  int32_t first;      // 1 = this task publishes the node's solution (slice 0)
+  int32_t tgt_begin, tgt_end;   // range in solve_targets: nodes whose unknowns this task's rows touch
+  int32_t pad[2];
+};
+static_assert(sizeof(SolveTask) == 48, "SolveTask layout");
+struct SolveCta {     // work of one CTA of the sweep kernel
+  int32_t kind;       // 0 = up to 8 narrow supernodes (one per warp), 1 = one slice
+  int32_t first;      // index of the first SolveTask
+  int32_t count;
+  int32_t pad;
+};
+
 struct PairDesc {
   int32_t tgt, src;  // supernodes
   int32_t lb;        // first row (index in src's row list) that falls inside tgt's columns
@@ -126,6 +149,13 @@ struct Plan {
   std::vector<int32_t> rel_pair_tgt;        // per rel-pair: target supernode
   std::vector<int32_t> rel_pair_lb;         // per rel-pair: lb
   int64_t rel_entries = 0;
+  // dataflow sweeps
+  int32_t n_nodes = 0;
+  std::vector<SolveTask> solve_tasks;      // forward order (dependency steps ascending)
+  std::vector<SolveCta> solve_ctas;        // forward order; the backward sweep walks it in reverse
+  std::vector<int32_t> solve_targets;      // node ids
+  std::vector<int32_t> node_need;          // forward: number of tasks that add into the node's right-hand side
+  std::vector<int32_t> node_tiles;         // backward: number of slices of the node (narrow supernodes: 1)
   int32_t n_slots = 0;
   int64_t n_pairs = 0, n_pairs_small = 0, n_pairs_tiled = 0, n_block_cols = 0;
   double flops_potrf = 0, flops_trsm = 0, flops_update = 0, bytes_solve = 0;

@@ -44,6 +44,14 @@ struct parsy_cuda_solver {
   double* d_rhs = nullptr;
   double* d_xs = nullptr;
   int* d_info = nullptr;
+  // dataflow sweeps
+  SolveTask* d_stasks = nullptr;
+  SolveCta* d_sctas = nullptr;
+  int* d_stargets = nullptr;
+  int* d_need = nullptr;
+  int* d_ntiles = nullptr;
+  int* d_sync = nullptr;      // [ticket | done or cnt (n_nodes) | solved (n_nodes)]
+  bool dataflow = true;
   int64_t device_bytes = 0;
   cudaGraphExec_t g_levels = nullptr, g_last = nullptr, g_fwd = nullptr, g_bwd = nullptr;
   int64_t launches_factor = 0, launches_fwd = 0, launches_bwd = 0;
@@ -200,6 +208,15 @@ static int64_t enqueue_fwd(parsy_cuda_solver* s) {
   int64_t launches = 0;
   const Plan& P = s->plan;
   cudaStream_t st = s->stream;
+  if (s->dataflow) {
+    if (P.solve_ctas.empty()) return 0;
+    cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 1), st);
+    k_fwd_dataflow<<<(int)P.solve_ctas.size(), SWEEP_THREADS, 0, st>>>(s->d_sctas, s->d_stasks, s->d_stargets, s->d_need,
+                                                                       s->d_sync + 1, s->d_sync, s->d_sup, s->d_lR, s->d_lv,
+                                                                       s->d_linv, s->d_rhs, s->d_xs);
+    cudaMemcpyAsync(s->d_rhs, s->d_xs, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToDevice, st);
+    return 1;
+  }
   for (size_t i = 0; i < P.steps.size(); ++i) {
     const Step& S = P.steps[i];
     if (S.small_sup.size()) {
@@ -221,6 +238,15 @@ static int64_t enqueue_bwd(parsy_cuda_solver* s) {
   int64_t launches = 0;
   const Plan& P = s->plan;
   cudaStream_t st = s->stream;
+  if (s->dataflow) {
+    if (P.solve_ctas.empty()) return 0;
+    cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 1), st);
+    k_bwd_dataflow<<<(int)P.solve_ctas.size(), SWEEP_THREADS, 0, st>>>(s->d_sctas, (int)P.solve_ctas.size(), s->d_stasks,
+                                                                       s->d_stargets, s->d_ntiles, s->d_sync + 1,
+                                                                       s->d_sync + 1 + P.n_nodes, s->d_sync, s->d_sup, s->d_lR,
+                                                                       s->d_lv, s->d_linv, s->d_rhs);
+    return 1;
+  }
   for (int i = (int)P.steps.size() - 1; i >= 0; --i) {
     const Step& S = P.steps[i];
     if (S.blocks.size()) {
@@ -268,7 +294,8 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
   if (s->g_fwd) cudaGraphExecDestroy(s->g_fwd);
   if (s->g_bwd) cudaGraphExecDestroy(s->g_bwd);
   void* ptrs[] = {s->d_sup, s->d_lR, s->d_small_list, s->d_blocks, s->d_gemm, s->d_small_tasks, s->d_rel, s->d_apos,
-                  s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info};
+                  s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info, s->d_stasks, s->d_sctas, s->d_stargets,
+                  s->d_need, s->d_ntiles, s->d_sync};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {s->ev_fork, s->ev_join, s->ev_F[0], s->ev_F[1], s->ev_R[0], s->ev_R[1]}) if (e) cudaEventDestroy(e);
@@ -333,6 +360,13 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
   TRY(dev_alloc(s, &s->d_rhs, (size_t)n));
   TRY(dev_alloc(s, &s->d_xs, (size_t)n));
   TRY(dev_alloc(s, &s->d_info, 1));
+  TRY(dev_upload(s, &s->d_stasks, P.solve_tasks.data(), P.solve_tasks.size()));
+  TRY(dev_upload(s, &s->d_sctas, P.solve_ctas.data(), P.solve_ctas.size()));
+  TRY(dev_upload(s, &s->d_stargets, P.solve_targets.data(), P.solve_targets.size()));
+  TRY(dev_upload(s, &s->d_need, P.node_need.data(), P.node_need.size()));
+  TRY(dev_upload(s, &s->d_ntiles, P.node_tiles.data(), P.node_tiles.size()));
+  TRY(dev_alloc(s, &s->d_sync, (size_t)2 * P.n_nodes + 1));
+  s->dataflow = o.reserved[1] == 0;   // reserved[1] = 1: one launch per dependency step instead
   TRYCU(cudaMemset(s->d_info, 0, sizeof(int)));
   TRYCU(cudaMemset(s->d_linv, 0, std::max<size_t>((size_t)P.n_slots * NB_MAX * NB_MAX, 1) * 8));
   // the blocking uploads above ran on the legacy stream; the solver's stream is non-blocking, so order them explicitly
