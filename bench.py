@@ -170,6 +170,106 @@ def reference_arm(args, kind, N, desc):
     return 0
 
 
+def sharded_arm(args, kind, N, desc, rank, world, local):
+    """N > 1: ONE factorization sharded over the GPUs (strong scaling): owned bottom subtrees -> NCCL broadcast of the
+    owners' panels over NVLink -> shared top on every rank.  SpTRSV is not sharded (replicas only)."""
+    import torch
+    import torch.distributed as dist
+    from parsy_bench_b200 import inspector, matrices
+    from parsy_bench_b200.sharded import ShardedCholesky
+
+    n, Ap, Ai, Ax = matrices.laplacian(kind, N)
+    t0 = time.time()
+    S = inspector.analyze(n, Ap, Ai, Ax, args.cost, args.level, args.div)
+    t_insp = time.time() - t0
+    t0 = time.time()
+    SC = ShardedCholesky(S, rank, world, local, top_levels=args.top_levels, block_cols=args.block_cols)
+    t_create = time.time() - t0
+    F = S.flops
+    h_vals = torch.from_numpy(S.A2_x.copy()).pin_memory()
+    SC.set_values(h_vals.numpy())
+    st1, st2 = SC.h1.stats(), SC.h2.stats()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        SC.factor(dist)
+    barrier()
+    if not SC.sync():
+        raise SystemExit("factorization failed: matrix not positive definite")
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(SC.s1)
+    for _ in range(args.steps):
+        SC.factor(dist)
+        SC.s1.wait_stream(SC.s2)          # the next step's phase 1 rewrites the shared buffer
+    e1.record(SC.s1)
+    barrier()
+    clocks = sampler.stop()
+    total_ms = e0.elapsed_time(e1)
+    t1 = SC.h1.factor_times()
+    t2 = SC.h2.factor_times()
+    # end to end: A's values from pinned host memory every step, a device->host read of the result's status + tail
+    tail = torch.empty(1024, dtype=torch.float64).pin_memory()
+    barrier()
+    tw = time.perf_counter()
+    for _ in range(args.steps):
+        SC.set_values(h_vals.numpy())
+        SC.factor(dist)
+        ok = SC.sync()
+        tail.copy_(SC.lv[-1024:])
+    barrier()
+    e2e_ms = (time.perf_counter() - tw) * 1e3 / args.steps
+    # parity spot check against the unsharded device factorization of rank 0 is done in tests/; here ||L||_F^2 = tr(A)
+    fro = float((SC.lv * SC.lv).sum().item())
+    trace = float(S.A2_x[S.A2_p[:-1]].sum())
+    prof = SC.h2.factor_profiled() if rank == 0 else None
+    t_loc = torch.tensor([total_ms, e2e_ms, t1["levels"] + t1["last_level"], t2["levels"] + t2["last_level"]],
+                         dtype=torch.float64, device="cuda")
+    dist.all_reduce(t_loc, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, p1_s, p2_s = [float(v) for v in t_loc.tolist()]
+    per_step = total_ms / args.steps
+    if rank == 0:
+        dmma = [k for k in prof if k.endswith("dmma")]
+        dm_ms = sum(prof[k]["ms"] for k in dmma)
+        dm_fl = sum(prof[k]["flops"] for k in dmma)
+        dm_n = sum(prof[k]["launches"] for k in dmma)
+        ach = dm_fl / (dm_ms * 1e-3) / 1e12 if dm_ms > 0 else 0.0
+        line = {
+            "metric": "cholesky_factor_gflops", "value": F / (per_step * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc + " (factorization only at N>1; SpTRSV: replicas only)", "n": n,
+                       "nnzL": int(S.xsize), "flops_sum_cc2": F,
+                       "lbc": {"costParam": args.cost, "levelParam": args.level, "divRate": args.div,
+                               "hlevels": int(S.nLevels), "wpartitions": int(S.nParts)},
+                       "parallelism": f"bottom subtrees sharded over {world} GPUs, {args.top_levels} top H-level(s) replicated; "
+                                      f"{SC.n_broadcasts} NCCL broadcasts per factorization",
+                       "l2": f"working set {8 * S.xsize / 1e6:.0f} MB (factor) > 126 MB L2, no flush needed"},
+            "breakdown_ms": {"phase1_owned_subtrees_max_rank": p1_s * 1e3, "phase2_shared_top": p2_s * 1e3,
+                             "exchange_and_sync": per_step - (p1_s + p2_s) * 1e3,
+                             "exchange_bytes_received_rank0": SC.exchange_bytes},
+            "e2e": {"value": F / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(8 * S.nnzA), "d2h_bytes_per_step": 8 * 1024 + 4,
+                    "api": "ShardedCholesky.set_values (pinned) + factor + sync + read-back of the factor's tail"},
+            "gpu_launches": int(args.steps * (st1["launches_factor"] + st2["launches_factor"])),
+            "roofline": {"bound": "tensor", "kernel": "k_gemm_tiles (FP64 DMMA) in the shared-top phase of rank 0",
+                         "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
+                         "traffic": None, "launches": dm_n,
+                         "whole_factor_frac_of_fp64_peak": F / (per_step * 1e-3) / 1e12 / (FP64_PEAK_TFLOPS * world)},
+            "cpu_baseline": None, "clocks": clocks, "fro2_over_trace": fro / trace, "factor_ok": bool(ok),
+            "setup_s": {"inspector": t_insp, "create": t_create},
+        }
+        print(json.dumps(line))
+    SC.close()
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +282,8 @@ def main():
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--block-cols", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N>1: one full factorization per GPU instead of sharding")
+    ap.add_argument("--top-levels", type=int, default=1, help="N>1: LBC H-levels kept shared (computed by every rank)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     kind, N, desc = CONFIGS[args.config]
@@ -200,6 +302,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    if world > 1 and not args.replicas:
+        return sharded_arm(args, kind, N, desc, rank, world, local)
 
     # ---- setup (untimed): synthetic matrix, host inspector, device-resident structure -------------------------
     n, Ap, Ai, Ax = matrices.laplacian(kind, N)

@@ -112,7 +112,7 @@ typedef struct parsy_cuda_options {
   int ignore_hlevels;  /* 1 = schedule by etree dependencies only, not by LBC H-level barriers     */
   int rank;            /* multi-GPU: this process' rank ...                                        */
   int world;           /* ... of `world` ranks (0/1 = single GPU)                                  */
-  int reserved[10];
+  int reserved[10];    /* [0]=1 no look-ahead stream, [1]=1 per-step sweeps, [2] phase, [3] top H-levels kept shared */
 } parsy_cuda_options;
 
 /* Builds the device-resident symbolic state from the inspector's arrays (all HOST pointers, copied):
@@ -187,11 +187,22 @@ double* parsy_cuda_device_rhs(parsy_cuda_solver* s);      /* n doubles     */
 double* parsy_cuda_device_values(parsy_cuda_solver* s);   /* nnzA doubles  */
 void* parsy_cuda_stream(parsy_cuda_solver* s);            /* cudaStream_t  */
 
-/* Multi-GPU: exchange hooks. With world > 1 each rank factors the subtrees it owns; before the shared
- * top of the tree every rank needs the panels of the others. The library exposes the ownership map and
- * the panel ranges so the host (torch.distributed / NCCL) moves them; see DESIGN.md (e). */
+/* Multi-GPU sharding (one process per GPU).  The bottom of the tree — every LBC H-level except the
+ * last options.reserved[3] (default 1) — is a forest of subtrees; they are dealt to the ranks in contiguous column order,
+ * balanced by cost, and need no communication.  Each rank creates two handles on the same arrays:
+ *   phase 1 (options.world = G, options.rank = r, options.reserved[2] = 1): zero + scatter A + the subtrees rank r owns
+ *   phase 2 (… reserved[2] = 2): the shared top, with every update into it — run after the exchange, on every rank
+ * Between the phases the host moves the owners' panels over NVLink: parsy_cuda_owned_ranges() lists, for any rank, the
+ * contiguous runs of lValues it owns (broadcast them from that rank with NCCL / torch.distributed on
+ * parsy_cuda_device_factor()).  parsy_cuda_adopt_factor() lets the phase-2 handle work on the phase-1 handle's buffer. */
 int parsy_cuda_owned_ranges(parsy_cuda_solver* s, int rank, int64_t* begin_end_pairs, int max_pairs);
-int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase);   /* 0 = owned subtrees, 1 = shared top */
+/* HOST-ONLY twin (no device): plans for `world` ranks and returns the runs owned by `for_rank`; -1 on error. */
+int parsy_cuda_plan_owned_ranges(int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
+                                 int supNo, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                                 const int* partition, int world, int top_levels, int for_rank,
+                                 int64_t* begin_end_pairs, int max_pairs);
+int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase);   /* checks that the handle was planned for `phase` */
+int parsy_cuda_adopt_factor(parsy_cuda_solver* s, parsy_cuda_solver* src);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,9 @@ class Stats(ctypes.Structure):
                [("device_bytes", ctypes.c_int64), ("reserved", ctypes.c_int64 * 8)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["reserved"] = list(self.reserved)
+        return d
 
 
 def lib():

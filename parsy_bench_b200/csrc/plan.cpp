@@ -111,6 +111,50 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     P.hlevel_first_step[nLevels] = nsteps;
   }
 
+  // ---- ownership for the sharded factorization ----------------------------------------------------------
+  P.owner.assign(supNo, opt.world > 1 ? -1 : 0);
+  if (opt.world > 1) {
+    const int first_top = std::max(0, nLevels - std::max(1, opt.top_levels));
+    std::vector<int32_t> par(supNo, -1), root(supNo, -1);
+    for (int s = 0; s < supNo; ++s) {
+      const SupInfo& I = P.sup[s];
+      if (I.r > I.w) par[s] = col2Sup[lR[I.rowptr + I.w]];   // supernodal etree parent = owner of the first row below
+    }
+    std::vector<double> cost;          // per bottom subtree, in column order of the roots
+    std::vector<int32_t> roots;
+    for (int s = supNo - 1; s >= 0; --s) {
+      if (hl[s] >= first_top) continue;
+      const int p2 = par[s];
+      root[s] = (p2 < 0 || hl[p2] >= first_top) ? s : root[p2];
+    }
+    std::vector<double> rcost(supNo, 0.0);
+    for (int s = 0; s < supNo; ++s)
+      if (root[s] >= 0) rcost[root[s]] += (double)P.sup[s].w * P.sup[s].w * P.sup[s].r;
+    double total = 0;
+    for (int s = 0; s < supNo; ++s) if (root[s] == s) { roots.push_back(s); total += rcost[s]; }
+    std::vector<int32_t> rown(supNo, -1);
+    double acc = 0;
+    for (int s : roots) {
+      // subtree goes to the rank whose cost interval contains its midpoint
+      const double mid = acc + 0.5 * rcost[s];
+      rown[s] = std::min(opt.world - 1, (int)(mid / (total > 0 ? total : 1.0) * opt.world));
+      acc += rcost[s];
+    }
+    for (int s = 0; s < supNo; ++s) if (root[s] >= 0) P.owner[s] = rown[root[s]];
+    for (const PairDesc& q : P.pairs)
+      if (P.owner[q.src] < 0 && P.owner[q.tgt] >= 0) { P.error = "top supernode updates a bottom one"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
+  }
+  auto sup_active = [&](int s) {
+    if (opt.phase == 1) return P.owner[s] == opt.rank;
+    if (opt.phase == 2) return P.owner[s] < 0;
+    return true;
+  };
+  auto pair_active = [&](int src, int tgt) {
+    if (opt.phase == 1) return P.owner[src] == opt.rank && P.owner[tgt] == opt.rank;
+    if (opt.phase == 2) return P.owner[tgt] < 0;
+    return true;
+  };
+
   // ---- update pairs ---------------------------------------------------------------------------------
   for (const PairDesc& q : P.pairs) {
     const double k = P.sup[q.src].w, nd1 = q.nd1, nd3 = q.m - q.nd1;
@@ -132,6 +176,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   // factor-side lists: small supernodes and block columns per step
   std::vector<int32_t> c_small(nsteps, 0), c_blk(nsteps, 0);
   for (int s = 0; s < supNo; ++s) {
+    if (!sup_active(s)) continue;
     if (P.sup[s].flags) { c_small[step0[s]]++; continue; }
     for (int b2 = 0; b2 < nblk[s]; ++b2) c_blk[step0[s] + b2]++;
   }
@@ -163,6 +208,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   int32_t slot = 0;
   for (int s = 0; s < supNo; ++s) {
     const SupInfo& I = P.sup[s];
+    if (!sup_active(s)) continue;
     if (I.flags) {
       P.small_list[o_small[step0[s]] + f_small[step0[s]]++] = s;
       P.class_flops[0] += (double)I.w * I.w * I.w / 3.0 + (double)I.w * I.w * (I.r - I.w);
@@ -220,7 +266,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     t.lda = t.ldb = D.r; t.ldc = T.r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
     P.rel_prefix[pi] = rel; P.rel_pair_src[pi] = q.src; P.rel_pair_tgt[pi] = q.tgt; P.rel_pair_lb[pi] = q.lb;
     rel += q.m;
-    emit_update(t, st, step0[q.tgt] == st + 1 ? 0 : 1, true);
+    if (pair_active(q.src, q.tgt)) emit_update(t, st, step0[q.tgt] == st + 1 ? 0 : 1, true);
   }
   P.rel_prefix[P.pairs.size()] = rel;
   P.rel_entries = rel;

@@ -128,6 +128,11 @@ struct Step {
 struct PlanOptions {
   int nb = 128;
   bool ignore_hlevels = false;
+  // multi-GPU sharding: the bottom of the tree (every H-level but the last `top_levels`) is a forest
+  // of subtrees, dealt to the ranks in contiguous column order balanced by cost; the top is computed by every rank.
+  //   phase 0: everything (single GPU)   phase 1: only what `rank` owns   phase 2: the shared top + every update
+  //   into it (run after the owners' panels have been exchanged)
+  int phase = 0, rank = 0, world = 1, top_levels = 1;
 };
 
 struct Plan {
@@ -149,6 +154,7 @@ struct Plan {
   std::vector<int32_t> rel_pair_tgt;        // per rel-pair: target supernode
   std::vector<int32_t> rel_pair_lb;         // per rel-pair: lb
   int64_t rel_entries = 0;
+  std::vector<int32_t> owner;               // per supernode: owning rank, -1 = shared top (world > 1 only)
   // dataflow sweeps
   int32_t n_nodes = 0;
   std::vector<SolveTask> solve_tasks;      // forward order (dependency steps ascending)

@@ -28,6 +28,8 @@ struct parsy_cuda_solver {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_F[2] = {nullptr, nullptr}, ev_R[2] = {nullptr, nullptr};
   bool lookahead = true;
+  int phase = 0;              // 0 single GPU, 1 owned bottom subtrees, 2 shared top (multi-GPU)
+  bool owns_lv = true;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device arrays
   SupInfo* d_sup = nullptr;
@@ -293,6 +295,7 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
   if (s->g_last) cudaGraphExecDestroy(s->g_last);
   if (s->g_fwd) cudaGraphExecDestroy(s->g_fwd);
   if (s->g_bwd) cudaGraphExecDestroy(s->g_bwd);
+  if (!s->owns_lv) s->d_lv = nullptr;   // adopted from another handle (parsy_cuda_adopt_factor)
   void* ptrs[] = {s->d_sup, s->d_lR, s->d_small_list, s->d_blocks, s->d_gemm, s->d_small_tasks, s->d_rel, s->d_apos,
                   s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info, s->d_stasks, s->d_sctas, s->d_stargets,
                   s->d_need, s->d_ntiles, s->d_sync};
@@ -326,6 +329,12 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
   PlanOptions po;
   po.nb = o.block_cols;
   po.ignore_hlevels = o.ignore_hlevels != 0;
+  po.rank = o.rank; po.world = std::max(1, o.world); po.phase = o.reserved[2]; po.top_levels = std::max(1, o.reserved[3]);
+  if (po.world > 1 && (po.rank < 0 || po.rank >= po.world || po.phase < 1 || po.phase > 2)) {
+    delete s;
+    return fail(PARSY_CUDA_ERR_BAD_ARG, "world > 1 needs 0 <= rank < world and reserved[2] (phase) in {1,2}");
+  }
+  s->phase = po.world > 1 ? po.phase : 0;
   // a missing schedule means "supernode order": one H-level with a single w-partition 0..supNo-1
   std::vector<int> tl, tp, tq;
   if (!levelPtr || !parPtr || !partition) {
@@ -442,14 +451,15 @@ extern "C" int parsy_cuda_set_values(parsy_cuda_solver* s, const double* values)
 
 extern "C" int parsy_cuda_factor(parsy_cuda_solver* s) {
   if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
-  if (!s->has_A || !s->has_values) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
+  if (s->phase != 2 && (!s->has_A || !s->has_values)) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
   CU(cudaSetDevice(s->device));
   const Plan& P = s->plan;
   cudaStream_t st = s->stream;
   CU(cudaEventRecord(s->ev[0], st));
   CU(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
-  CU(cudaMemsetAsync(s->d_lv, 0, sizeof(double) * (size_t)P.xsize, st));   // the reference's caller zeroes valL
-  if (P.nnzA > 0) {
+  // phase 2 continues on the factor phase 1 (and the exchange) left in place
+  if (s->phase != 2) CU(cudaMemsetAsync(s->d_lv, 0, sizeof(double) * (size_t)P.xsize, st));   // the reference's caller zeroes valL
+  if (s->phase != 2 && P.nnzA > 0) {
     const int grid = (int)std::min<int64_t>((P.nnzA + 255) / 256, 148 * 16);
     k_assemble<<<grid, 256, 0, st>>>(P.nnzA, s->d_apos, s->d_vals, s->d_lv);
   }
@@ -603,7 +613,10 @@ extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, con
                                      const int* partition, const parsy_cuda_options* opt, parsy_cuda_stats* o) {
   Plan P;
   PlanOptions po;
-  if (opt) { po.nb = opt->block_cols; po.ignore_hlevels = opt->ignore_hlevels != 0; }
+  if (opt) {
+    po.nb = opt->block_cols; po.ignore_hlevels = opt->ignore_hlevels != 0;
+    po.rank = opt->rank; po.world = std::max(1, opt->world); po.phase = opt->reserved[2]; po.top_levels = std::max(1, opt->reserved[3]);
+  }
   std::vector<int> tl, tp, tq;
   if (!levelPtr || !parPtr || !partition) {
     tl = {0, 1}; tp = {0, supNo}; tq.resize(std::max(supNo, 0));
@@ -619,6 +632,12 @@ extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, con
     o->n_steps = (int64_t)P.steps.size(); o->n_block_cols = P.n_block_cols; o->rel_entries = P.rel_entries;
     o->flops_potrf = P.flops_potrf; o->flops_trsm = P.flops_trsm; o->flops_update = P.flops_update;
     o->bytes_solve = P.bytes_solve;
+    // sharded plans: reserved[0] = supernodes this plan factors, reserved[1] = update tasks it runs,
+    // reserved[2] = supernodes owned by opt->rank, reserved[3] = shared (top) supernodes
+    o->reserved[0] = (int64_t)P.small_list.size();
+    for (const BlockTask& b : P.block_tasks) if (b.j0 == 0) o->reserved[0]++;
+    o->reserved[1] = (int64_t)P.gemm_tasks.size();
+    for (int s2 = 0; s2 < P.nsuper; ++s2) { if (P.owner[s2] == po.rank) o->reserved[2]++; if (P.owner[s2] < 0) o->reserved[3]++; }
   }
   return PARSY_CUDA_OK;
 }
@@ -800,12 +819,70 @@ extern "C" int parsy_cuda_lsolveParH2(int n, int* Lp, int* Li, double* Lx, doubl
   return parsy_cuda_lsolve(n, Lp, Li, Lx, x);
 }
 
-// ---- multi-GPU hooks -------------------------------------------------------------------
-extern "C" int parsy_cuda_owned_ranges(parsy_cuda_solver* s, int rank, int64_t* begin_end_pairs, int max_pairs) {
-  (void)s; (void)rank; (void)begin_end_pairs; (void)max_pairs;
-  return fail(PARSY_CUDA_ERR_STATE, "multi-GPU sharding not built in this round");
+static int owned_ranges_of(const Plan& P, int rank, int64_t* begin_end_pairs, int max_pairs) {
+  int cnt = 0;
+  int64_t b = -1, e = -1;
+  for (int i = 0; i <= P.nsuper; ++i) {
+    const bool mine = i < P.nsuper && P.owner[i] == rank;
+    if (mine) {
+      const SupInfo& I = P.sup[i];
+      if (b < 0) b = I.valptr;
+      e = I.valptr + (int64_t)I.w * I.r;
+    } else if (b >= 0) {
+      if (begin_end_pairs && cnt < max_pairs) { begin_end_pairs[2 * cnt] = b; begin_end_pairs[2 * cnt + 1] = e; }
+      ++cnt; b = -1;
+    }
+  }
+  return cnt;
 }
+
+// HOST-ONLY twin of parsy_cuda_owned_ranges (no device needed): plans and returns the runs owned by `for_rank`.
+extern "C" int parsy_cuda_plan_owned_ranges(int n, const size_t* lC, const int* lR, const size_t* Li_ptr,
+                                            const int* blockSet, int supNo, const int* col2Sup, int nLevels,
+                                            const int* levelPtr, const int* parPtr, const int* partition, int world,
+                                            int top_levels, int for_rank, int64_t* begin_end_pairs, int max_pairs) {
+  Plan P;
+  PlanOptions po;
+  po.world = std::max(1, world); po.rank = 0; po.phase = po.world > 1 ? 1 : 0; po.top_levels = std::max(1, top_levels);
+  const int rc = build_plan(P, n, lC, lR, Li_ptr, blockSet, supNo, nullptr, col2Sup, nLevels, levelPtr, parPtr, partition, po);
+  if (rc) { fail(rc, P.error); return -1; }
+  return owned_ranges_of(P, for_rank, begin_end_pairs, max_pairs);
+}
+
+// ---- multi-GPU hooks --------------------------------------------------------------------
+// Contiguous runs of lValues owned by `rank` (subtrees are contiguous in the postorder, so a rank owns a handful of
+// runs): out = {begin0, end0, begin1, end1, ...} in doubles; returns the number of runs (or -1).
+extern "C" int parsy_cuda_owned_ranges(parsy_cuda_solver* s, int rank, int64_t* begin_end_pairs, int max_pairs) {
+  if (!s) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle"); return -1; }
+  return owned_ranges_of(s->plan, rank, begin_end_pairs, max_pairs);
+}
+// Makes `s` (a phase-2 handle) work on the factor buffer of `src` (the phase-1 handle of the same rank).
 extern "C" int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase) {
-  (void)s; (void)phase;
-  return fail(PARSY_CUDA_ERR_STATE, "multi-GPU sharding not built in this round");
+  if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  return s->phase == phase ? PARSY_CUDA_OK : fail(PARSY_CUDA_ERR_STATE, "handle was planned for another phase");
+}
+extern "C" int parsy_cuda_adopt_factor(parsy_cuda_solver* s, parsy_cuda_solver* src) {
+  if (!s || !src) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  if (s->plan.xsize != src->plan.xsize || s->device != src->device) return fail(PARSY_CUDA_ERR_BAD_ARG, "handles differ");
+  CU(cudaSetDevice(s->device));
+  CU(cudaStreamSynchronize(s->stream));
+  if (s->owns_lv && s->d_lv) { cudaFree(s->d_lv); s->device_bytes -= (int64_t)sizeof(double) * s->plan.xsize; }
+  s->d_lv = src->d_lv;
+  s->owns_lv = false;
+  // the captured graphs hold the old pointer: re-capture
+  if (s->use_graph) {
+    if (s->g_levels) { cudaGraphExecDestroy(s->g_levels); s->g_levels = nullptr; }
+    if (s->g_last) { cudaGraphExecDestroy(s->g_last); s->g_last = nullptr; }
+    const Plan& P = s->plan;
+    const int nst = (int)P.steps.size();
+    const int last_begin = P.nlevels > 0 ? P.hlevel_first_step[P.nlevels - 1] : 0;
+    int64_t l0 = 0, l1 = 0;
+    int rc = capture(s, &s->g_levels, &l0, [&] { return enqueue_factor_steps(s, 0, last_begin); });
+    if (rc) return rc;
+    rc = capture(s, &s->g_last, &l1, [&] { return enqueue_factor_steps(s, last_begin, nst); });
+    if (rc) return rc;
+    s->launches_factor = l0 + l1;
+  }
+  s->factored = false;
+  return PARSY_CUDA_OK;
 }

@@ -200,11 +200,12 @@ def lsolveParH2(n, Lp, Li, Lx, x, levels, levelPtr, levelSet, parts, parPtr, par
 
 
 def plan_check(n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition, block_cols=0,
-               ignore_hlevels=False):
+               ignore_hlevels=False, rank=0, world=1, phase=0, top_levels=1):
     """Host-only planner run (no device needed): returns (status code, stats dict)."""
     L = lib()
     opt = Options()
     opt.block_cols, opt.ignore_hlevels, opt.use_graph = int(block_cols), int(ignore_hlevels), 1
+    opt.rank, opt.world, opt.reserved[2], opt.reserved[3] = int(rank), int(world), int(phase), int(top_levels)
     st = Stats()
     f = L.parsy_cuda_plan_check
     f.restype = c_int
@@ -218,6 +219,27 @@ def plan_check(n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, p
     return rc, st.as_dict()
 
 
+def plan_owned_ranges(n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition, world,
+                      for_rank, top_levels=1):
+    """Host-only: contiguous [begin, end) runs of lValues owned by `for_rank` when sharding over `world` ranks."""
+    L = lib()
+    f = L.parsy_cuda_plan_owned_ranges
+    f.restype = c_int
+    f.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                  c_int, c_int, c_int, c_void_p, c_int]
+    keep = [_u64(lC, "lC"), _i32(lR, "lR"), _u64(Li_ptr, "Li_ptr"), _i32(blockSet, "blockSet"),
+            _i32(col2Sup, "col2Sup"), _i32(levelPtr, "levelPtr"), _i32(parPtr, "parPtr"), _i32(partition, "partition")]
+    p = [k[1] for k in keep]
+    cnt = f(int(n), p[0], p[1], p[2], p[3], int(supNo), p[4], int(nLevels), p[5], p[6], p[7], int(world),
+            int(top_levels), int(for_rank), None, 0)
+    if cnt < 0:
+        raise ParsyCudaError(ERR_BAD_ARG, "parsy_cuda_plan_owned_ranges")
+    out = np.zeros(2 * max(cnt, 1), np.int64)
+    f(int(n), p[0], p[1], p[2], p[3], int(supNo), p[4], int(nLevels), p[5], p[6], p[7], int(world), int(top_levels),
+      int(for_rank), out.ctypes.data_as(c_void_p), cnt)
+    return out[:2 * cnt].reshape(-1, 2)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # resident handle
 # ---------------------------------------------------------------------------------------------------------
@@ -225,13 +247,17 @@ class Solver:
     """Device-resident symbolic state + factor. Arrays are the inspector's outputs."""
 
     def __init__(self, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
-                 device=0, block_cols=0, use_graph=True, ignore_hlevels=False):
+                 device=0, block_cols=0, use_graph=True, ignore_hlevels=False, lookahead=True, dataflow_sweeps=True,
+                 rank=0, world=1, phase=0, top_levels=1):
         L = lib()
         self._L = L
         self._h = c_void_p()
         opt = Options()
         opt.device, opt.block_cols, opt.use_graph, opt.ignore_hlevels = int(device), int(block_cols), int(use_graph), \
             int(ignore_hlevels)
+        opt.rank, opt.world = int(rank), int(world)
+        opt.reserved[0], opt.reserved[1] = int(not lookahead), int(not dataflow_sweeps)
+        opt.reserved[2], opt.reserved[3] = int(phase), int(top_levels)
         f = L.parsy_cuda_create
         f.restype = c_int
         f.argtypes = [POINTER(c_void_p), c_int] + [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + \
@@ -328,6 +354,28 @@ class Solver:
         if rc != OK:
             raise ParsyCudaError(rc, "parsy_cuda_get_stats")
         return st.as_dict()
+
+    def owned_ranges(self, rank):
+        """Contiguous [begin, end) runs of lValues (in doubles) owned by `rank` in the sharded factorization."""
+        f = self._L.parsy_cuda_owned_ranges
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_int, c_void_p, c_int]
+        cnt = f(self._h, int(rank), None, 0)
+        if cnt < 0:
+            raise ParsyCudaError(ERR_BAD_ARG, "parsy_cuda_owned_ranges")
+        out = np.zeros(2 * max(cnt, 1), np.int64)
+        f(self._h, int(rank), out.ctypes.data_as(c_void_p), cnt)
+        return out[:2 * cnt].reshape(-1, 2)
+
+    def adopt_factor(self, other):
+        """Work on `other`'s factor buffer (phase-2 handle adopting the phase-1 handle's)."""
+        f = self._L.parsy_cuda_adopt_factor
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_void_p]
+        rc = f(self._h, other._h)
+        if rc != OK:
+            raise ParsyCudaError(rc, "parsy_cuda_adopt_factor")
+        self._keep = other
 
     def device_pointers(self):
         L = self._L

@@ -1,0 +1,64 @@
+"""Sharded factorization across the GPUs of one node (one process per GPU): DESIGN.md §8.
+
+Phase 1: every rank factors the bottom subtrees it owns (no communication: LBC's lower levels are disjoint subtrees,
+cholesky/InspectionLevel_06.h:208-216).  Exchange: the owners' panels — a handful of contiguous runs of lValues per
+rank — are broadcast over NVLink with NCCL.  Phase 2: every rank applies the updates into the shared top separators
+and factors them.  torch.distributed is only the transport; all arithmetic runs in libparsy_cuda."""
+import numpy as np
+
+from . import executor as ex
+
+
+class _DevArray:
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+class ShardedCholesky:
+    def __init__(self, S, rank, world, device, top_levels=1, block_cols=0):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.device = rank, world, torch.device("cuda", device)
+        args = (S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels, S.levelPtr,
+                S.parPtr, S.partition)
+        self.h1 = ex.Solver(*args, device=device, block_cols=block_cols, rank=rank, world=world, phase=1,
+                            top_levels=top_levels)
+        self.h2 = ex.Solver(*args, device=device, block_cols=block_cols, rank=rank, world=world, phase=2,
+                            top_levels=top_levels)
+        self.h2.adopt_factor(self.h1)
+        self.ranges = [self.h1.owned_ranges(r) for r in range(world)]
+        p1, p2 = self.h1.device_pointers(), self.h2.device_pointers()
+        self.lv = torch.as_tensor(_DevArray(p1["factor"], S.xsize), device=self.device)
+        self.s1 = torch.cuda.ExternalStream(p1["stream"], device=self.device)
+        self.s2 = torch.cuda.ExternalStream(p2["stream"], device=self.device)
+        self.exchange_bytes = int(sum(int((r[:, 1] - r[:, 0]).sum()) for i, r in enumerate(self.ranges) if i != rank) * 8)
+        self.n_broadcasts = int(sum(len(r) for r in self.ranges))
+
+    def set_values(self, values):
+        self.h1.set_values(values)
+
+    def factor(self, dist=None):
+        """Enqueues phase 1, the NVLink exchange and phase 2; returns without synchronising."""
+        torch = self.torch
+        self.h1.factor()
+        with torch.cuda.stream(self.s1):
+            if dist is not None and self.world > 1:
+                for owner, runs in enumerate(self.ranges):
+                    for b, e in runs:
+                        dist.broadcast(self.lv[int(b):int(e)], src=owner)
+            ev = torch.cuda.Event()
+            ev.record(self.s1)
+        self.s2.wait_event(ev)
+        self.h2.factor()
+
+    def sync(self):
+        ok1 = self.h1.sync()
+        ok2 = self.h2.sync()
+        return ok1 and ok2
+
+    def get_factor(self):
+        return self.h2.get_factor()
+
+    def close(self):
+        self.h2.close()
+        self.h1.close()

@@ -234,3 +234,40 @@ def test_full_size_properties(case):
     assert np.linalg.norm(A @ sol - rhs) / np.linalg.norm(rhs) < 1e-9
     del L
     H.close()
+
+
+@pytest.mark.parametrize("world,top", [(2, 1), (3, 2)])
+def test_sharded_factorization_emulated_on_one_gpu(world, top):
+    """phase 1 per rank (owned bottom subtrees) -> panel exchange -> phase 2 (shared top).
+    All ranks are emulated on this one device; the exchange is done through host copies of the owned runs."""
+    S = analyze("3d27", 14, 64, 1, 2)
+    ref = orc.cholesky_left_par_05(S)
+    args = (S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels, S.levelPtr,
+            S.parPtr, S.partition)
+    merged = None
+    owned = np.zeros(S.xsize, bool)
+    for r in range(world):
+        h1 = ex.Solver(*args, rank=r, world=world, phase=1, top_levels=top)
+        h1.set_values(S.A2_x)
+        h1.factor()
+        assert h1.sync()
+        part = h1.get_factor()
+        if merged is None:
+            merged = part.copy()            # rank 0's buffer: zeroed + assembled A + its own subtrees
+        runs = h1.owned_ranges(r)
+        assert len(runs) >= 1
+        for b, e in runs:
+            assert not owned[b:e].any()
+            owned[b:e] = True
+            merged[b:e] = part[b:e]         # the "broadcast" from owner r
+        h1.close()
+    h1 = ex.Solver(*args, rank=0, world=world, phase=1, top_levels=top)
+    h1.set_values(S.A2_x)
+    h1.set_factor(merged)
+    h2 = ex.Solver(*args, rank=0, world=world, phase=2, top_levels=top)
+    h2.adopt_factor(h1)
+    h2.factor()
+    assert h2.sync()
+    assert rel_err(h2.get_factor(), ref) < TOL
+    h2.close()
+    h1.close()
