@@ -206,7 +206,7 @@ def sharded_arm(args, kind, N, desc, rank, world, local):
     e0.record(SC.s1)
     for _ in range(args.steps):
         SC.factor(dist)
-        SC.s1.wait_stream(SC.s2)          # the next step's phase 1 rewrites the shared buffer
+    SC.s1.wait_stream(SC.s2)
     e1.record(SC.s1)
     barrier()
     clocks = sampler.stop()

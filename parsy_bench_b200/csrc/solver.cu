@@ -489,13 +489,13 @@ extern "C" int parsy_cuda_factor(parsy_cuda_solver* s) {
 extern "C" int parsy_cuda_factor_profiled(parsy_cuda_solver* s, double* class_ms, int64_t* class_launches,
                                           double* class_flops) {
   if (!s || !class_ms || !class_launches || !class_flops) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
-  if (!s->has_A || !s->has_values) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
+  if (s->phase != 2 && (!s->has_A || !s->has_values)) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
   CU(cudaSetDevice(s->device));
   const Plan& P = s->plan;
   cudaStream_t st = s->stream;
   CU(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
-  CU(cudaMemsetAsync(s->d_lv, 0, sizeof(double) * (size_t)P.xsize, st));
-  if (P.nnzA > 0) {
+  if (s->phase != 2) CU(cudaMemsetAsync(s->d_lv, 0, sizeof(double) * (size_t)P.xsize, st));
+  if (s->phase != 2 && P.nnzA > 0) {
     const int grid = (int)std::min<int64_t>((P.nnzA + 255) / 256, 148 * 16);
     k_assemble<<<grid, 256, 0, st>>>(P.nnzA, s->d_apos, s->d_vals, s->d_lv);
   }

@@ -40,6 +40,7 @@ class ShardedCholesky:
     def factor(self, dist=None):
         """Enqueues phase 1, the NVLink exchange and phase 2; returns without synchronising."""
         torch = self.torch
+        self.s1.wait_stream(self.s2)      # phase 1 re-zeroes the buffer the previous phase 2 may still be writing
         self.h1.factor()
         with torch.cuda.stream(self.s1):
             if dist is not None and self.world > 1:
