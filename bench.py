@@ -412,9 +412,16 @@ def main():
     dm_n = sum(prof[k]["launches"] for k in dmma)
     peaks, peak_kind = measured_peaks()
     achieved_tf = dm_fl / (dm_ms * 1e-3) / 1e12 if dm_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f).get(args.config, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "k_gemm_tiles (FP64 DMMA m8n8k4: SYRK/GEMM update + TRSM)",
                 "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": achieved_tf / FP64_PEAK_TFLOPS, "traffic": None,
+                "frac": achieved_tf / FP64_PEAK_TFLOPS, "traffic": traffic,
+                "traffic_note": "dram bytes per launch from the committed ncu --set full capture (profiles/r01_ncu_gemm_cfg2.txt)",
                 "peak_source": "measured DMMA issue rate, tools/fp64_peak.cu (MEASURED_PEAKS.json has no FP64 entry)",
                 "launches": dm_n, "avg_launch_us": dm_ms * 1e3 / max(dm_n, 1),
                 "algorithmic_flops_per_step": dm_fl, "share_of_factor_time": dm_ms / tot_prof if tot_prof else None,
