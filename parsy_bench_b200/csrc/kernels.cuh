@@ -48,6 +48,8 @@ struct GemmCfg {
 };
 using Cfg128 = GemmCfg<128, 128, 32, 32, 16, 3>;   // 16 warps: 4 per SMSP keep the DMMA pipe fed across LDS/barrier stalls
 using Cfg64 = GemmCfg<64, 64, 32, 32, 8, 4>;
+// TRSM: 64-row tiles double the CTA count of the latency-critical panel solve; TN = 128 keeps it in place
+using CfgTrsm = GemmCfg<64, 128, 32, 32, 16, 3>;
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS) k_gemm_tiles(const GemmTask* __restrict__ tasks, int ntasks,

@@ -327,7 +327,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   for (int st = 0; st < nsteps; ++st) {
     Step& S = P.steps[st];
     int32_t acc = 0;
-    for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, 128); }
+    for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, 64); }
     S.trsm_tiles = acc;
     for (int g = 0; g < 2; ++g) {
       UpdGroup& U = S.upd[g];

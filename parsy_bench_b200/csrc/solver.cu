@@ -80,6 +80,7 @@ static int ensure_kernel_attrs() {
   if (done) return 0;
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg128::SMEM));
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg64::SMEM));
+  CU(cudaFuncSetAttribute(k_gemm_tiles<CfgTrsm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgTrsm::SMEM));
   CU(cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
   done = true;
   return 0;
@@ -125,8 +126,8 @@ static int64_t launch_factor_phase(parsy_cuda_solver* s, const Step& S, cudaStre
   }
   if (S.trsm_tiles) {
     PROF_BEGIN(2);
-    k_gemm_tiles<Cfg128><<<S.trsm_tiles, Cfg128::THREADS, Cfg128::SMEM, st>>>(s->d_gemm + S.trsm.begin, S.trsm.size(),
-                                                                              s->d_lv, s->d_linv, s->d_rel);
+    k_gemm_tiles<CfgTrsm><<<S.trsm_tiles, CfgTrsm::THREADS, CfgTrsm::SMEM, st>>>(s->d_gemm + S.trsm.begin, S.trsm.size(),
+                                                                                 s->d_lv, s->d_linv, s->d_rel);
     PROF_END();
     ++launches;
   }
