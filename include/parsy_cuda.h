@@ -112,7 +112,8 @@ typedef struct parsy_cuda_options {
   int ignore_hlevels;  /* 1 = schedule by etree dependencies only, not by LBC H-level barriers     */
   int rank;            /* multi-GPU: this process' rank ...                                        */
   int world;           /* ... of `world` ranks (0/1 = single GPU)                                  */
-  int reserved[10];    /* [0]=1 no look-ahead stream, [1]=1 per-step sweeps, [2] phase, [3] top H-levels kept shared */
+  int reserved[10];    /* [0]=1 no look-ahead stream, [1]=1 per-step sweeps, [2] phase, [3] top H-levels kept shared,
+                          [4]=1 replicate the top instead of distributing it */
 } parsy_cuda_options;
 
 /* Builds the device-resident symbolic state from the inspector's arrays (all HOST pointers, copied):
@@ -203,6 +204,19 @@ int parsy_cuda_plan_owned_ranges(int n, const size_t* lC, const int* lR, const s
                                  int64_t* begin_end_pairs, int max_pairs);
 int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase);   /* checks that the handle was planned for `phase` */
 int parsy_cuda_adopt_factor(parsy_cuda_solver* s, parsy_cuda_solver* src);
+/* Distributed top (default for phase 2; options.reserved[4] = 1 replicates the top instead): the block columns of the
+ * shared top separators are owned round-robin; every rank factors every top block column but applies only the updates
+ * into the ones it owns, so before a step is enqueued the owners broadcast the panels that step factors:
+ *   for step in 0..parsy_cuda_num_steps:  for (owner, begin, end) in parsy_cuda_step_bcasts(step): broadcast lValues[begin,end)
+ *                                         parsy_cuda_factor_steps(h, step, step + 1)
+ * Steps before parsy_cuda_first_top_step() have no broadcasts (they only carry updates from the bottom into the top)
+ * and can be enqueued in one call. */
+int parsy_cuda_num_steps(parsy_cuda_solver* s);
+int parsy_cuda_first_top_step(parsy_cuda_solver* s);
+int parsy_cuda_step_bcasts(parsy_cuda_solver* s, int step, int64_t* owner_begin_end_triples, int max_triples);
+int parsy_cuda_factor_steps(parsy_cuda_solver* s, int step_begin, int step_end);
+/* dst.lValues[begin,end) = src.lValues[begin,end), device to device (emulates the exchange between ranks on one GPU). */
+int parsy_cuda_copy_range(parsy_cuda_solver* dst, parsy_cuda_solver* src, int64_t begin, int64_t end);
 
 #ifdef __cplusplus
 }

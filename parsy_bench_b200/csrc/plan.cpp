@@ -144,6 +144,19 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     for (const PairDesc& q : P.pairs)
       if (P.owner[q.src] < 0 && P.owner[q.tgt] >= 0) { P.error = "top supernode updates a bottom one"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
   }
+  std::vector<int32_t> node_first(supNo + 1, 0);
+  for (int s = 0; s < supNo; ++s) node_first[s + 1] = node_first[s] + nblk[s];
+  const bool dist_top = opt.world > 1 && opt.phase == 2 && opt.top_distributed != 0;
+  P.node_owner.assign(node_first[supNo], -1);
+  P.first_top_step = nsteps;
+  if (opt.world > 1) {
+    int rr = 0;
+    for (int s = 0; s < supNo; ++s) {
+      if (P.owner[s] >= 0) continue;
+      P.first_top_step = std::min(P.first_top_step, (int)step0[s]);
+      for (int b2 = 0; b2 < nblk[s]; ++b2) P.node_owner[node_first[s] + b2] = rr++ % opt.world;
+    }
+  }
   auto sup_active = [&](int s) {
     if (opt.phase == 1) return P.owner[s] == opt.rank;
     if (opt.phase == 2) return P.owner[s] < 0;
@@ -234,7 +247,18 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         P.class_flops[2] += (double)Mb * nb * nb;
       }
       const int Nt = I.w - j0 - nb;   // trailing columns of the same supernode
-      if (Nt > 0) {
+      if (Nt > 0 && dist_top) {
+        // one task per later block column, kept only if this rank owns that block column
+        for (int b3 = b2 + 1; b3 < nblk[s]; ++b3) {
+          if (P.node_owner[node_first[s] + b3] != opt.rank) continue;
+          const int c0 = (b3 - b2 - 1) * NB, c1 = std::min(Nt, c0 + NB);
+          GemmTask t; memset(&t, 0, sizeof(t));
+          t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb + c0; t.b_off = t.a_off;
+          t.c_off = I.valptr + (int64_t)(j0 + nb + c0) * I.r + j0 + nb + c0;
+          t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = Mb - c0; t.N = c1 - c0; t.K = nb; t.flags = GF_LOWER;
+          emit_update(t, st, b3 == b2 + 1 ? 0 : 1, false);
+        }
+      } else if (Nt > 0) {
         // columns of the next block column first ("A"), the remainder of the trapezoid separately ("R")
         const int n1 = std::min(Nt, NB);
         GemmTask t; memset(&t, 0, sizeof(t));
@@ -266,7 +290,21 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     t.lda = t.ldb = D.r; t.ldc = T.r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
     P.rel_prefix[pi] = rel; P.rel_pair_src[pi] = q.src; P.rel_pair_tgt[pi] = q.tgt; P.rel_pair_lb[pi] = q.lb;
     rel += q.m;
-    if (pair_active(q.src, q.tgt)) emit_update(t, st, step0[q.tgt] == st + 1 ? 0 : 1, true);
+    if (!pair_active(q.src, q.tgt)) continue;
+    if (!dist_top) { emit_update(t, st, step0[q.tgt] == st + 1 ? 0 : 1, true); continue; }
+    // split the pair's columns by the target block column they fall into; keep what this rank owns
+    for (int n0 = 0; n0 < q.nd1;) {
+      auto blk_of = [&](int j) { return T.flags ? 0 : (lR[D.rowptr + q.lb + j] - T.col0) / NB; };
+      const int tb = blk_of(n0);
+      int n1 = n0 + 1;
+      while (n1 < q.nd1 && blk_of(n1) == tb) ++n1;
+      if (P.node_owner[node_first[q.tgt] + tb] == opt.rank) {
+        GemmTask u = t;
+        u.a_off += n0; u.b_off += n0; u.rel_off += n0; u.M = q.m - n0; u.N = n1 - n0;
+        emit_update(u, st, step0[q.tgt] + tb == st + 1 ? 0 : 1, true);
+      }
+      n0 = n1;
+    }
   }
   P.rel_prefix[P.pairs.size()] = rel;
   P.rel_entries = rel;
@@ -344,10 +382,28 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     }
     S.solve_tiles = acc;
   }
+  // ---- distributed top: panels to broadcast before each step ----------------------------------------------------
+  P.bcast_ptr.assign(nsteps + 1, 0);
+  if (dist_top) {
+    std::vector<std::vector<int64_t>> per(nsteps);
+    for (int s = 0; s < supNo; ++s) {
+      if (P.owner[s] >= 0) continue;
+      const SupInfo& I = P.sup[s];
+      for (int b2 = 0; b2 < nblk[s]; ++b2) {
+        const int j0 = I.flags ? 0 : b2 * NB, nb = I.flags ? I.w : std::min(NB, I.w - j0);
+        auto& v = per[step0[s] + b2];
+        v.push_back(P.node_owner[node_first[s] + b2]);
+        v.push_back(I.valptr + (int64_t)j0 * I.r);
+        v.push_back(I.valptr + (int64_t)(j0 + nb) * I.r);
+      }
+    }
+    for (int st = 0; st < nsteps; ++st) {
+      P.bcast.insert(P.bcast.end(), per[st].begin(), per[st].end());
+      P.bcast_ptr[st + 1] = (int32_t)(P.bcast.size() / 3);
+    }
+  }
   // ---- dataflow sweeps: nodes, tasks in dependency order, target lists, counters ------------------------------
   {
-    std::vector<int32_t> node_first(supNo + 1, 0);
-    for (int s = 0; s < supNo; ++s) node_first[s + 1] = node_first[s] + nblk[s];
     P.n_nodes = node_first[supNo];
     auto node_of_row = [&](int row) {
       const int t = col2Sup[row];

@@ -133,6 +133,10 @@ struct PlanOptions {
   //   phase 0: everything (single GPU)   phase 1: only what `rank` owns   phase 2: the shared top + every update
   //   into it (run after the owners' panels have been exchanged)
   int phase = 0, rank = 0, world = 1, top_levels = 1;
+  // phase 2: 1 = the top separators are distributed too (1-D block-cyclic by target block column: every rank
+  // factors every top block column, but applies only the updates into the block columns it owns; the owner broadcasts
+  // a block column's panel right before it is factored), 0 = the top is computed redundantly by every rank
+  int top_distributed = 1;
 };
 
 struct Plan {
@@ -155,6 +159,10 @@ struct Plan {
   std::vector<int32_t> rel_pair_lb;         // per rel-pair: lb
   int64_t rel_entries = 0;
   std::vector<int32_t> owner;               // per supernode: owning rank, -1 = shared top (world > 1 only)
+  std::vector<int32_t> node_owner;          // per node (narrow supernode / block column) of the top: owning rank
+  std::vector<int32_t> bcast_ptr;           // per step: range in bcast (phase 2, distributed top)
+  std::vector<int64_t> bcast;               // triples (owner, begin, end) in doubles: panels to broadcast before the step
+  int32_t first_top_step = 0;
   // dataflow sweeps
   int32_t n_nodes = 0;
   std::vector<SolveTask> solve_tasks;      // forward order (dependency steps ascending)

@@ -30,6 +30,7 @@ struct parsy_cuda_solver {
   bool lookahead = true;
   int phase = 0;              // 0 single GPU, 1 owned bottom subtrees, 2 shared top (multi-GPU)
   bool owns_lv = true;
+  bool dist_top = false;      // phase 2 with block-cyclic top: stepwise API, broadcasts between steps
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device arrays
   SupInfo* d_sup = nullptr;
@@ -336,6 +337,8 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
     return fail(PARSY_CUDA_ERR_BAD_ARG, "world > 1 needs 0 <= rank < world and reserved[2] (phase) in {1,2}");
   }
   s->phase = po.world > 1 ? po.phase : 0;
+  po.top_distributed = o.reserved[4] == 0;   // reserved[4] = 1: replicate the top instead of distributing it
+  s->dist_top = po.world > 1 && po.phase == 2 && po.top_distributed;
   // a missing schedule means "supernode order": one H-level with a single w-partition 0..supNo-1
   std::vector<int> tl, tp, tq;
   if (!levelPtr || !parPtr || !partition) {
@@ -428,8 +431,10 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
   const int last_begin = P.nlevels > 0 ? P.hlevel_first_step[P.nlevels - 1] : 0;
   if (s->use_graph) {
     int64_t l0 = 0, l1 = 0;
-    TRY(capture(s, &s->g_levels, &l0, [&] { return enqueue_factor_steps(s, 0, last_begin); }));
-    TRY(capture(s, &s->g_last, &l1, [&] { return enqueue_factor_steps(s, last_begin, nst); }));
+    if (!s->dist_top) {
+      TRY(capture(s, &s->g_levels, &l0, [&] { return enqueue_factor_steps(s, 0, last_begin); }));
+      TRY(capture(s, &s->g_last, &l1, [&] { return enqueue_factor_steps(s, last_begin, nst); }));
+    }
     s->launches_factor = l0 + l1 + (s->has_A ? 1 : 0);
     TRY(capture(s, &s->g_fwd, &s->launches_fwd, [&] { return enqueue_fwd(s); }));
     TRY(capture(s, &s->g_bwd, &s->launches_bwd, [&] { return enqueue_bwd(s); }));
@@ -453,6 +458,7 @@ extern "C" int parsy_cuda_set_values(parsy_cuda_solver* s, const double* values)
 extern "C" int parsy_cuda_factor(parsy_cuda_solver* s) {
   if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
   if (s->phase != 2 && (!s->has_A || !s->has_values)) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
+  if (s->dist_top) return fail(PARSY_CUDA_ERR_STATE, "distributed top: drive it with parsy_cuda_factor_steps and the per-step broadcasts");
   CU(cudaSetDevice(s->device));
   const Plan& P = s->plan;
   cudaStream_t st = s->stream;
@@ -633,11 +639,12 @@ extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, con
     o->n_steps = (int64_t)P.steps.size(); o->n_block_cols = P.n_block_cols; o->rel_entries = P.rel_entries;
     o->flops_potrf = P.flops_potrf; o->flops_trsm = P.flops_trsm; o->flops_update = P.flops_update;
     o->bytes_solve = P.bytes_solve;
-    // sharded plans: reserved[0] = supernodes this plan factors, reserved[1] = update tasks it runs,
+    // sharded plans: reserved[0] = supernodes this plan factors, reserved[1] = GEMM-shaped tasks it runs, reserved[4] = their update flops,
     // reserved[2] = supernodes owned by opt->rank, reserved[3] = shared (top) supernodes
     o->reserved[0] = (int64_t)P.small_list.size();
     for (const BlockTask& b : P.block_tasks) if (b.j0 == 0) o->reserved[0]++;
     o->reserved[1] = (int64_t)P.gemm_tasks.size();
+    o->reserved[4] = (int64_t)(P.class_flops[3] + P.class_flops[4] + P.class_flops[5]);   // flops of the update tasks this plan runs
     for (int s2 = 0; s2 < P.nsuper; ++s2) { if (P.owner[s2] == po.rank) o->reserved[2]++; if (P.owner[s2] < 0) o->reserved[3]++; }
   }
   return PARSY_CUDA_OK;
@@ -857,6 +864,42 @@ extern "C" int parsy_cuda_owned_ranges(parsy_cuda_solver* s, int rank, int64_t* 
   if (!s) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle"); return -1; }
   return owned_ranges_of(s->plan, rank, begin_end_pairs, max_pairs);
 }
+// ---- stepwise execution (distributed top) ------------------------------------------------------------------
+extern "C" int parsy_cuda_num_steps(parsy_cuda_solver* s) { return s ? (int)s->plan.steps.size() : -1; }
+extern "C" int parsy_cuda_first_top_step(parsy_cuda_solver* s) { return s ? s->plan.first_top_step : -1; }
+// Panels that must be broadcast from their owner before `step` is enqueued: triples (owner, begin, end) in doubles.
+extern "C" int parsy_cuda_step_bcasts(parsy_cuda_solver* s, int step, int64_t* triples, int max_triples) {
+  if (!s || step < 0 || step >= (int)s->plan.steps.size()) { fail(PARSY_CUDA_ERR_BAD_ARG, "bad step"); return -1; }
+  const Plan& P = s->plan;
+  const int b = P.bcast_ptr[step], e = P.bcast_ptr[step + 1];
+  for (int i = b; i < e && triples && i - b < max_triples; ++i)
+    for (int k = 0; k < 3; ++k) triples[3 * (i - b) + k] = P.bcast[3 * i + k];
+  return e - b;
+}
+// Enqueues steps [begin, end) on the handle's stream (no graph, no look-ahead stream).
+extern "C" int parsy_cuda_factor_steps(parsy_cuda_solver* s, int begin, int end) {
+  if (!s || begin < 0 || end > (int)s->plan.steps.size() || begin > end) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad step range");
+  CU(cudaSetDevice(s->device));
+  if (begin == 0) CU(cudaMemsetAsync(s->d_info, 0, sizeof(int), s->stream));
+  const bool la = s->lookahead;
+  s->lookahead = false;
+  const int64_t l = enqueue_factor_steps(s, begin, end);
+  s->lookahead = la;
+  if (begin == 0) s->launches_factor = 0;
+  s->launches_factor += l;
+  CU(cudaGetLastError());
+  if (end == (int)s->plan.steps.size()) s->factored = true;
+  return PARSY_CUDA_OK;
+}
+// dst.lValues[begin, end) = src.lValues[begin, end) (device to device; used to emulate the exchange on one GPU)
+extern "C" int parsy_cuda_copy_range(parsy_cuda_solver* dst, parsy_cuda_solver* src, int64_t begin, int64_t end) {
+  if (!dst || !src || begin < 0 || end > dst->plan.xsize || end > src->plan.xsize || begin > end) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad range");
+  CU(cudaSetDevice(dst->device));
+  CU(cudaStreamSynchronize(src->stream));
+  CU(cudaMemcpyAsync(dst->d_lv + begin, src->d_lv + begin, sizeof(double) * (size_t)(end - begin), cudaMemcpyDeviceToDevice, dst->stream));
+  return PARSY_CUDA_OK;
+}
+
 // Makes `s` (a phase-2 handle) work on the factor buffer of `src` (the phase-1 handle of the same rank).
 extern "C" int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase) {
   if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
@@ -871,7 +914,7 @@ extern "C" int parsy_cuda_adopt_factor(parsy_cuda_solver* s, parsy_cuda_solver* 
   s->d_lv = src->d_lv;
   s->owns_lv = false;
   // the captured graphs hold the old pointer: re-capture
-  if (s->use_graph) {
+  if (s->use_graph && !s->dist_top) {
     if (s->g_levels) { cudaGraphExecDestroy(s->g_levels); s->g_levels = nullptr; }
     if (s->g_last) { cudaGraphExecDestroy(s->g_last); s->g_last = nullptr; }
     const Plan& P = s->plan;

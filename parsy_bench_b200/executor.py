@@ -248,7 +248,7 @@ class Solver:
 
     def __init__(self, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
                  device=0, block_cols=0, use_graph=True, ignore_hlevels=False, lookahead=True, dataflow_sweeps=True,
-                 rank=0, world=1, phase=0, top_levels=1):
+                 rank=0, world=1, phase=0, top_levels=1, top_distributed=True):
         L = lib()
         self._L = L
         self._h = c_void_p()
@@ -257,7 +257,7 @@ class Solver:
             int(ignore_hlevels)
         opt.rank, opt.world = int(rank), int(world)
         opt.reserved[0], opt.reserved[1] = int(not lookahead), int(not dataflow_sweeps)
-        opt.reserved[2], opt.reserved[3] = int(phase), int(top_levels)
+        opt.reserved[2], opt.reserved[3], opt.reserved[4] = int(phase), int(top_levels), int(not top_distributed)
         f = L.parsy_cuda_create
         f.restype = c_int
         f.argtypes = [POINTER(c_void_p), c_int] + [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + \
@@ -376,6 +376,41 @@ class Solver:
         if rc != OK:
             raise ParsyCudaError(rc, "parsy_cuda_adopt_factor")
         self._keep = other
+
+    def num_steps(self):
+        f = self._L.parsy_cuda_num_steps
+        f.restype = c_int
+        f.argtypes = [c_void_p]
+        return int(f(self._h))
+
+    def first_top_step(self):
+        f = self._L.parsy_cuda_first_top_step
+        f.restype = c_int
+        f.argtypes = [c_void_p]
+        return int(f(self._h))
+
+    def step_bcasts(self, step):
+        """(owner, begin, end) of the panels to broadcast before `step` (distributed top)."""
+        f = self._L.parsy_cuda_step_bcasts
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_int, c_void_p, c_int]
+        cnt = f(self._h, int(step), None, 0)
+        if cnt <= 0:
+            return np.zeros((0, 3), np.int64)
+        out = np.zeros(3 * cnt, np.int64)
+        f(self._h, int(step), out.ctypes.data_as(c_void_p), cnt)
+        return out.reshape(-1, 3)
+
+    def factor_steps(self, begin, end):
+        self._call("parsy_cuda_factor_steps", int(begin), int(end))
+
+    def copy_range_from(self, other, begin, end):
+        f = self._L.parsy_cuda_copy_range
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64]
+        rc = f(self._h, other._h, int(begin), int(end))
+        if rc != OK:
+            raise ParsyCudaError(rc, "parsy_cuda_copy_range")
 
     def device_pointers(self):
         L = self._L

@@ -2,8 +2,9 @@
 
 Phase 1: every rank factors the bottom subtrees it owns (no communication: LBC's lower levels are disjoint subtrees,
 cholesky/InspectionLevel_06.h:208-216).  Exchange: the owners' panels — a handful of contiguous runs of lValues per
-rank — are broadcast over NVLink with NCCL.  Phase 2: every rank applies the updates into the shared top separators
-and factors them.  torch.distributed is only the transport; all arithmetic runs in libparsy_cuda."""
+rank — are broadcast over NVLink with NCCL.  Phase 2: the top separators, 1-D block-cyclic: every rank factors every
+top block column (POTRF/TRSM are latency-bound and cheap) but applies only the trailing / descendant updates into the
+block columns it owns; right before a block column is factored its owner broadcasts the panel.  torch.distributed is only the transport; all arithmetic runs in libparsy_cuda."""
 import numpy as np
 
 from . import executor as ex
@@ -15,7 +16,7 @@ class _DevArray:
 
 
 class ShardedCholesky:
-    def __init__(self, S, rank, world, device, top_levels=1, block_cols=0):
+    def __init__(self, S, rank, world, device, top_levels=1, block_cols=0, top_distributed=True):
         import torch
         self.torch = torch
         self.rank, self.world, self.device = rank, world, torch.device("cuda", device)
@@ -24,7 +25,8 @@ class ShardedCholesky:
         self.h1 = ex.Solver(*args, device=device, block_cols=block_cols, rank=rank, world=world, phase=1,
                             top_levels=top_levels)
         self.h2 = ex.Solver(*args, device=device, block_cols=block_cols, rank=rank, world=world, phase=2,
-                            top_levels=top_levels)
+                            top_levels=top_levels, top_distributed=top_distributed)
+        self.top_distributed = top_distributed and world > 1
         self.h2.adopt_factor(self.h1)
         self.ranges = [self.h1.owned_ranges(r) for r in range(world)]
         p1, p2 = self.h1.device_pointers(), self.h2.device_pointers()
@@ -33,6 +35,14 @@ class ShardedCholesky:
         self.s2 = torch.cuda.ExternalStream(p2["stream"], device=self.device)
         self.exchange_bytes = int(sum(int((r[:, 1] - r[:, 0]).sum()) for i, r in enumerate(self.ranges) if i != rank) * 8)
         self.n_broadcasts = int(sum(len(r) for r in self.ranges))
+        self.nsteps, self.first_top = self.h2.num_steps(), self.h2.first_top_step()
+        self.step_bcasts = {}
+        if self.top_distributed:
+            for st in range(self.first_top, self.nsteps):
+                bc = self.h2.step_bcasts(st)
+                if len(bc):
+                    self.step_bcasts[st] = [(int(o), int(b), int(e)) for o, b, e in bc]
+            self.n_broadcasts += sum(len(v) for v in self.step_bcasts.values())
 
     def set_values(self, values):
         self.h1.set_values(values)
@@ -50,7 +60,17 @@ class ShardedCholesky:
             ev = torch.cuda.Event()
             ev.record(self.s1)
         self.s2.wait_event(ev)
-        self.h2.factor()
+        if not self.top_distributed:
+            self.h2.factor()
+            return
+        # distributed top: updates from the bottom into the owned top block columns, then step by step:
+        # owners broadcast the block columns about to be factored, every rank factors them, owners update theirs
+        with torch.cuda.stream(self.s2):
+            self.h2.factor_steps(0, self.first_top)
+            for st in range(self.first_top, self.nsteps):
+                for owner, b, e in self.step_bcasts.get(st, ()):
+                    dist.broadcast(self.lv[b:e], src=owner)
+                self.h2.factor_steps(st, st + 1)
 
     def sync(self):
         ok1 = self.h1.sync()

@@ -48,13 +48,15 @@ def _worker(rank, world, port, q):
         rc, st = ex.plan_check(*args, rank=rank, world=world, phase=2, top_levels=2)
         assert rc == ex.OK
         top_sup = st["reserved"][3]
+        assert st["reserved"][0] == top_sup                # every rank factors every top supernode (POTRF/TRSM replicated)
         rc1, st1 = ex.plan_check(*args, rank=rank, world=world, phase=1, top_levels=2)
-        mine = torch.tensor([st1["reserved"][0], st1["reserved"][1]], dtype=torch.int64)
+        mine = torch.tensor([st1["reserved"][0], st1["reserved"][4] + st["reserved"][4]], dtype=torch.int64)
         tot = mine.clone()
         dist.all_reduce(tot)
         full = ex.plan_check(*args)[1]
-        assert int(tot[0]) + top_sup == S.nsuper           # every supernode is factored exactly once
-        assert int(tot[1]) + st["reserved"][1] == full["reserved"][1]   # every update task runs exactly once
+        assert int(tot[0]) + top_sup == S.nsuper           # every bottom supernode is factored exactly once
+        # every update (descendant pair or trailing block update) runs on exactly one rank: the flops add up
+        assert abs(int(tot[1]) - full["reserved"][4]) <= 4 * world
         assert bool(torch.isnan(lv[owned == 0]).all()) and not bool(torch.isnan(lv[owned == 1]).any())
         # checksum agreement across ranks
         chk = torch.nan_to_num(lv).sum().reshape(1)

@@ -236,38 +236,52 @@ def test_full_size_properties(case):
     H.close()
 
 
-@pytest.mark.parametrize("world,top", [(2, 1), (3, 2)])
-def test_sharded_factorization_emulated_on_one_gpu(world, top):
-    """phase 1 per rank (owned bottom subtrees) -> panel exchange -> phase 2 (shared top).
-    All ranks are emulated on this one device; the exchange is done through host copies of the owned runs."""
+@pytest.mark.parametrize("world,top,dist_top", [(2, 1, True), (3, 2, True), (2, 2, False)])
+def test_sharded_factorization_emulated_on_one_gpu(world, top, dist_top):
+    """phase 1 per rank (owned bottom subtrees) -> panel exchange -> phase 2 (top separators, block-cyclic
+    with a panel broadcast before every step, or replicated).  All ranks are emulated on this one device; the NCCL
+    broadcasts become device-to-device copies between the ranks' buffers."""
     S = analyze("3d27", 14, 64, 1, 2)
     ref = orc.cholesky_left_par_05(S)
     args = (S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels, S.levelPtr,
             S.parPtr, S.partition)
-    merged = None
+    h1 = [ex.Solver(*args, rank=r, world=world, phase=1, top_levels=top) for r in range(world)]
+    for h in h1:
+        h.set_values(S.A2_x)
+        h.factor()
+    for h in h1:
+        assert h.sync()
     owned = np.zeros(S.xsize, bool)
-    for r in range(world):
-        h1 = ex.Solver(*args, rank=r, world=world, phase=1, top_levels=top)
-        h1.set_values(S.A2_x)
-        h1.factor()
-        assert h1.sync()
-        part = h1.get_factor()
-        if merged is None:
-            merged = part.copy()            # rank 0's buffer: zeroed + assembled A + its own subtrees
-        runs = h1.owned_ranges(r)
-        assert len(runs) >= 1
-        for b, e in runs:
+    for o in range(world):
+        for b, e in h1[o].owned_ranges(o):
             assert not owned[b:e].any()
             owned[b:e] = True
-            merged[b:e] = part[b:e]         # the "broadcast" from owner r
-        h1.close()
-    h1 = ex.Solver(*args, rank=0, world=world, phase=1, top_levels=top)
-    h1.set_values(S.A2_x)
-    h1.set_factor(merged)
-    h2 = ex.Solver(*args, rank=0, world=world, phase=2, top_levels=top)
-    h2.adopt_factor(h1)
-    h2.factor()
-    assert h2.sync()
-    assert rel_err(h2.get_factor(), ref) < TOL
-    h2.close()
-    h1.close()
+            for r in range(world):
+                if r != o:
+                    h1[r].copy_range_from(h1[o], b, e)       # the "broadcast" from owner o
+    h2 = [ex.Solver(*args, rank=r, world=world, phase=2, top_levels=top, top_distributed=dist_top) for r in range(world)]
+    for r in range(world):
+        h2[r].adopt_factor(h1[r])
+    if dist_top:
+        ft, ns = h2[0].first_top_step(), h2[0].num_steps()
+        assert 0 < ft < ns
+        for h in h2:
+            h.factor_steps(0, ft)
+        nb = 0
+        for st in range(ft, ns):
+            for o, b, e in h2[0].step_bcasts(st):
+                nb += 1
+                for r in range(world):
+                    if r != o:
+                        h2[r].copy_range_from(h2[o], b, e)
+            for h in h2:
+                h.factor_steps(st, st + 1)
+        assert nb > 0
+    else:
+        for h in h2:
+            h.factor()
+    for h in h2:
+        assert h.sync()
+        assert rel_err(h.get_factor(), ref) < TOL
+    for h in h2 + h1:
+        h.close()
