@@ -183,7 +183,8 @@ def sharded_arm(args, kind, N, desc, rank, world, local):
     S = inspector.analyze(n, Ap, Ai, Ax, args.cost, args.level, args.div)
     t_insp = time.time() - t0
     t0 = time.time()
-    SC = ShardedCholesky(S, rank, world, local, top_levels=args.top_levels, block_cols=args.block_cols)
+    SC = ShardedCholesky(S, rank, world, local, top_levels=args.top_levels, block_cols=args.block_cols,
+                         top_distributed=not args.replicate_top)
     t_create = time.time() - t0
     F = S.flops
     h_vals = torch.from_numpy(S.A2_x.copy()).pin_memory()
@@ -211,8 +212,7 @@ def sharded_arm(args, kind, N, desc, rank, world, local):
     barrier()
     clocks = sampler.stop()
     total_ms = e0.elapsed_time(e1)
-    t1 = SC.h1.factor_times()
-    t2 = SC.h2.factor_times()
+    p1_ms, ex_ms, p2_ms = SC.phase_times_ms()
     # end to end: A's values from pinned host memory every step, a device->host read of the result's status + tail
     tail = torch.empty(1024, dtype=torch.float64).pin_memory()
     barrier()
@@ -228,10 +228,9 @@ def sharded_arm(args, kind, N, desc, rank, world, local):
     fro = float((SC.lv * SC.lv).sum().item())
     trace = float(S.A2_x[S.A2_p[:-1]].sum())
     prof = SC.h2.factor_profiled() if rank == 0 else None
-    t_loc = torch.tensor([total_ms, e2e_ms, t1["levels"] + t1["last_level"], t2["levels"] + t2["last_level"]],
-                         dtype=torch.float64, device="cuda")
+    t_loc = torch.tensor([total_ms, e2e_ms, p1_ms, ex_ms, p2_ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t_loc, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, p1_s, p2_s = [float(v) for v in t_loc.tolist()]
+    total_ms, e2e_ms, p1_ms, ex_ms, p2_ms = [float(v) for v in t_loc.tolist()]
     per_step = total_ms / args.steps
     if rank == 0:
         dmma = [k for k in prof if k.endswith("dmma")]
@@ -247,12 +246,14 @@ def sharded_arm(args, kind, N, desc, rank, world, local):
                        "nnzL": int(S.xsize), "flops_sum_cc2": F,
                        "lbc": {"costParam": args.cost, "levelParam": args.level, "divRate": args.div,
                                "hlevels": int(S.nLevels), "wpartitions": int(S.nParts)},
-                       "parallelism": f"bottom subtrees sharded over {world} GPUs, {args.top_levels} top H-level(s) replicated; "
-                                      f"{SC.n_broadcasts} NCCL broadcasts per factorization",
+                       "parallelism": f"bottom subtrees sharded over {world} GPUs; {args.top_levels} top H-level(s) "
+                                      + ("block-cyclic by target block column, panel broadcast before each step; "
+                                         if SC.top_distributed else "replicated; ")
+                                      + f"{SC.n_broadcasts} NCCL broadcasts per factorization",
                        "l2": f"working set {8 * S.xsize / 1e6:.0f} MB (factor) > 126 MB L2, no flush needed"},
-            "breakdown_ms": {"phase1_owned_subtrees_max_rank": p1_s * 1e3, "phase2_shared_top": p2_s * 1e3,
-                             "exchange_and_sync": per_step - (p1_s + p2_s) * 1e3,
-                             "exchange_bytes_received_rank0": SC.exchange_bytes},
+            "breakdown_ms": {"phase1_owned_subtrees_max_rank": p1_ms, "bottom_panel_exchange_max_rank": ex_ms,
+                             "phase2_top_separators_max_rank": p2_ms,
+                             "bottom_exchange_bytes_received_rank0": SC.exchange_bytes},
             "e2e": {"value": F / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(8 * S.nnzA), "d2h_bytes_per_step": 8 * 1024 + 4,
                     "api": "ShardedCholesky.set_values (pinned) + factor + sync + read-back of the factor's tail"},
@@ -283,6 +284,7 @@ def main():
     ap.add_argument("--block-cols", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N>1: one full factorization per GPU instead of sharding")
+    ap.add_argument("--replicate-top", action="store_true", help="N>1: every rank computes the top separators")
     ap.add_argument("--top-levels", type=int, default=1, help="N>1: LBC H-levels kept shared (computed by every rank)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -215,6 +215,16 @@ int parsy_cuda_num_steps(parsy_cuda_solver* s);
 int parsy_cuda_first_top_step(parsy_cuda_solver* s);
 int parsy_cuda_step_bcasts(parsy_cuda_solver* s, int step, int64_t* owner_begin_end_triples, int max_triples);
 int parsy_cuda_factor_steps(parsy_cuda_solver* s, int step_begin, int step_end);
+/* Look-ahead form of the same loop (the bulk updates R_i run on the main stream while the side stream carries
+ * broadcast -> POTRF/TRSM -> updates into the next block column):
+ *   parsy_cuda_factor_steps(h, 0, first_top);
+ *   for i in first_top..n:  parsy_cuda_step_begin(h, i, i == first_top);  <broadcasts on parsy_cuda_stream2(h)>;
+ *                           parsy_cuda_step_run(h, i);
+ *   parsy_cuda_steps_end(h); */
+int parsy_cuda_step_begin(parsy_cuda_solver* s, int step, int first);
+int parsy_cuda_step_run(parsy_cuda_solver* s, int step);
+int parsy_cuda_steps_end(parsy_cuda_solver* s);
+void* parsy_cuda_stream2(parsy_cuda_solver* s);   /* cudaStream_t of the side (high-priority) stream */
 /* dst.lValues[begin,end) = src.lValues[begin,end), device to device (emulates the exchange between ranks on one GPU). */
 int parsy_cuda_copy_range(parsy_cuda_solver* dst, parsy_cuda_solver* src, int64_t begin, int64_t end);
 

@@ -30,6 +30,7 @@ struct parsy_cuda_solver {
   bool lookahead = true;
   int phase = 0;              // 0 single GPU, 1 owned bottom subtrees, 2 shared top (multi-GPU)
   bool owns_lv = true;
+  int la_first = 0;
   bool dist_top = false;      // phase 2 with block-cyclic top: stepwise API, broadcasts between steps
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device arrays
@@ -891,6 +892,46 @@ extern "C" int parsy_cuda_factor_steps(parsy_cuda_solver* s, int begin, int end)
   if (end == (int)s->plan.steps.size()) s->factored = true;
   return PARSY_CUDA_OK;
 }
+// Look-ahead variant of the stepwise API (two streams, same dependency rules as enqueue_factor_steps):
+//   parsy_cuda_step_begin(h, i, first)  side stream waits for everything block column i depends on from the main stream
+//   <host: broadcasts of step i's panels on the side stream>
+//   parsy_cuda_step_run(h, i)           side: F_i, A_i      main: R_i (after F_i)
+//   parsy_cuda_steps_end(h)             main waits for the side stream
+extern "C" int parsy_cuda_step_begin(parsy_cuda_solver* s, int step, int first) {
+  if (!s || step < 0 || step >= (int)s->plan.steps.size()) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad step");
+  CU(cudaSetDevice(s->device));
+  if (first) {
+    CU(cudaEventRecord(s->ev_fork, s->stream));
+    CU(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
+    s->la_first = step;
+  } else if (step - 2 >= s->la_first) {
+    CU(cudaStreamWaitEvent(s->stream2, s->ev_R[(step - 1) & 1], 0));
+  }
+  return PARSY_CUDA_OK;
+}
+extern "C" int parsy_cuda_step_run(parsy_cuda_solver* s, int step) {
+  if (!s || step < 0 || step >= (int)s->plan.steps.size()) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad step");
+  CU(cudaSetDevice(s->device));
+  const Step& S = s->plan.steps[step];
+  int64_t l = launch_factor_phase(s, S, s->stream2, nullptr);
+  CU(cudaEventRecord(s->ev_F[step & 1], s->stream2));
+  l += launch_update_group(s, S.upd[0], s->stream2, nullptr);
+  CU(cudaStreamWaitEvent(s->stream, s->ev_F[step & 1], 0));
+  l += launch_update_group(s, S.upd[1], s->stream, nullptr);
+  CU(cudaEventRecord(s->ev_R[(step + 1) & 1], s->stream));
+  s->launches_factor += l;
+  CU(cudaGetLastError());
+  if (step + 1 == (int)s->plan.steps.size()) s->factored = true;
+  return PARSY_CUDA_OK;
+}
+extern "C" int parsy_cuda_steps_end(parsy_cuda_solver* s) {
+  if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  CU(cudaEventRecord(s->ev_join, s->stream2));
+  CU(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+  return PARSY_CUDA_OK;
+}
+extern "C" void* parsy_cuda_stream2(parsy_cuda_solver* s) { return s ? (void*)s->stream2 : nullptr; }
+
 // dst.lValues[begin, end) = src.lValues[begin, end) (device to device; used to emulate the exchange on one GPU)
 extern "C" int parsy_cuda_copy_range(parsy_cuda_solver* dst, parsy_cuda_solver* src, int64_t begin, int64_t end) {
   if (!dst || !src || begin < 0 || end > dst->plan.xsize || end > src->plan.xsize || begin > end) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad range");

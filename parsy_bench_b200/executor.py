@@ -404,6 +404,21 @@ class Solver:
     def factor_steps(self, begin, end):
         self._call("parsy_cuda_factor_steps", int(begin), int(end))
 
+    def step_begin(self, step, first):
+        self._call("parsy_cuda_step_begin", int(step), int(bool(first)))
+
+    def step_run(self, step):
+        self._call("parsy_cuda_step_run", int(step))
+
+    def steps_end(self):
+        self._call("parsy_cuda_steps_end")
+
+    def stream2(self):
+        f = self._L.parsy_cuda_stream2
+        f.restype = c_void_p
+        f.argtypes = [c_void_p]
+        return f(self._h)
+
     def copy_range_from(self, other, begin, end):
         f = self._L.parsy_cuda_copy_range
         f.restype = c_int

@@ -33,6 +33,8 @@ class ShardedCholesky:
         self.lv = torch.as_tensor(_DevArray(p1["factor"], S.xsize), device=self.device)
         self.s1 = torch.cuda.ExternalStream(p1["stream"], device=self.device)
         self.s2 = torch.cuda.ExternalStream(p2["stream"], device=self.device)
+        self.s2side = torch.cuda.ExternalStream(self.h2.stream2(), device=self.device)
+        self.lookahead = True
         self.exchange_bytes = int(sum(int((r[:, 1] - r[:, 0]).sum()) for i, r in enumerate(self.ranges) if i != rank) * 8)
         self.n_broadcasts = int(sum(len(r) for r in self.ranges))
         self.nsteps, self.first_top = self.h2.num_steps(), self.h2.first_top_step()
@@ -51,26 +53,52 @@ class ShardedCholesky:
         """Enqueues phase 1, the NVLink exchange and phase 2; returns without synchronising."""
         torch = self.torch
         self.s1.wait_stream(self.s2)      # phase 1 re-zeroes the buffer the previous phase 2 may still be writing
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        self.events = evs
+        evs[0].record(self.s1)
         self.h1.factor()
+        evs[1].record(self.s1)
         with torch.cuda.stream(self.s1):
             if dist is not None and self.world > 1:
                 for owner, runs in enumerate(self.ranges):
                     for b, e in runs:
                         dist.broadcast(self.lv[int(b):int(e)], src=owner)
-            ev = torch.cuda.Event()
+            ev = evs[2]
             ev.record(self.s1)
         self.s2.wait_event(ev)
         if not self.top_distributed:
             self.h2.factor()
+            evs[3].record(self.s2)
             return
         # distributed top: updates from the bottom into the owned top block columns, then step by step:
         # owners broadcast the block columns about to be factored, every rank factors them, owners update theirs
-        with torch.cuda.stream(self.s2):
-            self.h2.factor_steps(0, self.first_top)
-            for st in range(self.first_top, self.nsteps):
-                for owner, b, e in self.step_bcasts.get(st, ()):
-                    dist.broadcast(self.lv[b:e], src=owner)
-                self.h2.factor_steps(st, st + 1)
+        if not self.lookahead:
+            with torch.cuda.stream(self.s2):
+                self.h2.factor_steps(0, self.first_top)
+                for st in range(self.first_top, self.nsteps):
+                    for owner, b, e in self.step_bcasts.get(st, ()):
+                        dist.broadcast(self.lv[b:e], src=owner)
+                    self.h2.factor_steps(st, st + 1)
+                evs[3].record(self.s2)
+            return
+        # look-ahead: the side stream carries broadcast -> POTRF/TRSM -> updates into the next block column, the main
+        # stream the bulk of this rank's trailing updates
+        self.h2.factor_steps(0, self.first_top)
+        for st in range(self.first_top, self.nsteps):
+            self.h2.step_begin(st, st == self.first_top)
+            bc = self.step_bcasts.get(st, ())
+            if bc:
+                with torch.cuda.stream(self.s2side):
+                    for owner, b, e in bc:
+                        dist.broadcast(self.lv[b:e], src=owner)
+            self.h2.step_run(st)
+        self.h2.steps_end()
+        evs[3].record(self.s2)
+
+    def phase_times_ms(self):
+        """(phase 1, bottom exchange, phase 2 incl. its per-step broadcasts) of the last factor(), after sync()."""
+        e = self.events
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])
 
     def sync(self):
         ok1 = self.h1.sync()
