@@ -884,26 +884,28 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
   const SolveTask T = tasks[C.first];
   const SupInfo I = sup[T.sup];
   const int nb = T.nb, r = I.r, cbase = I.col0 + T.j0;
-  // slice of L21: row ri, columns cg*32 .. cg*32+31, loaded ahead of the wait
+  // slice of L21 in register tiles of 64 rows: row ri, columns cg*32 .. cg*32+31; the first tile is loaded ahead of
+  // the wait, the following ones (same diagonal-block solve, up to SOLVE_TASK_ROWS rows per task) stream behind it
   const int ri = tid & 63, cg = tid >> 6;
+  const double* __restrict__ Pbase = lv + I.valptr + (int64_t)T.j0 * r + T.row0;
+  const int* __restrict__ rowsT = lR + I.rowptr + T.row0;
   double lval[32];
   int myrow = -1;
   {
-    const double* __restrict__ P = lv + I.valptr + (int64_t)T.j0 * r + T.row0;
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
       const int c = cg * 32 + u;
-      lval[u] = (ri < T.nrows && c < nb) ? P[(int64_t)c * r + ri] : 0.0;
+      lval[u] = (ri < T.nrows && c < nb) ? Pbase[(int64_t)c * r + ri] : 0.0;
     }
-    if (cg == 0 && ri < T.nrows) myrow = lR[I.rowptr + T.row0 + ri];
+    if (cg == 0 && ri < T.nrows) myrow = rowsT[ri];
   }
   const double* __restrict__ X = linv + (int64_t)T.slot * NB_MAX * NB_MAX;
   if (tid == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
   __syncthreads();
   if (tid < nb) sy[tid] = __ldcg(&y[cbase + tid]);
   __syncthreads();
-  // x_b = inv(L_bb) y_b, recomputed by every slice (an extra flag hop would sit on the critical path):
-  // row i = tid & 127, the two halves of the block split k
+  // x_b = inv(L_bb) y_b, recomputed by every task of the block column (an extra flag hop would sit on the critical
+  // path): row i = tid & 127, the two halves of the block split k
   const int i = tid & 127, half = tid >> 7;
   {
     double acc0 = 0.0, acc1 = 0.0;
@@ -927,22 +929,34 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
   }
   __syncthreads();
   if (T.nrows > 0) {
-    double t0 = 0.0, t1 = 0.0;
+    for (int sub = 0; sub < T.nrows; sub += SOLVE_TILE_ROWS) {
+      if (sub > 0) {
+        const int rr = sub + ri;
 #pragma unroll
-    for (int u = 0; u < 32; u += 2) {
-      t0 = fma(lval[u], sx[(cg * 32 + u) & (NB_MAX - 1)], t0);
-      t1 = fma(lval[u + 1], sx[(cg * 32 + u + 1) & (NB_MAX - 1)], t1);
+        for (int u = 0; u < 32; ++u) {
+          const int c = cg * 32 + u;
+          lval[u] = (rr < T.nrows && c < nb) ? Pbase[(int64_t)c * r + rr] : 0.0;
+        }
+        myrow = (cg == 0 && rr < T.nrows) ? rowsT[rr] : -1;
+        __syncthreads();   // spart of the previous tile has been consumed
+      }
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int u = 0; u < 32; u += 2) {
+        t0 = fma(lval[u], sx[(cg * 32 + u) & (NB_MAX - 1)], t0);
+        t1 = fma(lval[u + 1], sx[(cg * 32 + u + 1) & (NB_MAX - 1)], t1);
+      }
+      spart[tid] = t0 + t1;
+      __syncthreads();
+      if (tid < 64 && myrow >= 0) atomicAdd(&y[myrow], -(spart[tid] + spart[tid + 64] + spart[tid + 128] + spart[tid + 192]));
     }
-    spart[tid] = t0 + t1;
-    __syncthreads();
-    if (tid < 64 && myrow >= 0) atomicAdd(&y[myrow], -(spart[tid] + spart[tid + 64] + spart[tid + 128] + spart[tid + 192]));
     __threadfence();
     __syncthreads();
     for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) atomicAdd(&done[targets[q]], 1);
   }
 }
 
-__global__ void __launch_bounds__(SWEEP_THREADS) k_bwd_dataflow(
+__global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
     const SolveCta* __restrict__ ctas, int nctas, const SolveTask* __restrict__ tasks,
     const int* __restrict__ targets, const int* __restrict__ ntiles, int* __restrict__ cnt, int* __restrict__ solved,
     int* __restrict__ ticket, const SupInfo* __restrict__ sup, const int* __restrict__ lR,
@@ -996,35 +1010,55 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_bwd_dataflow(
   const SolveTask T = tasks[C.first];
   const SupInfo I = sup[T.sup];
   const int nb = T.nb, r = I.r, cbase = I.col0 + T.j0;
-  // slice of L21 ahead of the wait: warp w owns columns w, w+8, ...; lanes own rows lane, lane+32
+  // slice of L21 in register tiles of 64 rows: warp w owns columns w, w+8, ...; lanes own rows lane, lane+32.
+  // The first tile is loaded ahead of the wait; partial sums of all tiles of the task accumulate in registers.
+  const double* __restrict__ Pbase = lv + I.valptr + (int64_t)T.j0 * r + T.row0;
+  const int* __restrict__ rowsT = lR + I.rowptr + T.row0;
   double lval[16][2];
-  {
-    const double* __restrict__ P = lv + I.valptr + (int64_t)T.j0 * r + T.row0;
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int c = warp + 8 * u;
+  for (int u = 0; u < 16; ++u) {
+    const int c = warp + 8 * u;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ii = lane + 32 * h;
-        lval[u][h] = (c < nb && ii < T.nrows) ? P[(int64_t)c * r + ii] : 0.0;
-      }
+    for (int h = 0; h < 2; ++h) {
+      const int ii = lane + 32 * h;
+      lval[u][h] = (c < nb && ii < T.nrows) ? Pbase[(int64_t)c * r + ii] : 0.0;
     }
   }
   int myrow = -1;
-  if (tid < T.nrows) myrow = lR[I.rowptr + T.row0 + tid];
+  if (tid < SOLVE_TILE_ROWS && tid < T.nrows) myrow = rowsT[tid];
   for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) spin_until_ge_busy(&solved[targets[q]], 1);
   __syncthreads();
   if (T.nrows > 0) {
-    if (tid < SOLVE_TILE_ROWS) sx[tid] = (myrow >= 0) ? __ldcg(&x[myrow]) : 0.0;
-    __syncthreads();
-    const double x0 = sx[lane], x1 = sx[lane + 32];
+    double part[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) part[u] = 0.0;
+    for (int sub = 0; sub < T.nrows; sub += SOLVE_TILE_ROWS) {
+      if (sub > 0) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int c = warp + 8 * u;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ii = sub + lane + 32 * h;
+            lval[u][h] = (c < nb && ii < T.nrows) ? Pbase[(int64_t)c * r + ii] : 0.0;
+          }
+        }
+        myrow = (tid < SOLVE_TILE_ROWS && sub + tid < T.nrows) ? rowsT[sub + tid] : -1;
+        __syncthreads();   // sx of the previous tile has been consumed
+      }
+      if (tid < SOLVE_TILE_ROWS) sx[tid] = (myrow >= 0) ? __ldcg(&x[myrow]) : 0.0;
+      __syncthreads();
+      const double x0 = sx[lane], x1 = sx[lane + 32];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) part[u] = fma(lval[u][0], x0, fma(lval[u][1], x1, part[u]));
+    }
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int c = warp + 8 * u;
-      double part = fma(lval[u][0], x0, lval[u][1] * x1);
+      double p2 = part[u];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0 && c < nb) atomicAdd(&x[cbase + c], -part);
+      for (int o = 16; o > 0; o >>= 1) p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+      if (lane == 0 && c < nb) atomicAdd(&x[cbase + c], -p2);
     }
   }
   __threadfence();

@@ -439,14 +439,14 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         const BlockTask& b = P.block_tasks[i];
         const SupInfo& I = P.sup[b.sup];
         const int below = I.r - b.j0 - b.nb;
-        const int ntile = std::max(1, cdiv(below, SOLVE_TILE_ROWS));
+        const int ntile = std::max(1, cdiv(below, SOLVE_TASK_ROWS));
         const int nd = node_first[b.sup] + b.j0 / NB;
         P.node_tiles[nd] = ntile;
         for (int k = 0; k < ntile; ++k) {
           SolveTask t; memset(&t, 0, sizeof(t));
           t.sup = b.sup; t.node = nd; t.j0 = b.j0; t.nb = b.nb; t.slot = b.slot;
-          t.row0 = b.j0 + b.nb + k * SOLVE_TILE_ROWS;
-          t.nrows = std::max(0, std::min(SOLVE_TILE_ROWS, I.r - t.row0));
+          t.row0 = b.j0 + b.nb + k * SOLVE_TASK_ROWS;
+          t.nrows = std::max(0, std::min(SOLVE_TASK_ROWS, I.r - t.row0));
           t.first = k == 0;
           add_targets(t, I);
           SolveCta c; c.kind = 1; c.first = (int32_t)P.solve_tasks.size(); c.count = 1; c.pad = 0;

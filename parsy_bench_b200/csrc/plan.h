@@ -73,7 +73,8 @@ static_assert(sizeof(BlockTask) == 32, "BlockTask layout");
 // ---- single-launch dataflow sweeps -------------------------------------------------------------------
 // A "node" is what gets solved as one unit: a narrow supernode or one block column.  A "solve task" is what one
 // warp (narrow supernode) or one CTA (128-row slice of a block column's rows below the diagonal block) does.
-constexpr int SOLVE_TILE_ROWS = 64;
+constexpr int SOLVE_TILE_ROWS = 64;     // rows a sweep CTA holds in registers at a time
+constexpr int SOLVE_TASK_ROWS = 256;    // rows of one solve task (4 register tiles share one diagonal-block solve)
 struct SolveTask {
   int32_t sup;        // supernode
   int32_t node;       // node this task belongs to (the one whose solution it consumes)
