@@ -45,14 +45,17 @@ struct GemmCfg {
   static constexpr int STAGE_DOUBLES = KC * (LDA + LDB);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_DOUBLES * 8 + (TM + TN) * 4;
   static constexpr int FM = WM / 8, FN = WN / 8;
+  static constexpr int MIN_CTAS = (THREADS <= 256 && SMEM <= 100 * 1024) ? 2 : 1;
 };
-using Cfg128 = GemmCfg<128, 128, 32, 32, 16, 3>;   // 16 warps: 4 per SMSP keep the DMMA pipe fed across LDS/barrier stalls
+// 128x64 tiles, 8 warps, two CTAs per SM: one CTA's prologue/epilogue overlaps the other's main loop and the SM
+// still holds 16 warps (4 per SMSP) to keep the DMMA pipe fed across LDS/barrier stalls
+using Cfg128 = GemmCfg<128, 64, 32, 32, 16, 3>;
 using Cfg64 = GemmCfg<64, 64, 32, 32, 8, 4>;
 // TRSM: 64-row tiles double the CTA count of the latency-critical panel solve; TN = 128 keeps it in place
 using CfgTrsm = GemmCfg<64, 128, 32, 32, 16, 3>;
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS) k_gemm_tiles(const GemmTask* __restrict__ tasks, int ntasks,
+__global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) k_gemm_tiles(const GemmTask* __restrict__ tasks, int ntasks,
                                                             double* __restrict__ lv, const double* __restrict__ linv,
                                                             const int* __restrict__ rel) {
   extern __shared__ __align__(16) double smem[];
@@ -69,11 +72,11 @@ __global__ void __launch_bounds__(C::THREADS) k_gemm_tiles(const GemmTask* __res
   int t = bid - T.tile0;
   const int MT = (T.M + C::TM - 1) / C::TM;
   int mi, ni;
-  if (T.flags & GF_LOWER) {        // lower trapezoid of tiles: column ni holds row tiles ni..MT-1
+  if (T.flags & GF_LOWER) {        // lower trapezoid of tiles: column tile ni holds the row tiles that reach its columns
     ni = 0;
-    int cnt = MT;
-    while (t >= cnt) { t -= cnt; ++ni; cnt = MT - ni; }
-    mi = ni + t;
+    int first = 0, cnt = MT;
+    while (t >= cnt) { t -= cnt; ++ni; first = (ni * C::TN) / C::TM; cnt = MT - first; }
+    mi = first + t;
   } else {
     mi = t % MT; ni = t / MT;
   }

@@ -28,9 +28,12 @@ void enumerate_pairs(std::vector<PairDesc>& out, int supNo, const int* blockSet,
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-static inline int lower_tiles(int M, int N, int T) {   // tiles (mi, ni) of a T x T grid with mi >= ni
-  const int MT = cdiv(M, T), NT = cdiv(N, T);
-  return NT * MT - NT * (NT - 1) / 2;
+// tiles (mi, ni) of a TM x TN grid over the lower trapezoid: column tile ni needs row tiles from (ni*TN)/TM on
+static inline int lower_tiles(int M, int N, int TM, int TN) {
+  const int MT = cdiv(M, TM), NT = cdiv(N, TN);
+  int cnt = 0;
+  for (int ni = 0; ni < NT; ++ni) cnt += MT - (ni * TN) / TM;
+  return cnt;
 }
 
 int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo,
@@ -370,9 +373,9 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     for (int g = 0; g < 2; ++g) {
       UpdGroup& U = S.upd[g];
       acc = 0;
-      for (int i = U.u128.begin; i < U.u128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128); }
+      for (int i = U.u128.begin; i < U.u128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128, 64); }
       U.tiles128 = acc; acc = 0;
-      for (int i = U.u64.begin; i < U.u64.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 64); }
+      for (int i = U.u64.begin; i < U.u64.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 64, 64); }
       U.tiles64 = acc;
     }
     acc = 0;
