@@ -229,7 +229,14 @@ __global__ void __launch_bounds__(128) k_update_small(const SmallTask* __restric
   const double* __restrict__ src = lv + T.a_off;
   // rows K..KT of Bs are multiplied by a[k] = 0: they must hold zeros, not whatever the SM's shared memory kept
   const int KT = KMAX <= 4 ? 4 : (T.K <= 4 ? 4 : (T.K <= 16 ? 16 : 32));
-  for (int k = 0; k < KT; ++k) Bs[k * 33 + lane] = (k < T.K && lane < T.N) ? src[(int64_t)k * T.lda + lane] : 0.0;
+  // batches of 8 independent loads (a rolled loop would pay one memory latency per k)
+  for (int k0 = 0; k0 < KT; k0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (k0 + u < T.K && lane < T.N) ? src[(int64_t)(k0 + u) * T.lda + lane] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (k0 + u < KT) Bs[(k0 + u) * 33 + lane] = v[u];
+  }
   if (lane < T.N) sRelc[warp][lane] = rel[T.rel_off + lane];
   __syncwarp();
   if (KMAX <= 4 || T.K <= 4) small_update_rows<4>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
@@ -255,8 +262,14 @@ __global__ void __launch_bounds__(128) k_factor_small(const int* __restrict__ li
   double* __restrict__ P = lv + I.valptr;
   double* S = sD[warp];
   double* R = sR[warp];
-  for (int c = 0; c < w; ++c)
-    if (lane < w) S[c * LDS + lane] = P[(int64_t)c * r + lane];
+  // diagonal block: batches of 8 independent column loads
+  for (int c0 = 0; c0 < w; c0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (c0 + u < w && lane < w) ? P[(int64_t)(c0 + u) * r + lane] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (c0 + u < w && lane < w) S[(c0 + u) * LDS + lane] = v[u];
+  }
   __syncwarp();
   for (int c = 0; c < w; ++c) {
     double acc = (lane < w) ? S[c * LDS + lane] : 0.0;
@@ -271,17 +284,28 @@ __global__ void __launch_bounds__(128) k_factor_small(const int* __restrict__ li
   }
   for (int c = 0; c < w; ++c)
     if (lane >= c && lane < w) P[(int64_t)c * r + lane] = S[c * LDS + lane];
-  // rows below the diagonal block: x * L11' = a, one lane per row
+  // rows below the diagonal block: x * L11' = a, one lane per row; columns in groups of 8 so that the group's loads
+  // are in flight together (one memory latency per group instead of one per column)
+  constexpr int G = WMAX < 8 ? WMAX : 8;
   for (int i = w + lane; i < r; i += 32) {
     double x[WMAX];
 #pragma unroll
-    for (int c = 0; c < WMAX; ++c) {
-      if (c < w) {
-        double a = P[(int64_t)c * r + i];
+    for (int c0 = 0; c0 < WMAX; c0 += G) {
+      if (c0 < w) {
 #pragma unroll
-        for (int k = 0; k < c; ++k) a = fma(-x[k], S[k * LDS + c], a);
-        x[c] = a * R[c];
-        P[(int64_t)c * r + i] = x[c];
+        for (int u = 0; u < G; ++u) x[c0 + u] = (c0 + u < w) ? P[(int64_t)(c0 + u) * r + i] : 0.0;
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          const int c = c0 + u;
+          if (c < w) {
+            double a = x[c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) a = fma(-x[k], S[k * LDS + c], a);
+            x[c] = a * R[c];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) if (c0 + u < w) P[(int64_t)(c0 + u) * r + i] = x[c0 + u];
       }
     }
   }
