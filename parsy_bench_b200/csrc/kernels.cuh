@@ -575,13 +575,17 @@ __device__ __forceinline__ void load_padded_block(double* S, const double* __res
   }
 }
 
+// smem_cols = widest (padded) block of the launch: narrower steps take less shared memory and co-reside on an SM
+__host__ __device__ constexpr size_t potrf_smem_bytes(int smem_cols) {
+  return (size_t)(smem_cols * PLD + NB_MAX + POTRF_XD + POTRF_T) * 8;
+}
 __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_block(const BlockTask* __restrict__ bt,
                                                                 const SupInfo* __restrict__ sup,
                                                                 double* __restrict__ lv, double* __restrict__ linv,
-                                                                int* __restrict__ info) {
+                                                                int* __restrict__ info, int smem_cols) {
   extern __shared__ __align__(16) double smem[];
   double* S = smem;
-  double* rd = S + POTRF_S;
+  double* rd = S + smem_cols * PLD;
   double* XD = rd + NB_MAX;
   double* Tt = XD + POTRF_XD;
   const BlockTask B = bt[blockIdx.x];

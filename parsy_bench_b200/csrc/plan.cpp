@@ -312,6 +312,30 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   P.rel_prefix[P.pairs.size()] = rel;
   P.rel_entries = rel;
 
+  // split-K: a launch with fewer tiles than the GPU has CTA slots cannot fill the machine, and its tiles with a long
+  // K (wide descendants) set the duration; the epilogue is an atomic add, so K can be cut into independent pieces
+  {
+    constexpr int FILL = 2 * 148;
+    std::vector<int32_t> tl(2 * (size_t)nsteps, 0);
+    auto ntiles = [&](const Gen& g) { return g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : lower_tiles(g.t.M, g.t.N, 64, 64); };
+    for (const Gen& g : gen) if (g.cls == 1 || g.cls == 2) tl[2 * g.step + g.grp] += ntiles(g);
+    const size_t n0 = gen.size();
+    for (size_t i = 0; i < n0; ++i) {
+      if ((gen[i].cls != 1 && gen[i].cls != 2) || gen[i].t.K < 128) continue;
+      const int total = tl[2 * gen[i].step + gen[i].grp];
+      if (total >= FILL) continue;
+      const int K = gen[i].t.K;
+      const int f = std::min(std::min(cdiv(K, 64), cdiv(FILL, std::max(total, 1))), 8);
+      if (f <= 1) continue;
+      const int chunk = cdiv(cdiv(K, f), 16) * 16;
+      for (int k0 = chunk; k0 < K; k0 += chunk) {
+        Gen g = gen[i];
+        g.t.a_off += (int64_t)k0 * g.t.lda; g.t.b_off += (int64_t)k0 * g.t.ldb; g.t.K = std::min(chunk, K - k0);
+        gen.push_back(g);
+      }
+      gen[i].t.K = chunk;
+    }
+  }
   if (gen.size() > (size_t)INT32_MAX) { P.error = "task list too large"; return PARSY_CUDA_ERR_BAD_ARG; }
   std::vector<int32_t> ord(gen.size());
   for (size_t i = 0; i < gen.size(); ++i) ord[i] = (int32_t)i;

@@ -121,8 +121,9 @@ static int64_t launch_factor_phase(parsy_cuda_solver* s, const Step& S, cudaStre
   }
   if (S.blocks.size()) {
     PROF_BEGIN(1);
-    k_potrf_block<<<S.blocks.size(), POTRF_THREADS, POTRF_SMEM, st>>>(s->d_blocks + S.blocks.begin, s->d_sup, s->d_lv,
-                                                                      s->d_linv, s->d_info);
+    const int cols = (S.max_nb + 15) & ~15;
+    k_potrf_block<<<S.blocks.size(), POTRF_THREADS, potrf_smem_bytes(cols), st>>>(s->d_blocks + S.blocks.begin, s->d_sup,
+                                                                                  s->d_lv, s->d_linv, s->d_info, cols);
     PROF_END();
     ++launches;
   }
