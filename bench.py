@@ -283,6 +283,7 @@ def main():
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--block-cols", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lookahead", action="store_true", help="single stream, no overlap of POTRF/TRSM with the bulk updates")
     ap.add_argument("--ignore-hlevels", action="store_true", help="schedule by dependencies only (no LBC H-level barriers)")
     ap.add_argument("--replicas", action="store_true", help="N>1: one full factorization per GPU instead of sharding")
     ap.add_argument("--replicate-top", action="store_true", help="N>1: every rank computes the top separators")
@@ -316,7 +317,8 @@ def main():
     t_insp = time.time() - t0
     t0 = time.time()
     H = ex.Solver(n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels, S.levelPtr,
-                  S.parPtr, S.partition, device=local, block_cols=args.block_cols, ignore_hlevels=args.ignore_hlevels)
+                  S.parPtr, S.partition, device=local, block_cols=args.block_cols, ignore_hlevels=args.ignore_hlevels,
+                  lookahead=not args.no_lookahead)
     t_create = time.time() - t0
     st = H.stats()
     F = S.flops
