@@ -864,12 +864,14 @@ __device__ __forceinline__ void spin_until_ge_busy(const int* p, int target) {
 }
 
 constexpr int SWEEP_THREADS = 256;
+constexpr size_t FWD_SWEEP_SMEM = (size_t)(NB_MAX * (NB_MAX + 1) / 2) * 8;   // packed lower triangle of one inverse block
 
 __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
     const SolveCta* __restrict__ ctas, const SolveTask* __restrict__ tasks, const int* __restrict__ targets,
     const int* __restrict__ need, int* __restrict__ done, int* __restrict__ ticket, const SupInfo* __restrict__ sup,
     const int* __restrict__ lR, const double* __restrict__ lv, const double* __restrict__ linv,
     double* __restrict__ y, double* __restrict__ xs) {
+  extern __shared__ __align__(16) double sX[];   // packed lower triangle of the inverse diagonal block (FWD_SWEEP_SMEM)
   __shared__ int s_cta;
   __shared__ double sy[NB_MAX], sx[NB_MAX], spart[SWEEP_THREADS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -930,10 +932,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
     }
     if (cg == 0 && ri < T.nrows) myrow = rowsT[ri];
   }
-  const double* __restrict__ X = linv + (int64_t)T.slot * NB_MAX * NB_MAX;
+  // inverse diagonal block: lower triangle packed by columns (column k starts at k*nb - k(k-1)/2), staged with
+  // cp.async ahead of the wait so that the post-wait GEMV reads shared memory, not L2
+  {
+    const double* __restrict__ X = linv + (int64_t)T.slot * NB_MAX * NB_MAX;
+    const int i2 = tid & 127;
+    for (int k = tid >> 7; k < nb; k += 2)
+      if (i2 >= k && i2 < nb) cp_async8(&sX[k * nb - (k * (k - 1)) / 2 + (i2 - k)], X + k * NB_MAX + i2, true);
+    cp_async_commit();
+  }
   if (tid == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
   __syncthreads();
   if (tid < nb) sy[tid] = __ldcg(&y[cbase + tid]);
+  cp_async_wait<0>();
   __syncthreads();
   // x_b = inv(L_bb) y_b, recomputed by every task of the block column (an extra flag hop would sit on the critical
   // path): row i = tid & 127, the two halves of the block split k
@@ -943,12 +954,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
     if (i < nb) {
       const int kend = min(i + 1, half ? nb : 64);
       int k = half * 64;
-#pragma unroll 8
+#pragma unroll 4
       for (; k + 1 < kend; k += 2) {
-        acc0 = fma(X[k * NB_MAX + i], sy[k], acc0);
-        acc1 = fma(X[(k + 1) * NB_MAX + i], sy[k + 1], acc1);
+        acc0 = fma(sX[k * nb - (k * (k - 1)) / 2 + (i - k)], sy[k], acc0);
+        acc1 = fma(sX[(k + 1) * nb - ((k + 1) * k) / 2 + (i - k - 1)], sy[k + 1], acc1);
       }
-      if (k < kend) acc0 = fma(X[k * NB_MAX + i], sy[k], acc0);
+      if (k < kend) acc0 = fma(sX[k * nb - (k * (k - 1)) / 2 + (i - k)], sy[k], acc0);
     }
     spart[tid] = acc0 + acc1;
   }
@@ -992,6 +1003,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
     const int* __restrict__ targets, const int* __restrict__ ntiles, int* __restrict__ cnt, int* __restrict__ solved,
     int* __restrict__ ticket, const SupInfo* __restrict__ sup, const int* __restrict__ lR,
     const double* __restrict__ lv, const double* __restrict__ linv, double* __restrict__ x) {
+  extern __shared__ __align__(16) double sX[];   // packed lower triangle of the inverse diagonal block (FWD_SWEEP_SMEM)
   __shared__ int s_cta, s_last;
   __shared__ double sx[SOLVE_TILE_ROWS], sy[NB_MAX];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1057,6 +1069,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
   }
   int myrow = -1;
   if (tid < SOLVE_TILE_ROWS && tid < T.nrows) myrow = rowsT[tid];
+  // whichever task finishes last solves the diagonal block: stage its inverse (packed lower triangle) ahead of the wait
+  {
+    const double* __restrict__ X = linv + (int64_t)T.slot * NB_MAX * NB_MAX;
+    const int i2 = tid & 127;
+    for (int k = tid >> 7; k < nb; k += 2)
+      if (i2 >= k && i2 < nb) cp_async8(&sX[k * nb - (k * (k - 1)) / 2 + (i2 - k)], X + k * NB_MAX + i2, true);
+    cp_async_commit();
+  }
   for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) spin_until_ge_busy(&solved[targets[q]], 1);
   __syncthreads();
   if (T.nrows > 0) {
@@ -1096,16 +1116,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&cnt[T.node], 1) == ntiles[T.node] - 1);
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) { cp_async_wait<0>(); return; }
   // every slice has added its partial: x_b = inv(L_bb)' x_b, one warp per column of the inverse
   __threadfence();
   if (tid < nb) sy[tid] = __ldcg(&x[cbase + tid]);
+  cp_async_wait<0>();
   __syncthreads();
-  const double* __restrict__ X = linv + (int64_t)T.slot * NB_MAX * NB_MAX;
   for (int c = warp; c < nb; c += SWEEP_THREADS / 32) {
     double part = 0.0;
+    const double* __restrict__ col = sX + (c * nb - (c * (c - 1)) / 2) - c;   // col[k] = X(k, c), k >= c
 #pragma unroll 4
-    for (int k = c + lane; k < nb; k += 32) part = fma(X[c * NB_MAX + k], sy[k], part);
+    for (int k = c + lane; k < nb; k += 32) part = fma(col[k], sy[k], part);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) x[cbase + c] = part;

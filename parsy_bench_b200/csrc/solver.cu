@@ -84,6 +84,8 @@ static int ensure_kernel_attrs() {
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg64::SMEM));
   CU(cudaFuncSetAttribute(k_gemm_tiles<CfgTrsm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgTrsm::SMEM));
   CU(cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+  CU(cudaFuncSetAttribute(k_fwd_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SWEEP_SMEM));
+  CU(cudaFuncSetAttribute(k_bwd_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SWEEP_SMEM));
   done = true;
   return 0;
 }
@@ -217,7 +219,7 @@ static int64_t enqueue_fwd(parsy_cuda_solver* s) {
   if (s->dataflow) {
     if (P.solve_ctas.empty()) return 0;
     cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 1), st);
-    k_fwd_dataflow<<<(int)P.solve_ctas.size(), SWEEP_THREADS, 0, st>>>(s->d_sctas, s->d_stasks, s->d_stargets, s->d_need,
+    k_fwd_dataflow<<<(int)P.solve_ctas.size(), SWEEP_THREADS, FWD_SWEEP_SMEM, st>>>(s->d_sctas, s->d_stasks, s->d_stargets, s->d_need,
                                                                        s->d_sync + 1, s->d_sync, s->d_sup, s->d_lR, s->d_lv,
                                                                        s->d_linv, s->d_rhs, s->d_xs);
     cudaMemcpyAsync(s->d_rhs, s->d_xs, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToDevice, st);
@@ -247,7 +249,7 @@ static int64_t enqueue_bwd(parsy_cuda_solver* s) {
   if (s->dataflow) {
     if (P.solve_ctas.empty()) return 0;
     cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 1), st);
-    k_bwd_dataflow<<<(int)P.solve_ctas.size(), SWEEP_THREADS, 0, st>>>(s->d_sctas, (int)P.solve_ctas.size(), s->d_stasks,
+    k_bwd_dataflow<<<(int)P.solve_ctas.size(), SWEEP_THREADS, FWD_SWEEP_SMEM, st>>>(s->d_sctas, (int)P.solve_ctas.size(), s->d_stasks,
                                                                        s->d_stargets, s->d_ntiles, s->d_sync + 1,
                                                                        s->d_sync + 1 + P.n_nodes, s->d_sync, s->d_sup, s->d_lR,
                                                                        s->d_lv, s->d_linv, s->d_rhs);
