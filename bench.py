@@ -433,7 +433,7 @@ def main():
                 "dominant_class": dom,
                 "whole_factor_frac_of_fp64_peak": F / (fac_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
     hbm = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
-    roofline_solve = {"bound": "hbm", "kernel": "forward sweep (k_fwd_small + k_fwd_block)",
+    roofline_solve = {"bound": "hbm", "kernel": "forward sweep (k_fwd_dataflow, one launch)",
                       "achieved": st["bytes_solve"] / (fwd_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                       "frac": st["bytes_solve"] / (fwd_ms * 1e-3) / 1e9 / hbm, "traffic": None,
                       "peak_source": peak_kind + " copy bandwidth", "algorithmic_bytes": st["bytes_solve"],
