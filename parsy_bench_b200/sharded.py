@@ -35,6 +35,8 @@ class ShardedCholesky:
         self.s2 = torch.cuda.ExternalStream(p2["stream"], device=self.device)
         self.s2side = torch.cuda.ExternalStream(self.h2.stream2(), device=self.device)
         self.lookahead = True
+        self.p2p_exchange = True
+        self.p2p_chunk = 1 << 28      # doubles per message (2 GiB)
         self.exchange_bytes = int(sum(int((r[:, 1] - r[:, 0]).sum()) for i, r in enumerate(self.ranges) if i != rank) * 8)
         self.n_broadcasts = int(sum(len(r) for r in self.ranges))
         self.nsteps, self.first_top = self.h2.num_steps(), self.h2.first_top_step()
@@ -60,9 +62,25 @@ class ShardedCholesky:
         evs[1].record(self.s1)
         with torch.cuda.stream(self.s1):
             if dist is not None and self.world > 1:
-                for owner, runs in enumerate(self.ranges):
-                    for b, e in runs:
-                        dist.broadcast(self.lv[int(b):int(e)], src=owner)
+                if self.p2p_exchange:
+                    # all owners send at once (one NCCL group of point-to-point ops): every rank's ingress link is busy
+                    # for the whole exchange instead of waiting for one broadcast root at a time
+                    ops = []
+                    for owner, runs in enumerate(self.ranges):
+                        for b, e in runs:
+                            for c0 in range(int(b), int(e), self.p2p_chunk):
+                                t = self.lv[c0:min(c0 + self.p2p_chunk, int(e))]
+                                if owner == self.rank:
+                                    ops += [dist.P2POp(dist.isend, t, peer) for peer in range(self.world) if peer != owner]
+                                else:
+                                    ops.append(dist.P2POp(dist.irecv, t, owner))
+                    if ops:
+                        for w in dist.batch_isend_irecv(ops):
+                            w.wait()
+                else:
+                    for owner, runs in enumerate(self.ranges):
+                        for b, e in runs:
+                            dist.broadcast(self.lv[int(b):int(e)], src=owner)
             ev = evs[2]
             ev.record(self.s1)
         self.s2.wait_event(ev)
