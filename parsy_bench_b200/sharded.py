@@ -35,7 +35,7 @@ class ShardedCholesky:
         self.s2 = torch.cuda.ExternalStream(p2["stream"], device=self.device)
         self.s2side = torch.cuda.ExternalStream(self.h2.stream2(), device=self.device)
         self.lookahead = True
-        self.p2p_exchange = True
+        self.p2p_exchange = False     # grouped point-to-point was slower than per-owner broadcasts at 8 GPUs (350 vs 286 ms, cfg5)
         self.p2p_chunk = 1 << 28      # doubles per message (2 GiB)
         self.exchange_bytes = int(sum(int((r[:, 1] - r[:, 0]).sum()) for i, r in enumerate(self.ranges) if i != rank) * 8)
         self.n_broadcasts = int(sum(len(r) for r in self.ranges))
