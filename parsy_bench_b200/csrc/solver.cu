@@ -77,16 +77,18 @@ template <class T> static int dev_upload(parsy_cuda_solver* s, T** p, const T* h
   return 0;
 }
 
-static int ensure_kernel_attrs() {
-  static bool done = false;
-  if (done) return 0;
+static int ensure_kernel_attrs(int device) {
+  // opt-in shared-memory sizes are per device (per context)
+  static bool done[64] = {false};
+  if (device >= 0 && device < 64 && done[device]) return 0;
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg128::SMEM));
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg64::SMEM));
   CU(cudaFuncSetAttribute(k_gemm_tiles<CfgTrsm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgTrsm::SMEM));
   CU(cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+  CU(cudaFuncSetAttribute(k_invert_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
   CU(cudaFuncSetAttribute(k_fwd_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SWEEP_SMEM));
   CU(cudaFuncSetAttribute(k_bwd_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SWEEP_SMEM));
-  done = true;
+  if (device >= 0 && device < 64) done[device] = true;
   return 0;
 }
 
@@ -326,7 +328,7 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
   if (opt) o = *opt;
   if (o.device < 0 || o.device >= parsy_cuda_device_count()) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad device ordinal");
   CU(cudaSetDevice(o.device));
-  int rc = ensure_kernel_attrs();
+  int rc = ensure_kernel_attrs(o.device);
   if (rc) return rc;
 
   parsy_cuda_solver* s = new parsy_cuda_solver();
@@ -552,8 +554,6 @@ extern "C" int parsy_cuda_set_factor(parsy_cuda_solver* s, const double* lValues
   const Plan& P = s->plan;
   CU(cudaMemcpyAsync(s->d_lv, lValues, sizeof(double) * (size_t)P.xsize, cudaMemcpyHostToDevice, s->stream));
   if (!P.block_tasks.empty()) {
-    static bool attr = false;
-    if (!attr) { CU(cudaFuncSetAttribute(k_invert_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM)); attr = true; }
     k_invert_block<<<(int)P.block_tasks.size(), POTRF_THREADS, POTRF_SMEM, s->stream>>>(s->d_blocks, s->d_sup, s->d_lv,
                                                                                       s->d_linv);
   }

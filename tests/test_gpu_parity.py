@@ -208,6 +208,30 @@ def test_full_solve_residual_vs_oracle(case):
     H.close()
 
 
+def test_per_step_sweeps_and_single_stream_factorization():
+    """the alternative code paths kept behind options: one launch per dependency step for the sweeps
+    (options.reserved[1]) and the single-stream factorization without look-ahead (options.reserved[0])"""
+    S = analyze("3d27", 16, 8, 1, 2)
+    n = S.n
+    Lref = orc.cholesky_left_par_05(S)
+    b = 1.0 + np.arange(n) / n
+    yr = orc.blockedLsolve(S, Lref, b)
+    xr = orc.blockedLtsolve(S, Lref, yr)
+    H = ex.Solver(n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                  S.levelPtr, S.parPtr, S.partition, lookahead=False, dataflow_sweeps=False)
+    H.set_values(S.A2_x)
+    H.factor()
+    assert H.sync() and rel_err(H.get_factor(), Lref) < TOL
+    H.set_rhs(b)
+    H.solve(ex.SOLVE_FWD)
+    assert rel_err(H.get_rhs(), yr) < 1e-9
+    H.solve(ex.SOLVE_BWD)
+    assert rel_err(H.get_rhs(), xr) < 1e-8
+    st = H.stats()
+    assert st["launches_fwd"] > 1 and st["launches_bwd"] > 1
+    H.close()
+
+
 @pytest.mark.parametrize("case", [("2d5", 1000, 8, 1, 2), ("3d27", 64, 8, 1, 2)])
 def test_full_size_properties(case):
     """BASELINE.json configs 2 and 4 at full size: identities that need no CPU factorization."""
