@@ -157,6 +157,9 @@ int parsy_cuda_factor_times(parsy_cuda_solver* s, double* out3);
  * 0 factor_small, 1 potrf_block, 2 TRSM tiles (DMMA), 3 update tiles 128 (DMMA), 4 update tiles 64 (DMMA),
  * 5 update_small.  This is where bench.py's roofline numbers come from. */
 int parsy_cuda_factor_profiled(parsy_cuda_solver* s, double* class_ms6, int64_t* class_launches6, double* class_flops6);
+/* The same pass, one record per kernel launch: dependency step, kernel class (numbering above), device time in ms.
+ * Returns the number of launches (records beyond max_records are dropped), -1 on error. */
+int parsy_cuda_factor_trace(parsy_cuda_solver* s, int max_records, int* step, int* cls, float* ms);
 
 /* Introspection used by bench.py / tests (counts are exact, computed by the planner). */
 typedef struct parsy_cuda_stats {

@@ -51,8 +51,15 @@ struct GemmCfg {
 // still holds 16 warps (4 per SMSP) to keep the DMMA pipe fed across LDS/barrier stalls
 using Cfg128 = GemmCfg<128, 64, 32, 32, 16, 3>;
 using Cfg64 = GemmCfg<64, 64, 32, 32, 8, 4>;
-// TRSM: 64-row tiles double the CTA count of the latency-critical panel solve; TN = 128 keeps it in place
+// latency configuration for launches that cannot fill the GPU with larger tiles (the panel -> next block column
+// updates on the critical path of a separator): 32x32 tiles, 4 warps of 16x16; a tile with K = 128 is ~1 us of DMMA
+// issue on its SM, so the launch is spread over up to 16x more SMs than with 128x64 tiles
+using Cfg32 = GemmCfg<32, 32, 16, 16, 16, 3>;
+// TRSM: TN = 128 keeps it in place (a CTA owns whole rows); the row-tile height is picked per step so that the
+// latency-critical panel solve covers the GPU: 64, 32 or 16 rows
 using CfgTrsm = GemmCfg<64, 128, 32, 32, 16, 3>;
+using CfgTrsm32 = GemmCfg<32, 128, 16, 32, 16, 3>;
+using CfgTrsm16 = GemmCfg<16, 128, 16, 32, 16, 3>;
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) k_gemm_tiles(const GemmTask* __restrict__ tasks, int ntasks,
@@ -327,36 +334,33 @@ constexpr int XDLD = 20;
 constexpr int POTRF_THREADS = 256;
 constexpr int POTRF_S = NB_MAX * PLD;                 // doubles
 constexpr int POTRF_XD = (NB_MAX / 16) * 16 * XDLD;   // diagonal inverse blocks
-constexpr int POTRF_T = NB_MAX * XDLD;                // 16 x 128 temporary, column-major with ld XDLD
+constexpr int POTRF_T = NB_MAX * XDLD;                // per-warp 16 x 8 scratch tiles, column-major with ld XDLD
 constexpr size_t POTRF_SMEM = (size_t)(POTRF_S + NB_MAX + POTRF_XD + POTRF_T) * 8;
 constexpr int POTRF_LD = PLD;
 
-// 1/sqrt(a) for the pivot chain: FP32 seed (MUFU.RSQ) + two Newton steps in FP64 (6 dependent FP64 ops; error
-// ~1 ulp).  The library rsqrt() carries special-case branches that sit on the factorization's critical path.
-__device__ __forceinline__ double fast_rsqrt(double a) {
-  // scale by an even power of two into [1,4) so the FP32 seed never leaves float range
-  const int hi = __double2hiint(a);
-  const int ex = (((hi >> 20) & 0x7ff) - 1023) & ~1;
-  const double as = __hiloint2double(hi - (ex << 20), __double2loint(a));
-  double y = (double)rsqrtf((float)as);
-  const double h = 0.5 * as;
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double e = fma(-h * y, y, 0.5);   // 0.5 - 0.5*a*y^2
-    y = fma(y, e, y);
-  }
-  y = __hiloint2double(__double2hiint(y) - ((ex >> 1) << 20), __double2loint(y));
-  // zero, negative, NaN, Inf, denormal: library path (rare; the test is off the dependent chain)
-  if (!(a > 1e-300 && a < 1e300)) y = rsqrt(a);
-  return y;
+// 1/sqrt(a) for the pivot chain: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) + one third-order step — the
+// scheme of the CUDA math library's rsqrt() without its range fix-ups, 4 dependent FP64 operations after the seed
+// (~50 cycles against ~190 for an FP32 seed with two Newton steps, tools/fp64_latency.cu).  Non-positive pivots give
+// NaN/Inf, which the caller reports through `info`.
+__device__ __forceinline__ double rsqrt_pivot(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double t = a * y;
+  const double e = fma(-t, y, 1.0);      // 1 - a y^2
+  const double p = fma(0.375, e, 0.5);   // 1/2 + 3/8 e
+  const double ye = y * e;
+  return fma(ye, p, y);
 }
 
-// micro panel: columns [p0, p0+8), thread t owns row p0+t
+// micro panel: columns [p0, p0+8), thread t owns row p0+t.  Every row-thread factors the 8x8 diagonal block
+// redundantly in registers (no intra-panel synchronisation) with 2x2 block pivots — both reciprocal square roots of a
+// column pair start together: l00 = sqrt(a), l11 = sqrt(det/a), det = a e - b^2 — and carries its own row along as a
+// ninth row of the elimination.
 __device__ __forceinline__ void potrf_micro8(double* S, double* rd, int p0, int nbp, int tid, int* info, int colbase,
                                              int nb) {
   const int i = p0 + tid;
   const bool active = i < nbp;
-  double d[8][8], x[8], rr[8];
+  double d[8][8], x[8];
   if (active) {
 #pragma unroll
     for (int k = 0; k < 8; ++k)
@@ -368,53 +372,56 @@ __device__ __forceinline__ void potrf_micro8(double* S, double* rd, int p0, int 
   __syncthreads();   // every thread has its copy of the diagonal block before its rows are overwritten
   if (!active) return;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const double piv = d[c][c];
-    if (tid == 0 && !(piv > 0.0) && p0 + c < nb) atomicCAS(info, 0, colbase + p0 + c + 1);
-    const double r = fast_rsqrt(piv);
-    rr[c] = r;
-    d[c][c] = piv * r;
+  for (int c = 0; c < 8; c += 2) {
+    const double a = d[c][c], b = d[c + 1][c], e = d[c + 1][c + 1];
+    const double det = fma(a, e, -b * b);
+    if (tid == 0) {
+      if (!(a > 0.0)) { if (p0 + c < nb) atomicCAS(info, 0, colbase + p0 + c + 1); }
+      else if (!(det > 0.0) && p0 + c + 1 < nb) atomicCAS(info, 0, colbase + p0 + c + 2);
+    }
+    const double r0 = rsqrt_pivot(a);       // 1 / l00
+    const double rdet = rsqrt_pivot(det);   // 1 / sqrt(det)
+    const double l10 = b * r0;
+    const double r1 = rdet * (a * r0);      // 1 / l11 = sqrt(a) / sqrt(det)
 #pragma unroll
-    for (int k = c + 1; k < 8; ++k) d[k][c] *= r;
+    for (int k = c + 2; k < 8; ++k) {
+      const double x0 = d[k][c] * r0;
+      d[k][c] = x0;
+      d[k][c + 1] = fma(-x0, l10, d[k][c + 1]) * r1;
+    }
+    {
+      const double x0 = x[c] * r0;
+      x[c] = x0;
+      x[c + 1] = fma(-x0, l10, x[c + 1]) * r1;
+    }
 #pragma unroll
-    for (int k = c + 1; k < 8; ++k)
+    for (int k = c + 2; k < 8; ++k)
 #pragma unroll
-      for (int m = c + 1; m <= k; ++m) d[k][m] = fma(-d[k][c], d[m][c], d[k][m]);
+      for (int m = c + 2; m <= k; ++m) d[k][m] = fma(-d[k][c + 1], d[m][c + 1], fma(-d[k][c], d[m][c], d[k][m]));
+#pragma unroll
+    for (int m = c + 2; m < 8; ++m) x[m] = fma(-x[c + 1], d[m][c + 1], fma(-x[c], d[m][c], x[m]));
+    if (tid == 0) { rd[p0 + c] = r0; rd[p0 + c + 1] = r1; }
   }
-  // own row against the factored diagonal block: x * L_dd' = a
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    double v = x[c];
-#pragma unroll
-    for (int m = 0; m < c; ++m) v = fma(-x[m], d[c][m], v);
-    x[c] = v * rr[c];
-  }
-  // rows inside the diagonal block reproduce L_dd itself (x[c] == d[t][c] for c <= t)
+  // a row inside the diagonal block reproduces L_dd itself up to its diagonal entry; what lies right of it is scratch
 #pragma unroll
   for (int c = 0; c < 8; ++c)
-    if (i > p0 + c) S[(p0 + c) * PLD + i] = x[c];
-    else if (i == p0 + c) S[(p0 + c) * PLD + i] = d[c][c];
-  if (tid == 0) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) rd[p0 + c] = rr[c];
-  }
+    if (p0 + c <= i) S[(p0 + c) * PLD + i] = x[c];
 }
 
-// rank-8 update of columns [p0+8, p0+16) by the micro panel [p0, p0+8); thread t owns row p0+8+t
-__device__ __forceinline__ void potrf_mid8(double* S, int p0, int nbp, int tid) {
-  const int i = p0 + 8 + tid;
-  if (i >= nbp) return;
-  double x[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) x[c] = S[(p0 + c) * PLD + i];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (i >= p0 + 8 + k) {
-      double v = S[(p0 + 8 + k) * PLD + i];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) v = fma(-x[c], S[(p0 + c) * PLD + p0 + 8 + k], v);
-      S[(p0 + 8 + k) * PLD + i] = v;
-    }
+// rank-8 update of columns [p0+8, p0+16) by the micro panel [p0, p0+8) on DMMA: 8x8 tiles of rows, K = 8
+__device__ __forceinline__ void potrf_mid8(double* S, int p0, int nbp, int warp, int lane) {
+  const int fr = lane >> 2, fk = lane & 3;
+  const int q0 = p0 + 8;
+  const int nt = (nbp - q0) >> 3;
+  const double b0 = S[(p0 + fk) * PLD + q0 + fr], b1 = S[(p0 + 4 + fk) * PLD + q0 + fr];
+  for (int t = warp; t < nt; t += POTRF_THREADS / 32) {
+    const int r0 = q0 + t * 8;
+    double c0 = S[(q0 + fk * 2) * PLD + r0 + fr], c1 = S[(q0 + fk * 2 + 1) * PLD + r0 + fr];
+    const double a0 = -S[(p0 + fk) * PLD + r0 + fr], a1 = -S[(p0 + 4 + fk) * PLD + r0 + fr];
+    dmma884(c0, c1, a0, b0);
+    dmma884(c0, c1, a1, b1);
+    S[(q0 + fk * 2) * PLD + r0 + fr] = c0;
+    S[(q0 + fk * 2 + 1) * PLD + r0 + fr] = c1;
   }
 }
 
@@ -460,16 +467,33 @@ __device__ __forceinline__ void potrf_trailing16(double* S, int p0, int nbp, int
   }
 }
 
-// Cholesky of the padded nbp x nbp block held in S (lower part); fills rd = 1/diag(L)
-__device__ __forceinline__ void potrf_in_smem(double* S, double* rd, int nb, int nbp, int tid, int* info, int colbase) {
+// finished columns [p0, p0+16) of the block -> global panel (rows >= column, below nb); fire-and-forget stores that
+// overlap the trailing update instead of a write-back pass at the end
+__device__ __forceinline__ void store_panel16(const double* S, double* __restrict__ P, int64_t r, int nb, int p0, int tid) {
+  const int i = p0 + (tid & 127);
+  if (i >= nb) return;
+  const int cb = p0 + (tid >> 7) * 8;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = cb + u;
+    if (c <= i) P[(int64_t)c * r + i] = S[c * PLD + i];
+  }
+}
+
+// Cholesky of the padded nbp x nbp block held in S (lower part), written to the global panel P (ld r) as the
+// columns finish; fills rd = 1/diag(L).  Right-looking over 16-column macro panels, each made of two 8-column micro
+// panels joined by a DMMA rank-8 update, followed by a DMMA rank-16 trailing update.
+__device__ __forceinline__ void potrf_in_smem(double* S, double* rd, int nb, int nbp, int tid, int* info, int colbase,
+                                              double* __restrict__ P, int64_t r) {
   const int warp = tid >> 5, lane = tid & 31;
   for (int p0 = 0; p0 < nbp; p0 += 16) {
     potrf_micro8(S, rd, p0, nbp, tid, info, colbase, nb);
     __syncthreads();
-    potrf_mid8(S, p0, nbp, tid);
+    potrf_mid8(S, p0, nbp, warp, lane);
     __syncthreads();
     potrf_micro8(S, rd, p0 + 8, nbp, tid, info, colbase, nb);
     __syncthreads();
+    if (P) store_panel16(S, P, r, nb, p0, tid);
     if (p0 + 16 < nbp) {
       potrf_trailing16(S, p0, nbp, warp, lane);
       __syncthreads();
@@ -477,11 +501,17 @@ __device__ __forceinline__ void potrf_in_smem(double* S, double* rd, int nb, int
   }
 }
 
-// X = inv(L): leaves X(I,J), J < I, in the upper block (J,I) of S and the diagonal blocks D_I in XD
-__device__ __forceinline__ void invert_in_smem(double* S, const double* rd, double* XD, double* Tt, int nbp, int tid) {
+// X = inv(L) -> global Xg (column-major, ld NB_MAX, lower part; the rest of the slot stays zero).
+//   D_I = inv(L_II) for the 16x16 diagonal blocks (16 threads per block, one column each), kept in XD;
+//   then every 8-column group g of X is an independent block forward substitution down its block rows,
+//     X(I,g) = -D_I * sum_{K=J..I-1} L(I,K) X(K,g),     J = block of g,
+//   run by one warp on DMMA with only warp-level synchronisation: the group's finished blocks are parked in the
+//   unused upper block (J,I) of S (read back as B operands by the same warp) and stored to global straight from the
+//   accumulator fragments.  Groups g and 15-g share a warp (long chains with short ones).
+__device__ __forceinline__ void invert_in_smem(double* S, const double* rd, double* XD, double* Tt, double* __restrict__ Xg,
+                                               int nb, int nbp, int tid) {
   const int warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fk = lane & 3;
   const int nI = nbp >> 4;
-  // D_I = inv(L_II): 16 threads per block, thread c solves L_II x = e_c
   if (tid < nI * 16) {
     const int I = tid >> 4, c = tid & 15, o = I * 16;
     double x[16];
@@ -496,62 +526,66 @@ __device__ __forceinline__ void invert_in_smem(double* S, const double* rd, doub
     for (int i = 0; i < 16; ++i) XD[I * 16 * XDLD + c * XDLD + i] = x[i];   // zero above the diagonal (i < c)
   }
   __syncthreads();
-  for (int I = 1; I < nI; ++I) {
-    const int ntile = 4 * I;   // 2 row fragments x 2I column fragments of the 16 x 16I block row
-    // phase A: T = sum_{K<I} L(I,K) X(K, 0..16I)
-    for (int tt = warp; tt < ntile; tt += POTRF_THREADS / 32) {
-      const int fi = tt & 1, fj = tt >> 1, J = fj >> 1, cj = (fj & 1) * 8;
-      double c0 = 0.0, c1 = 0.0;
+  for (int idx = tid; idx < nI * 256; idx += POTRF_THREADS) {
+    const int I = idx >> 8, c = (idx >> 4) & 15, i = idx & 15;
+    const int row = I * 16 + i, col = I * 16 + c;
+    if (row < nb && col < nb) Xg[col * NB_MAX + row] = XD[I * 16 * XDLD + c * XDLD + i];
+  }
+  double* T = Tt + warp * 8 * XDLD;   // warp-private 16 x 8 scratch
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int g = half == 0 ? warp : 15 - warp;
+    const int J = g >> 1, cj = (g & 1) * 8;
+#pragma unroll 1
+    for (int I = J + 1; I < nI; ++I) {
+      // T = sum_K L(I,K) X(K,g): two row fragments, each split over two accumulator pairs (even / odd k4 steps)
+      double t[2][2][2];
+#pragma unroll
+      for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) t[fi][h][0] = t[fi][h][1] = 0.0;
+#pragma unroll 1
       for (int K = J; K < I; ++K) {
 #pragma unroll
         for (int k4 = 0; k4 < 16; k4 += 4) {
-          const double a = S[(K * 16 + k4 + fk) * PLD + I * 16 + fi * 8 + fr];
           const double b = (K == J) ? XD[J * 16 * XDLD + (cj + fr) * XDLD + k4 + fk]
                                     : S[(K * 16 + cj + fr) * PLD + J * 16 + k4 + fk];
-          dmma884(c0, c1, a, b);
+#pragma unroll
+          for (int fi = 0; fi < 2; ++fi) {
+            const double a = S[(K * 16 + k4 + fk) * PLD + I * 16 + fi * 8 + fr];
+            dmma884(t[fi][(k4 >> 2) & 1][0], t[fi][(k4 >> 2) & 1][1], a, b);
+          }
         }
       }
-      Tt[(fj * 8 + fk * 2) * XDLD + fi * 8 + fr] = c0;
-      Tt[(fj * 8 + fk * 2 + 1) * XDLD + fi * 8 + fr] = c1;
-    }
-    __syncthreads();
-    // phase B: X(I, 0..16I) = -D_I T
-    for (int tt = warp; tt < ntile; tt += POTRF_THREADS / 32) {
-      const int fi = tt & 1, fj = tt >> 1, J = fj >> 1, cj = (fj & 1) * 8;
-      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int fi = 0; fi < 2; ++fi) {
+        T[(fk * 2) * XDLD + fi * 8 + fr] = t[fi][0][0] + t[fi][1][0];
+        T[(fk * 2 + 1) * XDLD + fi * 8 + fr] = t[fi][0][1] + t[fi][1][1];
+      }
+      __syncwarp();
+      // X(I,g) = -D_I T
+      double xv[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
       for (int k4 = 0; k4 < 16; k4 += 4) {
-        const double a = -XD[I * 16 * XDLD + (k4 + fk) * XDLD + fi * 8 + fr];
-        const double b = Tt[(fj * 8 + fr) * XDLD + k4 + fk];
-        dmma884(c0, c1, a, b);
+        const double b = T[fr * XDLD + k4 + fk];
+#pragma unroll
+        for (int fi = 0; fi < 2; ++fi) {
+          const double a = -XD[I * 16 * XDLD + (k4 + fk) * XDLD + fi * 8 + fr];
+          dmma884(xv[fi][0], xv[fi][1], a, b);
+        }
       }
-      S[(I * 16 + cj + fk * 2) * PLD + J * 16 + fi * 8 + fr] = c0;
-      S[(I * 16 + cj + fk * 2 + 1) * PLD + J * 16 + fi * 8 + fr] = c1;
+#pragma unroll
+      for (int fi = 0; fi < 2; ++fi)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int lr = fi * 8 + fr, lc = cj + fk * 2 + e;
+          S[(I * 16 + lc) * PLD + J * 16 + lr] = xv[fi][e];
+          const int row = I * 16 + lr, col = J * 16 + lc;
+          if (row < nb && col < nb) Xg[col * NB_MAX + row] = xv[fi][e];
+        }
+      __syncwarp();
     }
-    __syncthreads();
   }
-}
-
-// row = tid & 127, two column phases: no integer division, coalesced along rows
-__device__ __forceinline__ void store_inverse(const double* S, const double* XD, double* __restrict__ X, int nb,
-                                              int tid) {
-  const int i = tid & 127, I = i >> 4;
-  if (i >= nb) return;
-#pragma unroll 8
-  for (int c = tid >> 7; c < nb; c += 2) {
-    const int J = c >> 4;
-    double v = 0.0;
-    if (I == J) v = XD[I * 16 * XDLD + (c & 15) * XDLD + (i & 15)];
-    else if (I > J) v = S[(I * 16 + (c & 15)) * PLD + J * 16 + (i & 15)];
-    X[c * NB_MAX + i] = v;
-  }
-}
-
-__device__ __forceinline__ void store_factor_block(const double* S, double* __restrict__ P, int64_t r, int nb, int tid) {
-  const int i = tid & 127;
-  if (i >= nb) return;
-#pragma unroll 8
-  for (int c = tid >> 7; c <= i; c += 2) P[(int64_t)c * r + i] = S[c * PLD + i];
 }
 
 __device__ __forceinline__ void load_padded_block(double* S, const double* __restrict__ P, int64_t r, int nb, int nbp,
@@ -595,10 +629,8 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_potrf_block(const BlockTask* 
   double* __restrict__ P = lv + I.valptr + (int64_t)B.j0 * r + B.j0;   // (j0, j0) of the panel
   load_padded_block(S, P, r, nb, nbp, tid);
   __syncthreads();
-  potrf_in_smem(S, rd, nb, nbp, tid, info, I.col0 + B.j0);
-  store_factor_block(S, P, r, nb, tid);
-  invert_in_smem(S, rd, XD, Tt, nbp, tid);
-  store_inverse(S, XD, linv + (int64_t)B.slot * NB_MAX * NB_MAX, nb, tid);
+  potrf_in_smem(S, rd, nb, nbp, tid, info, I.col0 + B.j0, P, r);
+  invert_in_smem(S, rd, XD, Tt, linv + (int64_t)B.slot * NB_MAX * NB_MAX, nb, nbp, tid);
 }
 
 // inverse diagonal blocks for a factor that was produced elsewhere (parsy_cuda_set_factor, drop-in solves)
@@ -620,8 +652,7 @@ __global__ void __launch_bounds__(POTRF_THREADS) k_invert_block(const BlockTask*
   __syncthreads();
   if (tid < nbp) rd[tid] = 1.0 / S[tid * PLD + tid];
   __syncthreads();
-  invert_in_smem(S, rd, XD, Tt, nbp, tid);
-  store_inverse(S, XD, linv + (int64_t)B.slot * NB_MAX * NB_MAX, nb, tid);
+  invert_in_smem(S, rd, XD, Tt, linv + (int64_t)B.slot * NB_MAX * NB_MAX, nb, nbp, tid);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -312,16 +312,40 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   P.rel_prefix[P.pairs.size()] = rel;
   P.rel_entries = rel;
 
+  // tile size per launch: a (step, group) launch whose 128x64 / 64x64 tiles cannot cover the SMs is latency-bound by
+  // the duration of one tile, so it is re-cut into 64x64 or 32x32 tiles (the panel -> next block column updates on the
+  // critical path of a separator are the typical case)
+  {
+    constexpr int SMS = 148;
+    std::vector<int32_t> tdef(2 * (size_t)nsteps, 0), t64(2 * (size_t)nsteps, 0);
+    for (const Gen& g : gen) {
+      if (g.cls != 1 && g.cls != 2) continue;
+      tdef[2 * g.step + g.grp] += g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : lower_tiles(g.t.M, g.t.N, 64, 64);
+      t64[2 * g.step + g.grp] += lower_tiles(g.t.M, g.t.N, 64, 64);
+    }
+    for (Gen& g : gen) {
+      if (g.cls != 1 && g.cls != 2) continue;
+      const int k = 2 * g.step + g.grp;
+      if (tdef[k] >= SMS) continue;
+      const double fl = upd_flops(g.t);
+      const int ncls = t64[k] >= SMS ? 2 : 4;
+      if (ncls == g.cls) continue;
+      if (g.cls == 1) { P.class_flops[3] -= fl; P.class_flops[4] += fl; }
+      g.cls = (int8_t)ncls;
+    }
+  }
   // split-K: a launch with fewer tiles than the GPU has CTA slots cannot fill the machine, and its tiles with a long
   // K (wide descendants) set the duration; the epilogue is an atomic add, so K can be cut into independent pieces
   {
     constexpr int FILL = 2 * 148;
     std::vector<int32_t> tl(2 * (size_t)nsteps, 0);
-    auto ntiles = [&](const Gen& g) { return g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : lower_tiles(g.t.M, g.t.N, 64, 64); };
-    for (const Gen& g : gen) if (g.cls == 1 || g.cls == 2) tl[2 * g.step + g.grp] += ntiles(g);
+    auto ntiles = [&](const Gen& g) {
+      return g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : g.cls == 2 ? lower_tiles(g.t.M, g.t.N, 64, 64) : lower_tiles(g.t.M, g.t.N, 32, 32);
+    };
+    for (const Gen& g : gen) if (g.cls == 1 || g.cls == 2 || g.cls == 4) tl[2 * g.step + g.grp] += ntiles(g);
     const size_t n0 = gen.size();
     for (size_t i = 0; i < n0; ++i) {
-      if ((gen[i].cls != 1 && gen[i].cls != 2) || gen[i].t.K < 128) continue;
+      if ((gen[i].cls != 1 && gen[i].cls != 2 && gen[i].cls != 4) || gen[i].t.K < 128) continue;
       const int total = tl[2 * gen[i].step + gen[i].grp];
       if (total >= FILL) continue;
       const int K = gen[i].t.K;
@@ -358,6 +382,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       for (int g = 0; g < 2; ++g) S.upd[g].u128 = take(1, g);
       for (int g = 0; g < 2; ++g) S.upd[g].u64 = take(2, g);
       for (int g = 0; g < 2; ++g) S.upd[g].small_pairs = take(3, g);
+      for (int g = 0; g < 2; ++g) S.upd[g].u32 = take(4, g);
     }
   }
   std::vector<Gen>().swap(gen);
@@ -392,7 +417,16 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   for (int st = 0; st < nsteps; ++st) {
     Step& S = P.steps[st];
     int32_t acc = 0;
-    for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, 64); }
+    // TRSM row-tile height: the tallest of 64 / 32 / 16 that still gives every SM a tile
+    S.trsm_tm = 64;
+    for (int tm : {64, 32, 16}) {
+      acc = 0;
+      for (int i = S.trsm.begin; i < S.trsm.end; ++i) acc += cdiv(P.gemm_tasks[i].M, tm);
+      S.trsm_tm = tm;
+      if (acc >= 148) break;
+    }
+    acc = 0;
+    for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, S.trsm_tm); }
     S.trsm_tiles = acc;
     for (int g = 0; g < 2; ++g) {
       UpdGroup& U = S.upd[g];
@@ -400,7 +434,9 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       for (int i = U.u128.begin; i < U.u128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128, 64); }
       U.tiles128 = acc; acc = 0;
       for (int i = U.u64.begin; i < U.u64.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 64, 64); }
-      U.tiles64 = acc;
+      U.tiles64 = acc; acc = 0;
+      for (int i = U.u32.begin; i < U.u32.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 32, 32); }
+      U.tiles32 = acc;
     }
     acc = 0;
     for (int i = S.blocks.begin; i < S.blocks.end; ++i) {

@@ -109,6 +109,8 @@ struct UpdGroup {
   int32_t tiles128 = 0;
   Range u64;           // gemm_tasks, 64x64 DMMA tiles
   int32_t tiles64 = 0;
+  Range u32;           // gemm_tasks, 32x32 DMMA tiles (launches that cannot fill the GPU with larger tiles)
+  int32_t tiles32 = 0;
   Range small_pairs;   // gemm_tasks of the warp-FMA pairs (addressed through small_tasks)
   Range small;         // small_tasks (row chunks); the first small_narrow have K <= 4
   int32_t small_narrow = 0;
@@ -121,6 +123,7 @@ struct Step {
   Range blocks;      // into block_tasks
   Range trsm;        // into gemm_tasks (T128, GF_OVERWRITE|GF_B_LINV)
   int32_t trsm_tiles = 0;
+  int32_t trsm_tm = 64;      // row-tile height of this step's TRSM launch (64, 32 or 16)
   UpdGroup upd[2];   // [0] targets factored in the next step ("A"), [1] everything else ("R")
   int32_t solve_tiles = 0;   // row tiles of the block tasks (forward / backward sweeps)
   int32_t max_nb = 0;        // widest block column in this step

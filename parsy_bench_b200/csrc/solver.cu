@@ -83,7 +83,10 @@ static int ensure_kernel_attrs(int device) {
   if (device >= 0 && device < 64 && done[device]) return 0;
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg128::SMEM));
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg64::SMEM));
+  CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg32::SMEM));
   CU(cudaFuncSetAttribute(k_gemm_tiles<CfgTrsm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgTrsm::SMEM));
+  CU(cudaFuncSetAttribute(k_gemm_tiles<CfgTrsm32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgTrsm32::SMEM));
+  CU(cudaFuncSetAttribute(k_gemm_tiles<CfgTrsm16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgTrsm16::SMEM));
   CU(cudaFuncSetAttribute(k_potrf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
   CU(cudaFuncSetAttribute(k_invert_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
   CU(cudaFuncSetAttribute(k_fwd_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SWEEP_SMEM));
@@ -98,9 +101,10 @@ static inline int cdivi(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // optional per-launch CUDA-event instrumentation (parsy_cuda_factor_profiled)
 struct LaunchProfiler {
   std::vector<cudaEvent_t> ev;
-  std::vector<int> cls;
+  std::vector<int> cls, step;
+  int cur_step = 0;
   cudaStream_t st = nullptr;
-  void begin(int c) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev.push_back(a); ev.push_back(b); cls.push_back(c); cudaEventRecord(a, st); }
+  void begin(int c) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev.push_back(a); ev.push_back(b); cls.push_back(c); step.push_back(cur_step); cudaEventRecord(a, st); }
   void end() { cudaEventRecord(ev.back(), st); }
 };
 #define PROF_BEGIN(c) do { if (prof) prof->begin(c); } while (0)
@@ -133,8 +137,13 @@ static int64_t launch_factor_phase(parsy_cuda_solver* s, const Step& S, cudaStre
   }
   if (S.trsm_tiles) {
     PROF_BEGIN(2);
-    k_gemm_tiles<CfgTrsm><<<S.trsm_tiles, CfgTrsm::THREADS, CfgTrsm::SMEM, st>>>(s->d_gemm + S.trsm.begin, S.trsm.size(),
-                                                                                 s->d_lv, s->d_linv, s->d_rel);
+    const GemmTask* tk = s->d_gemm + S.trsm.begin;
+    if (S.trsm_tm == 64)
+      k_gemm_tiles<CfgTrsm><<<S.trsm_tiles, CfgTrsm::THREADS, CfgTrsm::SMEM, st>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+    else if (S.trsm_tm == 32)
+      k_gemm_tiles<CfgTrsm32><<<S.trsm_tiles, CfgTrsm32::THREADS, CfgTrsm32::SMEM, st>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+    else
+      k_gemm_tiles<CfgTrsm16><<<S.trsm_tiles, CfgTrsm16::THREADS, CfgTrsm16::SMEM, st>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
     PROF_END();
     ++launches;
   }
@@ -153,6 +162,13 @@ static int64_t launch_update_group(parsy_cuda_solver* s, const UpdGroup& U, cuda
   if (U.tiles64) {
     PROF_BEGIN(4);
     k_gemm_tiles<Cfg64><<<U.tiles64, Cfg64::THREADS, Cfg64::SMEM, st>>>(s->d_gemm + U.u64.begin, U.u64.size(), s->d_lv,
+                                                                        s->d_linv, s->d_rel);
+    PROF_END();
+    ++launches;
+  }
+  if (U.tiles32) {
+    PROF_BEGIN(4);
+    k_gemm_tiles<Cfg32><<<U.tiles32, Cfg32::THREADS, Cfg32::SMEM, st>>>(s->d_gemm + U.u32.begin, U.u32.size(), s->d_lv,
                                                                         s->d_linv, s->d_rel);
     PROF_END();
     ++launches;
@@ -190,6 +206,7 @@ static int64_t enqueue_factor_steps(parsy_cuda_solver* s, int step_begin, int st
   if (step_end <= step_begin) return 0;
   if (prof || !s->lookahead) {
     for (int i = step_begin; i < step_end; ++i) {
+      if (prof) prof->cur_step = i;
       launches += launch_factor_phase(s, P.steps[i], mainst, prof);
       launches += launch_update_group(s, P.steps[i].upd[0], mainst, prof);
       launches += launch_update_group(s, P.steps[i].upd[1], mainst, prof);
@@ -499,9 +516,7 @@ extern "C" int parsy_cuda_factor(parsy_cuda_solver* s) {
 // One factorization without CUDA graphs, every launch bracketed by CUDA events on the solver's stream.
 // class_ms[6] / class_launches[6] / class_flops[6]: 0 factor_small, 1 potrf_block, 2 trsm tiles (DMMA), 3 update
 // tiles 128 (DMMA), 4 update tiles 64 (DMMA), 5 update_small.
-extern "C" int parsy_cuda_factor_profiled(parsy_cuda_solver* s, double* class_ms, int64_t* class_launches,
-                                          double* class_flops) {
-  if (!s || !class_ms || !class_launches || !class_flops) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+static int factor_profiled_impl(parsy_cuda_solver* s, LaunchProfiler& prof, std::vector<float>& ms) {
   if (s->phase != 2 && (!s->has_A || !s->has_values)) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
   CU(cudaSetDevice(s->device));
   const Plan& P = s->plan;
@@ -512,21 +527,40 @@ extern "C" int parsy_cuda_factor_profiled(parsy_cuda_solver* s, double* class_ms
     const int grid = (int)std::min<int64_t>((P.nnzA + 255) / 256, 148 * 16);
     k_assemble<<<grid, 256, 0, st>>>(P.nnzA, s->d_apos, s->d_vals, s->d_lv);
   }
-  LaunchProfiler prof;
   prof.st = st;
   enqueue_factor_steps(s, 0, (int)P.steps.size(), &prof);
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
-  for (int c = 0; c < 6; ++c) { class_ms[c] = 0; class_launches[c] = 0; class_flops[c] = P.class_flops[c]; }
+  ms.assign(prof.cls.size(), 0.f);
   for (size_t i = 0; i < prof.cls.size(); ++i) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
-    class_ms[prof.cls[i]] += ms;
-    class_launches[prof.cls[i]]++;
+    cudaEventElapsedTime(&ms[i], prof.ev[2 * i], prof.ev[2 * i + 1]);
     cudaEventDestroy(prof.ev[2 * i]); cudaEventDestroy(prof.ev[2 * i + 1]);
   }
   s->factored = true;
   return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_factor_profiled(parsy_cuda_solver* s, double* class_ms, int64_t* class_launches,
+                                          double* class_flops) {
+  if (!s || !class_ms || !class_launches || !class_flops) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  LaunchProfiler prof;
+  std::vector<float> ms;
+  const int rc = factor_profiled_impl(s, prof, ms);
+  if (rc) return rc;
+  for (int c = 0; c < 6; ++c) { class_ms[c] = 0; class_launches[c] = 0; class_flops[c] = s->plan.class_flops[c]; }
+  for (size_t i = 0; i < prof.cls.size(); ++i) { class_ms[prof.cls[i]] += ms[i]; class_launches[prof.cls[i]]++; }
+  return PARSY_CUDA_OK;
+}
+
+// Same pass, one record per launch: dependency step, kernel class (as above) and device time in ms.
+// Returns the number of launches (records beyond max_records are dropped), or -1 on error.
+extern "C" int parsy_cuda_factor_trace(parsy_cuda_solver* s, int max_records, int* step, int* cls, float* ms_out) {
+  if (!s || (max_records > 0 && (!step || !cls || !ms_out))) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return -1; }
+  LaunchProfiler prof;
+  std::vector<float> ms;
+  if (factor_profiled_impl(s, prof, ms)) return -1;
+  for (size_t i = 0; i < prof.cls.size() && (int)i < max_records; ++i) { step[i] = prof.step[i]; cls[i] = prof.cls[i]; ms_out[i] = ms[i]; }
+  return (int)prof.cls.size();
 }
 
 extern "C" int parsy_cuda_sync(parsy_cuda_solver* s) {

@@ -345,6 +345,21 @@ class Solver:
         return {k: {"ms": float(ms[i]), "launches": int(nl[i]), "flops": float(fl[i])}
                 for i, k in enumerate(self.KERNEL_CLASSES)}
 
+    def factor_trace(self, max_records=1 << 16):
+        """One event-instrumented factorization: per-launch arrays (step, kernel class index, ms)."""
+        step = np.zeros(max_records, np.int32)
+        cls = np.zeros(max_records, np.int32)
+        ms = np.zeros(max_records, np.float32)
+        f = self._L.parsy_cuda_factor_trace
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+        cnt = f(self._h, int(max_records), step.ctypes.data_as(c_void_p), cls.ctypes.data_as(c_void_p),
+                ms.ctypes.data_as(c_void_p))
+        if cnt < 0:
+            raise ParsyCudaError(ERR_CUDA, "parsy_cuda_factor_trace")
+        cnt = min(cnt, max_records)
+        return step[:cnt], cls[:cnt], ms[:cnt]
+
     def stats(self):
         st = Stats()
         f = self._L.parsy_cuda_get_stats
