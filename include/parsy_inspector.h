@@ -69,6 +69,24 @@ int parsy_etree_level_set(int nsuper, const int* sParent, int* levelPtr /*nsuper
  * Pass Ci = Cx = NULL to only count. */
 int64_t parsy_bcsc2csc(const parsy_symbolic* sym, const double* Lx, int* Cp, int* Ci, double* Cx);
 
+/* Matrix-Market input.
+ *
+ * parsy_read_matrix replaces `readMatrix` (common/Util.h:77-179; call site examples/choleskyTest01.cpp:118-127):
+ * a coordinate file holding the LOWER half of a symmetric matrix, entries ordered by column, becomes 0-based CSC.
+ * Row order inside a column is kept as written (the inspector wants the diagonal first, as the reference does).
+ * Returns 0, or: 1 header has fewer than 5 tokens, 2 banner, 3 not "matrix", 4 not "coordinate", 5 arithmetic is not
+ * "real", 6 size line missing, 7 n or nnz <= 0, 8 index outside the matrix, 9 entries not ordered by column / empty
+ * column, 10 file shorter than announced, 11 I/O or NULL argument (text in parsy_inspector_last_error; the reference
+ * prints the same messages for codes 1-6 and returns false). The arrays are malloc'ed; release with parsy_matrix_free. */
+int parsy_read_matrix(const char* path, int* n, int64_t* nnz, int** col, int** row, double** val);
+void parsy_matrix_free(int* col, int* row, double* val);
+
+/* Replaces `printLower` of examples/MakingLowerHalf.cpp:10-100: reads a FULL symmetric coordinate file and writes the
+ * entries with row >= col to out_path under a "symmetric" banner, size line "n n (nnz-n)/2+n", 1-based indices, the
+ * diagonal shifted by +tol (or -tol when negative; the reference hard-codes tol = 0.1), values in the default ostream
+ * format (6 significant digits) so that the output is byte-identical to the reference's stdout. Same return codes. */
+int parsy_make_lower_half(const char* in_path, const char* out_path, double tol);
+
 #ifdef __cplusplus
 }
 #endif

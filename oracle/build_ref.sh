@@ -27,3 +27,7 @@ g++ -O2 -DNDEBUG -std=c++11 -fpermissive -w -fopenmp -DMKL -DMETIS \
     -I"$HERE/shim" -I"$TMP/cholesky" -I"$TMP/common" -I"$TMP/triangularSolve" \
     "$HERE/ref_driver.cpp" "$METIS" "$BLAS" -Wl,--disable-new-dtags,-rpath,"$(dirname "$BLAS")" -o "$OUT/parsy_ref"
 echo "built $OUT/parsy_ref"
+# examples/MakingLowerHalf.cpp is a self-contained program (std headers only): compiled where it lies, used by
+# tests/test_mmio.py to pin parsy_make_lower_half byte for byte.
+g++ -O2 -w "$REF/examples/MakingLowerHalf.cpp" -o "$OUT/making_lower_half"
+echo "built $OUT/making_lower_half"

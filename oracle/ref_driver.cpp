@@ -77,7 +77,7 @@ template <typename T> static void dump(const std::string& dir, const char* name,
 int main(int argc, char** argv) {
   int kind = 0, N = 100, costParam = 8, levelParam = 1, divRate = 2, threads = 1, blasThreads = -1, iters = 1;
   int doFactor = 1, doSolve = 1, dumpL = 1, chunk = 1;
-  std::string dir;
+  std::string dir, mtx;
   for (int a = 1; a < argc; ++a) {
     std::string s = argv[a];
     auto nxt = [&]() { return std::string(argv[++a]); };
@@ -93,6 +93,7 @@ int main(int argc, char** argv) {
     else if (s == "--no-factor") doFactor = 0;
     else if (s == "--no-solve") doSolve = 0;
     else if (s == "--no-dump-values") dumpL = 0;
+    else if (s == "--mtx") mtx = nxt();
     else { fprintf(stderr, "unknown arg %s\n", s.c_str()); return 2; }
   }
   if (blasThreads < 0) blasThreads = threads;
@@ -100,6 +101,14 @@ int main(int argc, char** argv) {
   openblas_set_num_threads(1);
 
   std::vector<int> Ap, Ai; std::vector<double> Ax;
+  if (!mtx.empty()) {
+    // Matrix-Market input through the reference's own reader (common/Util.h:77 readMatrix)
+    size_t rn = 0, rnnz = 0; int *rc = NULL, *rr = NULL; double* rv = NULL;
+    if (!readMatrix(mtx, rn, rnnz, rc, rr, rv)) { fprintf(stderr, "readMatrix failed for %s\n", mtx.c_str()); return 3; }
+    Ap.assign(rc, rc + rn + 1); Ai.assign(rr, rr + rnnz); Ax.assign(rv, rv + rnnz);
+    delete[] rc; delete[] rr; delete[] rv;
+    kind = -1; N = (int)rn;
+  } else
   gen_laplacian(kind, N, Ap, Ai, Ax);
   size_t n = Ap.size() - 1, nnzA = Ai.size();
   dump(dir, "A_p.i32", Ap.data(), n + 1); dump(dir, "A_i.i32", Ai.data(), nnzA); dump(dir, "A_x.f64", Ax.data(), nnzA);

@@ -416,6 +416,7 @@ template <class T> T* dup(const std::vector<T>& v) {
 }  // namespace
 
 extern "C" const char* parsy_inspector_last_error(void) { return g_err.c_str(); }
+void parsy_inspector_set_error(const std::string& msg) { g_err = msg; }   // used by mmio.cpp
 
 extern "C" void parsy_symbolic_free(parsy_symbolic* s) {
   if (!s) return;

@@ -975,6 +975,13 @@ extern "C" int parsy_cuda_copy_range(parsy_cuda_solver* dst, parsy_cuda_solver* 
   CU(cudaSetDevice(dst->device));
   CU(cudaStreamSynchronize(src->stream));
   CU(cudaMemcpyAsync(dst->d_lv + begin, src->d_lv + begin, sizeof(double) * (size_t)(end - begin), cudaMemcpyDeviceToDevice, dst->stream));
+  // a broadcast is ordered on the owner's stream as well: the owner factors the panel in place right afterwards, so
+  // its stream must not run ahead of this read (write-after-read hazard of the emulation; NCCL orders it by itself)
+  cudaEvent_t done;
+  CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  CU(cudaEventRecord(done, dst->stream));
+  CU(cudaStreamWaitEvent(src->stream, done, 0));
+  CU(cudaEventDestroy(done));
   return PARSY_CUDA_OK;
 }
 

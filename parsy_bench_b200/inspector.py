@@ -43,6 +43,13 @@ def lib():
         L.parsy_etree_level_set.argtypes = [c_int, c_void_p, c_void_p, c_void_p]
         L.parsy_bcsc2csc.restype = c_int64
         L.parsy_bcsc2csc.argtypes = [POINTER(_Symbolic), c_void_p, c_void_p, c_void_p, c_void_p]
+        L.parsy_read_matrix.restype = c_int
+        L.parsy_read_matrix.argtypes = [ctypes.c_char_p, POINTER(c_int), POINTER(c_int64), POINTER(POINTER(c_int)),
+                                        POINTER(POINTER(c_int)), POINTER(POINTER(c_double))]
+        L.parsy_matrix_free.restype = None
+        L.parsy_matrix_free.argtypes = [POINTER(c_int), POINTER(c_int), POINTER(c_double)]
+        L.parsy_make_lower_half.restype = c_int
+        L.parsy_make_lower_half.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_double]
         _lib = L
     return _lib
 
@@ -135,3 +142,36 @@ def analyze(n, Ap, Ai, Ax, costParam=8, levelParam=1, divRate=2, perm=None) -> S
     if rc != 0:
         raise RuntimeError(f"parsy_inspect failed ({rc}): {lib().parsy_inspector_last_error().decode()}")
     return Symbolic(out)
+
+
+class MatrixMarketError(ValueError):
+    def __init__(self, code, msg):
+        super().__init__(f"Matrix-Market input rejected ({code}): {msg}")
+        self.code = code
+
+
+def read_matrix(path):
+    """``readMatrix`` (common/Util.h:77-179): lower-half, column-ordered coordinate file -> ``(n, col, row, val)``
+    0-based CSC, row order inside a column as written.  Raises MatrixMarketError where the reference returns false."""
+    L = lib()
+    n, nnz = c_int(), c_int64()
+    col, row, val = POINTER(c_int)(), POINTER(c_int)(), POINTER(c_double)()
+    rc = L.parsy_read_matrix(os.fsencode(path), byref(n), byref(nnz), byref(col), byref(row), byref(val))
+    if rc != 0:
+        raise MatrixMarketError(rc, L.parsy_inspector_last_error().decode())
+    try:
+        Ap = np.ctypeslib.as_array(col, shape=(n.value + 1,)).copy()
+        Ai = np.ctypeslib.as_array(row, shape=(nnz.value,)).copy()
+        Ax = np.ctypeslib.as_array(val, shape=(nnz.value,)).copy()
+    finally:
+        L.parsy_matrix_free(col, row, val)
+    return n.value, Ap, Ai, Ax
+
+
+def make_lower_half(in_path, out_path, tol=0.1):
+    """``printLower`` of examples/MakingLowerHalf.cpp:10-100: full symmetric coordinate file -> lower-half file with
+    the diagonal shifted by ``tol`` (the reference's constant is 0.1)."""
+    L = lib()
+    rc = L.parsy_make_lower_half(os.fsencode(in_path), os.fsencode(out_path), float(tol))
+    if rc != 0:
+        raise MatrixMarketError(rc, L.parsy_inspector_last_error().decode())

@@ -58,3 +58,16 @@ def expected_nnz(kind: str, N: int) -> int:
     if kind == "3d7":
         return n + 3 * N * N * (N - 1)
     return n + 3 * N * N * (N - 1) + 6 * N * (N - 1) ** 2 + 4 * (N - 1) ** 3
+
+
+def write_mtx(path, n, Ap, Ai, Ax, symmetric=True, comment=None):
+    """Writes a CSC matrix column by column as a Matrix-Market coordinate file (1-based ``row col value`` triplets,
+    17 significant digits) — the layout ``readMatrix`` (common/Util.h:77) expects for the lower half."""
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate real {'symmetric' if symmetric else 'general'}\n")
+        if comment:
+            f.write(f"% {comment}\n")
+        f.write(f"{n} {n} {len(Ai)}\n")
+        for j in range(n):
+            for k in range(int(Ap[j]), int(Ap[j + 1])):
+                f.write(f"{int(Ai[k]) + 1} {j + 1} {float(Ax[k]):.17g}\n")

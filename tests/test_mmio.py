@@ -1,0 +1,165 @@
+"""CPU: Matrix-Market input — parsy_read_matrix against the reference's readMatrix
+(common/Util.h:77, through oracle/_ref/parsy_ref --mtx), parsy_make_lower_half against the compiled
+examples/MakingLowerHalf.cpp and against committed fixtures, and a non-stencil SPD matrix read from a file through the
+whole inspector, bit for bit against the reference's inspector."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refdump
+from parsy_bench_b200 import inspector, matrices
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+MLH_BIN = os.path.join(refdump.ROOT, "oracle", "_ref", "making_lower_half")
+
+
+def random_spd_lower(n, extra_per_col, seed):
+    """Lower half (diagonal first, rows ascending) of a symmetric, strictly diagonally dominant matrix with a random
+    sparsity pattern plus a path (so that the graph is connected)."""
+    rng = np.random.default_rng(seed)
+    cols = [set() for _ in range(n)]
+    for j in range(n - 1):
+        cols[j].add(j + 1)
+        for i in rng.integers(j + 1, n, size=extra_per_col):
+            cols[j].add(int(i))
+    rowsum = np.zeros(n)
+    Ap, Ai, Ax = [0], [], []
+    offs = []
+    for j in range(n):
+        rows = sorted(cols[j])
+        vals = -rng.uniform(0.1, 1.0, size=len(rows))
+        offs.append((rows, vals))
+        for i, v in zip(rows, vals):
+            rowsum[i] += abs(v)
+            rowsum[j] += abs(v)
+    for j in range(n):
+        rows, vals = offs[j]
+        Ai += [j] + rows
+        Ax += [rowsum[j] + 1.0 + 0.01 * j] + list(vals)
+        Ap.append(len(Ai))
+    return n, np.array(Ap, np.int32), np.array(Ai, np.int32), np.array(Ax)
+
+
+def test_round_trip_of_a_laplacian(tmp_path):
+    n, Ap, Ai, Ax = matrices.laplacian("2d5", 12)
+    f = tmp_path / "lap.mtx"
+    matrices.write_mtx(f, n, Ap, Ai, Ax, comment="2D 5-point Laplacian 12x12, lower half")
+    n2, Bp, Bi, Bx = inspector.read_matrix(f)
+    assert n2 == n
+    assert np.array_equal(Ap, Bp) and np.array_equal(Ai, Bi) and np.array_equal(Ax, Bx)
+
+
+def test_upper_case_banner_and_comments(tmp_path):
+    f = tmp_path / "m.mtx"
+    f.write_text("%%MATRIXMARKET Matrix Coordinate REAL Symmetric\n% a comment\n%another\n2 2 3\n1 1 2.5\n2 1 -1\n2 2 3e0\n")
+    n, Ap, Ai, Ax = inspector.read_matrix(f)
+    assert n == 2 and Ap.tolist() == [0, 2, 3] and Ai.tolist() == [0, 1, 1] and Ax.tolist() == [2.5, -1.0, 3.0]
+
+
+@pytest.mark.parametrize("text,code", [
+    ("", 1),                                                                        # missing file content
+    ("%%MatrixMarket matrix coordinate real\n1 1 1\n1 1 1\n", 1),                  # four tokens
+    ("%MatrixMarket matrix coordinate real symmetric\n1 1 1\n1 1 1\n", 2),
+    ("%%MatrixMarket vector coordinate real symmetric\n1 1 1\n1 1 1\n", 3),
+    ("%%MatrixMarket matrix array real symmetric\n1 1 1\n1 1 1\n", 4),
+    ("%%MatrixMarket matrix coordinate complex hermitian\n1 1 1\n1 1 1 0\n", 5),
+    ("%%MatrixMarket matrix coordinate pattern symmetric\n1 1 1\n1 1\n", 5),
+    ("%%MatrixMarket matrix coordinate integer symmetric\n1 1 1\n1 1 1\n", 5),
+    ("%%MatrixMarket matrix coordinate real symmetric\n% only comments\n", 6),
+    ("%%MatrixMarket matrix coordinate real symmetric\n0 0 0\n", 7),
+    ("%%MatrixMarket matrix coordinate real symmetric\n2 2 3\n1 1 1\n2 1 1\n2 3 1\n", 8),   # column 3 of 2
+    ("%%MatrixMarket matrix coordinate real symmetric\n2 2 3\n1 1 1\n3 1 1\n2 2 1\n", 8),   # row 3 of 2
+    ("%%MatrixMarket matrix coordinate real symmetric\n3 3 3\n1 1 1\n3 3 1\n2 2 1\n", 9),   # column skipped / unordered
+    ("%%MatrixMarket matrix coordinate real symmetric\n3 3 2\n1 1 1\n2 2 1\n", 9),          # last column empty
+    ("%%MatrixMarket matrix coordinate real symmetric\n2 2 3\n1 1 1\n2 1 1\n", 10),         # short file
+])
+def test_rejections(tmp_path, text, code):
+    f = tmp_path / "bad.mtx"
+    f.write_text(text)
+    with pytest.raises(inspector.MatrixMarketError) as e:
+        inspector.read_matrix(f)
+    assert e.value.code == code
+
+
+def test_missing_file_is_an_invalid_header(tmp_path):
+    with pytest.raises(inspector.MatrixMarketError) as e:
+        inspector.read_matrix(tmp_path / "does_not_exist.mtx")
+    assert e.value.code == 1    # the reference's getline on a closed stream yields an empty header line
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="compiled reference (oracle/_ref) not built")
+def test_reader_and_inspector_match_the_reference_on_a_file(tmp_path):
+    """A matrix that is NOT a stencil: read by the reference's readMatrix and by ours, then through both inspectors."""
+    n, Ap, Ai, Ax = random_spd_lower(400, 2, seed=7)
+    f = tmp_path / "rand.mtx"
+    matrices.write_mtx(f, n, Ap, Ai, Ax)
+    d = tmp_path / "dump"
+    d.mkdir()
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+    subprocess.run([refdump.REF_BIN, "--mtx", str(f), "--cost", "8", "--level", "1", "--div", "2", "--threads", "1",
+                    "--dump", str(d), "--no-factor", "--no-solve"], check=True, capture_output=True, env=env)
+    ld = lambda name, dt: np.fromfile(d / name, dtype=dt)  # noqa: E731
+    n2, Bp, Bi, Bx = inspector.read_matrix(f)
+    assert n2 == n
+    assert np.array_equal(ld("A_p.i32", np.int32), Bp)
+    assert np.array_equal(ld("A_i.i32", np.int32), Bi)
+    assert np.array_equal(ld("A_x.f64", np.float64), Bx)
+    assert np.array_equal(Bx, Ax)          # 17 digits round-trip
+    S = inspector.analyze(n2, Bp, Bi, Bx, 8, 1, 2)
+    for name, dt in [("Perm", np.int32), ("ColCount", np.int32), ("super", np.int32), ("sParent", np.int32),
+                     ("col2Sup", np.int32), ("s", np.int32), ("p", np.uint64), ("i_ptr", np.uint64),
+                     ("levelPtr", np.int32), ("parPtr", np.int32), ("partition", np.int32), ("A2_p", np.int32),
+                     ("A2_i", np.int32), ("A1_p", np.int32), ("A1_i", np.int32)]:
+        ext = "u64" if dt == np.uint64 else "i32"
+        assert np.array_equal(ld(f"{name}.{ext}", dt), getattr(S, name)), name
+    assert np.array_equal(ld("A2_x.f64", np.float64), S.A2_x)
+
+
+def _full_symmetric_file(path):
+    """Full storage (both triangles) of a small symmetric matrix with a negative and a zero diagonal entry."""
+    rng = np.random.default_rng(3)
+    n = 9
+    M = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i):
+            if rng.random() < 0.4:
+                M[i, j] = M[j, i] = round(float(rng.normal()), 9)
+    M[np.diag_indices(n)] = [4, -3.25, 0, 1e-7, 123456.789, 2, 7.5, 1, 3]
+    ent = [(i + 1, j + 1, M[i, j]) for j in range(n) for i in range(n) if M[i, j] != 0 or i == j]
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n% full storage\n")
+        f.write(f"{n} {n} {len(ent)}\n")
+        for i, j, v in ent:
+            f.write(f"{i} {j} {v:.12g}\n")
+
+
+def test_make_lower_half_matches_committed_fixture(tmp_path):
+    out = tmp_path / "lower.mtx"
+    inspector.make_lower_half(os.path.join(GOLDEN, "mm_full.mtx"), out)
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "mm_lower_expected.mtx"), "rb").read()
+    # and the result is something read_matrix accepts
+    n, Ap, Ai, Ax = inspector.read_matrix(out)
+    assert n == 9 and Ap[-1] == len(Ai) and all(Ai[Ap[j]] == j for j in range(n))
+
+
+@pytest.mark.skipif(not os.path.exists(MLH_BIN), reason="compiled MakingLowerHalf (oracle/_ref) not built")
+def test_make_lower_half_matches_the_reference_program(tmp_path):
+    src = tmp_path / "full.mtx"
+    _full_symmetric_file(src)
+    ref = subprocess.run([MLH_BIN, str(src)], check=True, capture_output=True).stdout
+    out = tmp_path / "lower.mtx"
+    inspector.make_lower_half(src, out)
+    assert out.read_bytes() == ref
+    # same generator as the committed fixture
+    assert src.read_bytes() == open(os.path.join(GOLDEN, "mm_full.mtx"), "rb").read()
+
+
+def test_make_lower_half_propagates_header_errors(tmp_path):
+    src = tmp_path / "bad.mtx"
+    src.write_text("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n")
+    with pytest.raises(inspector.MatrixMarketError) as e:
+        inspector.make_lower_half(src, tmp_path / "o.mtx")
+    assert e.value.code == 4
