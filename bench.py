@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="single stream, no overlap of POTRF/TRSM with the bulk updates")
     ap.add_argument("--ignore-hlevels", action="store_true", help="schedule by dependencies only (no LBC H-level barriers)")
+    ap.add_argument("--general-sweeps", action="store_true", help="leaf region of the sweeps on the general dataflow kernel (A/B)")
     ap.add_argument("--replicas", action="store_true", help="N>1: one full factorization per GPU instead of sharding")
     ap.add_argument("--replicate-top", action="store_true", help="N>1: every rank computes the top separators")
     ap.add_argument("--top-levels", type=int, default=1, help="N>1: LBC H-levels kept shared (computed by every rank)")
@@ -318,7 +319,7 @@ def main():
     t0 = time.time()
     H = ex.Solver(n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels, S.levelPtr,
                   S.parPtr, S.partition, device=local, block_cols=args.block_cols, ignore_hlevels=args.ignore_hlevels,
-                  lookahead=not args.no_lookahead)
+                  lookahead=not args.no_lookahead, narrow_sweeps=not args.general_sweeps)
     t_create = time.time() - t0
     st = H.stats()
     F = S.flops
@@ -433,7 +434,7 @@ def main():
                 "dominant_class": dom,
                 "whole_factor_frac_of_fp64_peak": F / (fac_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
     hbm = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
-    roofline_solve = {"bound": "hbm", "kernel": "forward sweep (k_fwd_dataflow, one launch)",
+    roofline_solve = {"bound": "hbm", "kernel": "forward sweep (k_fwd_narrow for the leaf region + k_fwd_dataflow)",
                       "achieved": st["bytes_solve"] / (fwd_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                       "frac": st["bytes_solve"] / (fwd_ms * 1e-3) / 1e9 / hbm, "traffic": None,
                       "peak_source": peak_kind + " copy bandwidth", "algorithmic_bytes": st["bytes_solve"],

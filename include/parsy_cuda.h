@@ -113,7 +113,8 @@ typedef struct parsy_cuda_options {
   int rank;            /* multi-GPU: this process' rank ...                                        */
   int world;           /* ... of `world` ranks (0/1 = single GPU)                                  */
   int reserved[10];    /* [0]=1 no look-ahead stream, [1]=1 per-step sweeps, [2] phase, [3] top H-levels kept shared,
-                          [4]=1 replicate the top instead of distributing it */
+                          [4]=1 replicate the top instead of distributing it,
+                          [5]=1 run the leaf region of the sweeps on the general dataflow kernel too */
 } parsy_cuda_options;
 
 /* Builds the device-resident symbolic state from the inspector's arrays (all HOST pointers, copied):
@@ -147,6 +148,23 @@ int parsy_cuda_set_factor(parsy_cuda_solver* s, const double* lValues);
 int parsy_cuda_set_rhs(parsy_cuda_solver* s, const double* b);      /* host n doubles -> device */
 int parsy_cuda_get_rhs(parsy_cuda_solver* s, double* x);            /* device -> host           */
 int parsy_cuda_solve(parsy_cuda_solver* s, int which);              /* FWD, BWD or FWD|BWD      */
+
+/* Full system A x = b on the factored handle.  The reference itself stops at the forward
+ * sweep (fact 2 of SURVEY.md); its driver only sketches the CHOLMOD-style right-hand side b_i = 1 + i/n and solve
+ * (examples/choleskyTest01.cpp:408-432), so parity is pinned by the oracle's restated sweeps and the residual.
+ *
+ * parsy_cuda_set_permutation: perm[k] = index, in the caller's ordering, of the unknown at position k of the factored
+ *   matrix — L->Perm of the inspector (cholesky/LSparsity.h:613, choleskyTest01.cpp:190).  NULL = identity.  Returns
+ *   PARSY_CUDA_ERR_BAD_ARG unless perm is a permutation of 0..n-1.
+ * parsy_cuda_solve_system: for each of the nrhs columns of b (host, caller's ordering, column j at b + j*ld):
+ *   y = P b;  L z = y;  L' w = z;  then refine_steps times { r = y - (P A P') w;  w += (L L')^{-1} r };  x = P' w.
+ *   x (host) may alias b.  rel_residual, if not NULL, receives (refine_steps+1) values per column:
+ *   ||y - (P A P') w||_2 / ||y||_2 before each refinement step and after the last one.  The residual uses the values
+ *   last given to parsy_cuda_set_values; without them (handle built from set_factor only) refine_steps must be 0 and
+ *   rel_residual NULL, else PARSY_CUDA_ERR_STATE. */
+int parsy_cuda_set_permutation(parsy_cuda_solver* s, const int* perm);
+int parsy_cuda_solve_system(parsy_cuda_solver* s, const double* b, double* x, int nrhs, int64_t ld, int refine_steps,
+                            double* rel_residual);
 
 /* Device-side timing of the last parsy_cuda_factor call (CUDA events):
  * out[0] = all H-levels but the last, out[1] = last H-level, out[2] = assembly (zero + scatter A), seconds. */

@@ -240,3 +240,18 @@ int oracle_testTriangular(size_t n, const double* x) {
   for (size_t i = 0; i < n; ++i) if (1 - x[i] < 0.001) test++;
   return n - test > 0 ? 0 : 1;
 }
+
+/* ---- full system A x = b around the sweeps (test oracle for parsy_cuda_solve_system) -----------------------------
+ * The reference has no such routine: its driver only sketches the right-hand side b_i = 1 + i/n and a CHOLMOD solve
+ * (examples/choleskyTest01.cpp:408-432).  res = b - A x for the symmetric A whose lower half is stored by columns
+ * (c, r, values as handed to cholesky_left_par_05, parallel_PB_Cholesky_05.h:27-28). */
+void oracle_residual_sym_lower(int n, const int* c, const int* r, const double* values, const double* x,
+                               const double* b, double* res) {
+  for (int j = 0; j < n; ++j) res[j] = b[j];
+  for (int j = 0; j < n; ++j)
+    for (int p = c[j]; p < c[j + 1]; ++p) {
+      const int i = r[p];
+      res[i] -= values[p] * x[j];
+      if (i != j) res[j] -= values[p] * x[i];
+    }
+}

@@ -153,3 +153,36 @@ def test_triangular(x):
     f.restype = c_int
     f.argtypes = [c_size_t, c_void_p]
     return bool(f(a.size, p))
+
+
+def residual_sym_lower(S, x, b, values=None):
+    """b - (P A P') x with the symmetric matrix given by its lower half (S.A2_p, S.A2_i, values)."""
+    L = lib()
+    n = len(S.col2Sup)
+    k = [_p(S.A2_p, np.int32), _p(S.A2_i, np.int32), _p(S.A2_x if values is None else values, np.float64),
+         _p(x, np.float64), _p(b, np.float64)]
+    res = np.zeros(n)
+    f = L.oracle_residual_sym_lower
+    f.restype = None
+    f.argtypes = [c_int] + [c_void_p] * 6
+    f(n, k[0][1], k[1][1], k[2][1], k[3][1], k[4][1], res.ctypes.data_as(c_void_p))
+    return res
+
+
+def solve_system(S, Lx, b, refine_steps=0, values=None):
+    """x = P' (L L')^{-1} P b with `refine_steps` rounds of iterative refinement; restated sweeps only
+    (blockedLsolve Triangular_BCSC.h:14 + the reverse sweep).  Returns (x, rel) with rel[k] = ||y - (PAP')w|| / ||y||
+    before refinement step k (last entry: final) — the oracle for parsy_cuda_solve_system."""
+    perm = np.asarray(S.Perm)
+    y = np.asarray(b, np.float64)[perm]
+    w = blockedLtsolve(S, Lx, blockedLsolve(S, Lx, y))
+    rel = []
+    for it in range(refine_steps + 1):
+        r = residual_sym_lower(S, w, y, values)
+        rel.append(float(np.linalg.norm(r) / np.linalg.norm(y)))
+        if it == refine_steps:
+            break
+        w = w + blockedLtsolve(S, Lx, blockedLsolve(S, Lx, r))
+    x = np.empty_like(w)
+    x[perm] = w
+    return x, np.array(rel)

@@ -1168,6 +1168,170 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
 }
 
 // ------------------------------------------------------------------------------------------------
+// Narrow-only sweep kernels for the leaf region of the tree (the CTAs of the plan that come before the first
+// block-column task; on the 2-D problems > 95 % of all supernodes).  Same ticket / counter protocol as the kernels
+// above, but nothing of the block path: no 66 KB inverse block, ~40 registers, so 40-48 warps per SM are in flight
+// instead of 16 — these tasks are a chain of dependent L2/HBM round trips and their throughput is occupancy.
+// The diagonal block sits in shared memory (packed lower triangle, column c at c*w - c(c-1)/2) with the reciprocal
+// diagonal beside it; the first 32 rows below the block (indices and up to four columns) are fetched before the
+// wait as well.
+// ------------------------------------------------------------------------------------------------
+constexpr int NARROW_TRI = SMALL_W * (SMALL_W + 1) / 2;
+constexpr int NARROW_PF = 4;
+
+__device__ __forceinline__ void narrow_stage_diag(double* L, double* R, const double* __restrict__ P, int w, int r, int lane) {
+  for (int c0 = 0; c0 < w; c0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + u;
+      v[u] = (c < w && lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + u;
+      if (c < w && lane >= c && lane < w) L[c * w - (c * (c - 1)) / 2 + (lane - c)] = v[u];
+    }
+  }
+  __syncwarp();
+  if (lane < w) R[lane] = 1.0 / L[lane * w - (lane * (lane - 1)) / 2];
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 5) k_fwd_narrow(
+    const SolveCta* __restrict__ ctas, const SolveTask* __restrict__ tasks, const int* __restrict__ targets,
+    const int* __restrict__ need, int* __restrict__ done, int* __restrict__ ticket, const SupInfo* __restrict__ sup,
+    const int* __restrict__ lR, const double* __restrict__ lv, double* __restrict__ y, double* __restrict__ xs) {
+  __shared__ double sL[8][NARROW_TRI];
+  __shared__ double sR[8][SMALL_W];
+  __shared__ int s_cta;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cta = atomicAdd(ticket, 1);
+  __syncthreads();
+  const SolveCta C = ctas[s_cta];
+  if (warp >= C.count) return;
+  const SolveTask T = tasks[C.first + warp];
+  const SupInfo I = sup[T.sup];
+  const int w = I.w, r = I.r;
+  const double* __restrict__ P = lv + I.valptr;
+  const int* __restrict__ rows = lR + I.rowptr;
+  double* L = sL[warp];
+  double* R = sR[warp];
+  // everything that does not depend on the right-hand side, ahead of the wait
+  const int ifirst = w + lane;
+  const int row_first = (ifirst < r) ? rows[ifirst] : -1;
+  double pf[NARROW_PF];
+#pragma unroll
+  for (int u = 0; u < NARROW_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
+  narrow_stage_diag(L, R, P, w, r, lane);
+  if (lane == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
+  __syncwarp();
+  double xv = (lane < w) ? __ldcg(&y[I.col0 + lane]) : 0.0;
+  for (int c = 0; c < w; ++c) {
+    const double xc = __shfl_sync(0xffffffffu, xv, c) * R[c];
+    if (lane == c) xv = xc;
+    else if (lane > c && lane < w) xv = fma(-L[c * w - (c * (c - 1)) / 2 + (lane - c)], xc, xv);
+  }
+  if (lane < w) xs[I.col0 + lane] = xv;
+  for (int i0 = w; i0 < r; i0 += 32) {
+    const int i = i0 + lane;
+    const bool firstc = i0 == w;
+    double t = 0.0;
+    int c = 0;
+    if (firstc) {
+#pragma unroll
+      for (int u = 0; u < NARROW_PF; ++u)
+        if (u < w) t = fma(pf[u], __shfl_sync(0xffffffffu, xv, u), t);
+      c = min(w, NARROW_PF);
+    }
+    for (; c < w; c += 4) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (c + u < w && i < r) ? P[(int64_t)(c + u) * r + i] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t = fma(v[u], __shfl_sync(0xffffffffu, xv, (c + u) & 31), t);
+    }
+    const int row = firstc ? row_first : (i < r ? rows[i] : -1);
+    if (row >= 0) atomicAdd(&y[row], -t);
+  }
+  __threadfence();
+  __syncwarp();
+  for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) atomicAdd(&done[targets[q]], 1);
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 5) k_bwd_narrow(
+    const SolveCta* __restrict__ ctas, int nctas, const SolveTask* __restrict__ tasks, const int* __restrict__ targets,
+    int* __restrict__ solved, int* __restrict__ ticket, const SupInfo* __restrict__ sup, const int* __restrict__ lR,
+    const double* __restrict__ lv, double* __restrict__ x) {
+  __shared__ double sL[8][NARROW_TRI];
+  __shared__ double sR[8][SMALL_W];
+  __shared__ int s_cta;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cta = nctas - 1 - atomicAdd(ticket, 1);
+  __syncthreads();
+  const SolveCta C = ctas[s_cta];
+  if (warp >= C.count) return;
+  const SolveTask T = tasks[C.first + warp];
+  const SupInfo I = sup[T.sup];
+  const int w = I.w, r = I.r;
+  const double* __restrict__ P = lv + I.valptr;
+  const int* __restrict__ rows = lR + I.rowptr;
+  double* L = sL[warp];
+  double* R = sR[warp];
+  const int ifirst = w + lane;
+  const int row_first = (ifirst < r) ? rows[ifirst] : -1;
+  double pf[NARROW_PF];
+#pragma unroll
+  for (int u = 0; u < NARROW_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
+  narrow_stage_diag(L, R, P, w, r, lane);
+  for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) spin_until_ge_busy(&solved[targets[q]], 1);
+  __syncwarp();
+  double mine = (lane < w) ? __ldcg(&x[I.col0 + lane]) : 0.0;
+  const double xr_first = (row_first >= 0) ? __ldcg(&x[row_first]) : 0.0;
+  // t_c = sum_i L(i,c) x[rows[i]], four columns at a time: per-lane partial sums over the lane's rows, then one
+  // interleaved shuffle reduction per group
+  for (int c0 = 0; c0 < w; c0 += 4) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i0 = w; i0 < r; i0 += 32) {
+      const int ii = i0 + lane;
+      if (i0 == w) {
+        if (c0 == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fma(pf[u], xr_first, acc[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = (c0 + u < w && ii < r) ? fma(P[(int64_t)(c0 + u) * r + ii], xr_first, acc[u]) : acc[u];
+        }
+      } else {
+        const double xr = (ii < r) ? __ldcg(&x[rows[ii]]) : 0.0;
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (c0 + u < w && ii < r) ? P[(int64_t)(c0 + u) * r + ii] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(v[u], xr, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (lane == c0 + u) mine -= acc[u];
+  }
+  // L11' x = t, column-oriented: x_c is final once every x_k, k > c, has been eliminated from it
+  for (int c = w - 1; c >= 0; --c) {
+    const double xc = __shfl_sync(0xffffffffu, mine, c) * R[c];
+    if (lane == c) mine = xc;
+    else if (lane < c) mine = fma(-L[lane * w - (lane * (lane - 1)) / 2 + (c - lane)], xc, mine);
+  }
+  if (lane < w) x[I.col0 + lane] = mine;
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(&solved[T.node], 1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // column (CSC) forward solve, one level per launch: warp per column            (Triangular_CSC.h:50-71)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_csc_level(const int* __restrict__ cols, int count, const int* __restrict__ Lp,
@@ -1180,6 +1344,56 @@ __global__ void k_csc_level(const int* __restrict__ cols, int count, const int* 
   for (int p = p0 + 1 + lane; p < p1; p += 32) atomicAdd(&x[Li[p]], -Lx[p] * xj);
   __syncwarp();
   if (lane == 0) x[j] = xj;
+}
+
+// ------------------------------------------------------------------------------------------------
+// full system A x = b around the two sweeps: permutation, residual of the symmetric matrix
+// given by its lower half, update.  All HBM-bound, algorithmic bytes: 16 B per vector entry moved, 12 B per stored
+// entry of A for the residual.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_perm_gather(int n, const int* __restrict__ perm, const double* __restrict__ b, double* __restrict__ y) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) y[k] = b[perm[k]];
+}
+__global__ void k_perm_scatter(int n, const int* __restrict__ perm, const double* __restrict__ y, double* __restrict__ x) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) x[perm[k]] = y[k];
+}
+// res -= A x for the symmetric A whose lower half (by columns) is (c, r, vals); res holds b on entry.
+// One thread per column: the column's own contribution is summed in a register, the mirrored ones go out as atomics.
+__global__ void k_residual_sym_lower(int n, const int* __restrict__ c, const int* __restrict__ r,
+                                     const double* __restrict__ vals, const double* __restrict__ x,
+                                     double* __restrict__ res) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const double xj = x[j];
+    double own = 0.0;
+    for (int p = c[j]; p < c[j + 1]; ++p) {
+      const int i = r[p];
+      const double a = vals[p];
+      if (i == j) own = fma(a, xj, own);
+      else {
+        own = fma(a, x[i], own);            // A(j,i) x(i), the mirrored entry
+        atomicAdd(&res[i], -a * xj);        // A(i,j) x(j)
+      }
+    }
+    atomicAdd(&res[j], -own);
+  }
+}
+// out[0] += sum v^2
+__global__ void __launch_bounds__(256) k_sumsq(int n, const double* __restrict__ v, double* __restrict__ out) {
+  __shared__ double sw[8];
+  double acc = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) acc = fma(v[k], v[k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sw[w];
+    atomicAdd(out, t);
+  }
+}
+__global__ void k_add_inplace(int n, const double* __restrict__ d, double* __restrict__ x) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) x[k] += d[k];
 }
 
 }  // namespace parsy

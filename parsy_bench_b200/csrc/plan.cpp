@@ -483,8 +483,12 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       }
       t.tgt_end = (int32_t)P.solve_targets.size();
     };
+    bool seen_block = false;
+    P.n_narrow_prefix_ctas = 0;
     for (int st = 0; st < nsteps; ++st) {
       const Step& S = P.steps[st];
+      if (S.blocks.begin < S.blocks.end) seen_block = true;
+      if (!seen_block) P.n_narrow_prefix_ctas += cdiv(S.small_sup.end - S.small_sup.begin, 8);
       // narrow supernodes, eight per CTA
       for (int i0 = S.small_sup.begin; i0 < S.small_sup.end; i0 += 8) {
         SolveCta c; c.kind = 0; c.first = (int32_t)P.solve_tasks.size(); c.count = std::min(8, S.small_sup.end - i0); c.pad = 0;

@@ -171,6 +171,8 @@ struct Plan {
   int32_t n_nodes = 0;
   std::vector<SolveTask> solve_tasks;      // forward order (dependency steps ascending)
   std::vector<SolveCta> solve_ctas;        // forward order; the backward sweep walks it in reverse
+  int32_t n_narrow_prefix_ctas = 0;        // leading CTAs (all of kind 0) that come before the first block-column task:
+                                           // the leaf region of the tree, run by the light narrow-only sweep kernels
   std::vector<int32_t> solve_targets;      // node ids
   std::vector<int32_t> node_need;          // forward: number of tasks that add into the node's right-hand side
   std::vector<int32_t> node_tiles;         // backward: number of slices of the node (narrow supernodes: 1)

@@ -1,5 +1,6 @@
 // libparsy_cuda: resident solver object + C ABI (include/parsy_cuda.h).
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -48,6 +49,13 @@ struct parsy_cuda_solver {
   double* d_rhs = nullptr;
   double* d_xs = nullptr;
   int* d_info = nullptr;
+  // full-system driver (parsy_cuda_solve_system): A's pattern, fill-reducing permutation, work vectors
+  int* d_Ac = nullptr;
+  int* d_Ar = nullptr;
+  int* d_perm = nullptr;
+  double* d_sys = nullptr;    // [b permuted | x accumulated | staging in the caller's ordering], 3n doubles
+  double* d_norms = nullptr;  // pairs (||r||^2, ||b||^2)
+  int norms_cap = 0;
   // dataflow sweeps
   SolveTask* d_stasks = nullptr;
   SolveCta* d_sctas = nullptr;
@@ -56,6 +64,7 @@ struct parsy_cuda_solver {
   int* d_ntiles = nullptr;
   int* d_sync = nullptr;      // [ticket | done or cnt (n_nodes) | solved (n_nodes)]
   bool dataflow = true;
+  bool narrow_sweeps = true;  // leaf region of the sweeps on the light narrow-only kernels (reserved[5] = 1 disables)
   int64_t device_bytes = 0;
   cudaGraphExec_t g_levels = nullptr, g_last = nullptr, g_fwd = nullptr, g_bwd = nullptr;
   int64_t launches_factor = 0, launches_fwd = 0, launches_bwd = 0;
@@ -237,12 +246,24 @@ static int64_t enqueue_fwd(parsy_cuda_solver* s) {
   cudaStream_t st = s->stream;
   if (s->dataflow) {
     if (P.solve_ctas.empty()) return 0;
-    cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 1), st);
-    k_fwd_dataflow<<<(int)P.solve_ctas.size(), SWEEP_THREADS, FWD_SWEEP_SMEM, st>>>(s->d_sctas, s->d_stasks, s->d_stargets, s->d_need,
-                                                                       s->d_sync + 1, s->d_sync, s->d_sup, s->d_lR, s->d_lv,
-                                                                       s->d_linv, s->d_rhs, s->d_xs);
+    cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 2), st);
+    // leaf region (narrow supernodes only) on the light kernel, everything from the first block column on after it;
+    // the counters carry the dependencies across the two launches
+    const int total = (int)P.solve_ctas.size(), npre = s->narrow_sweeps ? P.n_narrow_prefix_ctas : 0;
+    int* ticket2 = s->d_sync + 1 + 2 * (size_t)P.n_nodes;
+    if (npre > 0) {
+      k_fwd_narrow<<<npre, SWEEP_THREADS, 0, st>>>(s->d_sctas, s->d_stasks, s->d_stargets, s->d_need, s->d_sync + 1, s->d_sync,
+                                                  s->d_sup, s->d_lR, s->d_lv, s->d_rhs, s->d_xs);
+      ++launches;
+    }
+    if (total > npre) {
+      k_fwd_dataflow<<<total - npre, SWEEP_THREADS, FWD_SWEEP_SMEM, st>>>(s->d_sctas + npre, s->d_stasks, s->d_stargets, s->d_need,
+                                                                         s->d_sync + 1, ticket2, s->d_sup, s->d_lR, s->d_lv,
+                                                                         s->d_linv, s->d_rhs, s->d_xs);
+      ++launches;
+    }
     cudaMemcpyAsync(s->d_rhs, s->d_xs, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToDevice, st);
-    return 1;
+    return launches;
   }
   for (size_t i = 0; i < P.steps.size(); ++i) {
     const Step& S = P.steps[i];
@@ -267,12 +288,22 @@ static int64_t enqueue_bwd(parsy_cuda_solver* s) {
   cudaStream_t st = s->stream;
   if (s->dataflow) {
     if (P.solve_ctas.empty()) return 0;
-    cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 1), st);
-    k_bwd_dataflow<<<(int)P.solve_ctas.size(), SWEEP_THREADS, FWD_SWEEP_SMEM, st>>>(s->d_sctas, (int)P.solve_ctas.size(), s->d_stasks,
-                                                                       s->d_stargets, s->d_ntiles, s->d_sync + 1,
-                                                                       s->d_sync + 1 + P.n_nodes, s->d_sync, s->d_sup, s->d_lR,
-                                                                       s->d_lv, s->d_linv, s->d_rhs);
-    return 1;
+    cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 2), st);
+    const int total = (int)P.solve_ctas.size(), npre = s->narrow_sweeps ? P.n_narrow_prefix_ctas : 0;
+    int* ticket2 = s->d_sync + 1 + 2 * (size_t)P.n_nodes;
+    if (total > npre) {
+      k_bwd_dataflow<<<total - npre, SWEEP_THREADS, FWD_SWEEP_SMEM, st>>>(s->d_sctas + npre, total - npre, s->d_stasks,
+                                                                         s->d_stargets, s->d_ntiles, s->d_sync + 1,
+                                                                         s->d_sync + 1 + P.n_nodes, s->d_sync, s->d_sup, s->d_lR,
+                                                                         s->d_lv, s->d_linv, s->d_rhs);
+      ++launches;
+    }
+    if (npre > 0) {
+      k_bwd_narrow<<<npre, SWEEP_THREADS, 0, st>>>(s->d_sctas, npre, s->d_stasks, s->d_stargets, s->d_sync + 1 + P.n_nodes,
+                                                  ticket2, s->d_sup, s->d_lR, s->d_lv, s->d_rhs);
+      ++launches;
+    }
+    return launches;
   }
   for (int i = (int)P.steps.size() - 1; i >= 0; --i) {
     const Step& S = P.steps[i];
@@ -323,7 +354,7 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
   if (!s->owns_lv) s->d_lv = nullptr;   // adopted from another handle (parsy_cuda_adopt_factor)
   void* ptrs[] = {s->d_sup, s->d_lR, s->d_small_list, s->d_blocks, s->d_gemm, s->d_small_tasks, s->d_rel, s->d_apos,
                   s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info, s->d_stasks, s->d_sctas, s->d_stargets,
-                  s->d_need, s->d_ntiles, s->d_sync};
+                  s->d_need, s->d_ntiles, s->d_sync, s->d_Ac, s->d_Ar, s->d_perm, s->d_sys, s->d_norms};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {s->ev_fork, s->ev_join, s->ev_F[0], s->ev_F[1], s->ev_R[0], s->ev_R[1]}) if (e) cudaEventDestroy(e);
@@ -401,8 +432,9 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
   TRY(dev_upload(s, &s->d_stargets, P.solve_targets.data(), P.solve_targets.size()));
   TRY(dev_upload(s, &s->d_need, P.node_need.data(), P.node_need.size()));
   TRY(dev_upload(s, &s->d_ntiles, P.node_tiles.data(), P.node_tiles.size()));
-  TRY(dev_alloc(s, &s->d_sync, (size_t)2 * P.n_nodes + 1));
+  TRY(dev_alloc(s, &s->d_sync, (size_t)2 * P.n_nodes + 2));
   s->dataflow = o.reserved[1] == 0;   // reserved[1] = 1: one launch per dependency step instead
+  s->narrow_sweeps = o.reserved[5] == 0;
   TRYCU(cudaMemset(s->d_info, 0, sizeof(int)));
   TRYCU(cudaMemset(s->d_linv, 0, std::max<size_t>((size_t)P.n_slots * NB_MAX * NB_MAX, 1) * 8));
   // the blocking uploads above ran on the legacy stream; the solver's stream is non-blocking, so order them explicitly
@@ -433,7 +465,8 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
     const int64_t nnz = c[n];
     P.nnzA = nnz;
     int *d_c = nullptr, *d_r = nullptr, *d_c2s = nullptr;
-    TRYCU(cudaMalloc(&d_c, (size_t)(n + 1) * 4)); TRYCU(cudaMalloc(&d_r, std::max<size_t>(nnz, 1) * 4));
+    TRY(dev_alloc(s, &s->d_Ac, (size_t)(n + 1))); TRY(dev_alloc(s, &s->d_Ar, (size_t)nnz));   // kept: residual of A x = b
+    d_c = s->d_Ac; d_r = s->d_Ar;
     TRYCU(cudaMalloc(&d_c2s, std::max<size_t>(n, 1) * 4));
     TRYCU(cudaMemcpy(d_c, c, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
     TRYCU(cudaMemcpy(d_r, r, (size_t)nnz * 4, cudaMemcpyHostToDevice));
@@ -446,7 +479,7 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
       k_build_apos<<<grid, 256, 0, s->stream>>>(nnz, n, d_c, d_r, d_c2s, s->d_sup, s->d_lR, s->d_apos);
     }
     TRYCU(cudaStreamSynchronize(s->stream));
-    cudaFree(d_c); cudaFree(d_r); cudaFree(d_c2s);
+    cudaFree(d_c2s);
     s->has_A = true;
   }
   // CUDA graphs: all H-levels but the last / the last H-level / forward sweep / backward sweep
@@ -624,6 +657,89 @@ extern "C" int parsy_cuda_solve(parsy_cuda_solver* s, int which) {
     else s->launches_bwd = enqueue_bwd(s);
   }
   CU(cudaGetLastError());
+  return PARSY_CUDA_OK;
+}
+
+// ---- full system A x = b -----------------------------------------------------------
+// The reference stops at the forward sweep; its driver only sketches the CHOLMOD-style right-hand side and solve
+// (examples/choleskyTest01.cpp:408-432).  Here: x = P' (L L')^{-1} P b with optional iterative refinement on the
+// residual of tril(P A P') as handed to parsy_cuda_create / parsy_cuda_set_values.
+extern "C" int parsy_cuda_set_permutation(parsy_cuda_solver* s, const int* perm) {
+  if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  CU(cudaSetDevice(s->device));
+  const int n = s->plan.n;
+  std::vector<int> p(n);
+  if (perm) {
+    std::vector<char> seen(n, 0);
+    for (int k = 0; k < n; ++k) {
+      if (perm[k] < 0 || perm[k] >= n || seen[perm[k]]) return fail(PARSY_CUDA_ERR_BAD_ARG, "perm is not a permutation of 0..n-1");
+      seen[perm[k]] = 1;
+      p[k] = perm[k];
+    }
+  } else {
+    for (int k = 0; k < n; ++k) p[k] = k;
+  }
+  if (!s->d_perm) { int rc = dev_alloc(s, &s->d_perm, (size_t)n); if (rc) return rc; }
+  CU(cudaStreamSynchronize(s->stream));
+  CU(cudaMemcpy(s->d_perm, p.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_solve_system(parsy_cuda_solver* s, const double* b, double* x, int nrhs, int64_t ld,
+                                       int refine_steps, double* rel_residual) {
+  if (!s || !b || !x) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  const int n = s->plan.n;
+  if (nrhs < 0 || refine_steps < 0 || (nrhs > 1 && ld < n)) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad nrhs / ld / refine_steps");
+  if (!s->factored) return fail(PARSY_CUDA_ERR_STATE, "solve before factor / set_factor");
+  const bool need_res = refine_steps > 0 || rel_residual != nullptr;
+  if (need_res && (!s->has_A || !s->has_values)) return fail(PARSY_CUDA_ERR_STATE, "the residual needs A: create the handle with c, r and call set_values");
+  CU(cudaSetDevice(s->device));
+  if (!s->d_perm) { int rc = parsy_cuda_set_permutation(s, nullptr); if (rc) return rc; }
+  if (!s->d_sys) { int rc = dev_alloc(s, &s->d_sys, (size_t)3 * n); if (rc) return rc; }
+  const int per = refine_steps + 1;
+  if (need_res && s->norms_cap < 2 * per * nrhs) {
+    if (s->d_norms) { CU(cudaFree(s->d_norms)); s->d_norms = nullptr; }
+    int rc = dev_alloc(s, &s->d_norms, (size_t)2 * per * nrhs);
+    if (rc) return rc;
+    s->norms_cap = 2 * per * nrhs;
+  }
+  cudaStream_t st = s->stream;
+  double *d_b = s->d_sys, *d_x = s->d_sys + n, *d_io = s->d_sys + 2 * (size_t)n;
+  const size_t vb = sizeof(double) * (size_t)n;
+  const int grid = std::max(1, std::min(cdivi(n, 256), 148 * 8));
+  if (need_res) CU(cudaMemsetAsync(s->d_norms, 0, sizeof(double) * 2 * per * nrhs, st));
+  auto sweeps = [&]() -> int {
+    int rc = parsy_cuda_solve(s, PARSY_CUDA_SOLVE_FWD | PARSY_CUDA_SOLVE_BWD);
+    return rc;
+  };
+  for (int j = 0; j < nrhs; ++j) {
+    CU(cudaMemcpyAsync(d_io, b + (size_t)j * ld, vb, cudaMemcpyHostToDevice, st));
+    k_perm_gather<<<grid, 256, 0, st>>>(n, s->d_perm, d_io, d_b);
+    CU(cudaMemcpyAsync(s->d_rhs, d_b, vb, cudaMemcpyDeviceToDevice, st));
+    int rc = sweeps();
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(d_x, s->d_rhs, vb, cudaMemcpyDeviceToDevice, st));
+    for (int it = 0; need_res && it <= refine_steps; ++it) {
+      double* nr = s->d_norms + 2 * ((size_t)j * per + it);
+      CU(cudaMemcpyAsync(s->d_rhs, d_b, vb, cudaMemcpyDeviceToDevice, st));
+      k_residual_sym_lower<<<grid, 256, 0, st>>>(n, s->d_Ac, s->d_Ar, s->d_vals, d_x, s->d_rhs);
+      k_sumsq<<<grid, 256, 0, st>>>(n, s->d_rhs, nr);
+      k_sumsq<<<grid, 256, 0, st>>>(n, d_b, nr + 1);
+      if (it == refine_steps) break;
+      rc = sweeps();                    // d = (L L')^{-1} r
+      if (rc) return rc;
+      k_add_inplace<<<grid, 256, 0, st>>>(n, s->d_rhs, d_x);
+    }
+    k_perm_scatter<<<grid, 256, 0, st>>>(n, s->d_perm, d_x, d_io);
+    CU(cudaMemcpyAsync(x + (size_t)j * ld, d_io, vb, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  if (rel_residual) {
+    std::vector<double> h((size_t)2 * per * nrhs);
+    CU(cudaMemcpy(h.data(), s->d_norms, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    for (int q = 0; q < per * nrhs; ++q) rel_residual[q] = h[2 * q + 1] > 0 ? std::sqrt(h[2 * q] / h[2 * q + 1]) : std::sqrt(h[2 * q]);
+  }
   return PARSY_CUDA_OK;
 }
 

@@ -248,7 +248,7 @@ class Solver:
 
     def __init__(self, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
                  device=0, block_cols=0, use_graph=True, ignore_hlevels=False, lookahead=True, dataflow_sweeps=True,
-                 rank=0, world=1, phase=0, top_levels=1, top_distributed=True):
+                 rank=0, world=1, phase=0, top_levels=1, top_distributed=True, narrow_sweeps=True):
         L = lib()
         self._L = L
         self._h = c_void_p()
@@ -258,6 +258,7 @@ class Solver:
         opt.rank, opt.world = int(rank), int(world)
         opt.reserved[0], opt.reserved[1] = int(not lookahead), int(not dataflow_sweeps)
         opt.reserved[2], opt.reserved[3], opt.reserved[4] = int(phase), int(top_levels), int(not top_distributed)
+        opt.reserved[5] = int(not narrow_sweeps)
         f = L.parsy_cuda_create
         f.restype = c_int
         f.argtypes = [POINTER(c_void_p), c_int] + [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + \
@@ -326,6 +327,37 @@ class Solver:
 
     def solve(self, which=SOLVE_FWD | SOLVE_BWD):
         self._call("parsy_cuda_solve", int(which))
+
+    def set_permutation(self, perm):
+        """perm[k] = caller's index of the unknown at position k of the factored matrix (the inspector's ``Perm``);
+        None = identity."""
+        pp, ptr = _i32(perm, "perm", allow_none=True)
+        if pp is not None and pp.size != self.n:
+            raise ValueError("perm must have n entries")
+        self._call("parsy_cuda_set_permutation", ptr)
+
+    def solve_system(self, b, refine_steps=0, residuals=False):
+        """A x = b in the caller's ordering: permute, forward + backward sweep, ``refine_steps`` rounds of iterative
+        refinement, permute back.  ``b``: (n,) or (nrhs, n) C-contiguous rows (one right-hand side per row).
+        Returns x (same shape), or (x, rel) with rel[j, k] = relative residual of column j before refinement step k
+        (last entry: final) when ``residuals`` is true."""
+        B = np.ascontiguousarray(b, np.float64)
+        one = B.ndim == 1
+        B2 = B.reshape(1, -1) if one else B
+        if B2.ndim != 2 or B2.shape[1] != self.n:
+            raise ValueError("b must be (n,) or (nrhs, n)")
+        nrhs = B2.shape[0]
+        X = np.empty_like(B2)
+        rel = np.zeros((nrhs, refine_steps + 1)) if residuals else None
+        f = self._L.parsy_cuda_solve_system
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_void_p, c_void_p, c_int, ctypes.c_int64, c_int, c_void_p]
+        rc = f(self._h, B2.ctypes.data_as(c_void_p), X.ctypes.data_as(c_void_p), nrhs, self.n, int(refine_steps),
+               None if rel is None else rel.ctypes.data_as(c_void_p))
+        if rc != OK:
+            raise ParsyCudaError(rc, "parsy_cuda_solve_system")
+        X = X[0] if one else X
+        return (X, rel[0] if one else rel) if residuals else X
 
     def factor_times(self):
         t = np.zeros(3, np.float64)

@@ -232,6 +232,31 @@ def test_per_step_sweeps_and_single_stream_factorization():
     H.close()
 
 
+@pytest.mark.parametrize("case", [("2d5", 120, 8, 1, 2), ("3d27", 16, 8, 1, 2), ("2d5", 64, 64, 0, 4)])
+def test_narrow_sweep_kernels_agree_with_the_general_dataflow_kernel(case):
+    """The leaf region of both sweeps runs on the light narrow-only kernels by default (two launches per sweep);
+    options.reserved[5] = 1 keeps everything on the general kernel (one launch).  Both against the oracle."""
+    S = analyze(*case)
+    n = S.n
+    Lref = orc.cholesky_left_par_05(S)
+    b = 1.0 + np.arange(n) / n
+    yr = orc.blockedLsolve(S, Lref, b)
+    xr = orc.blockedLtsolve(S, Lref, yr)
+    for narrow in (True, False):
+        H = ex.Solver(n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                      S.levelPtr, S.parPtr, S.partition, narrow_sweeps=narrow)
+        H.set_factor(Lref)
+        for _ in range(2):                               # twice: the counters are re-armed by every sweep
+            H.set_rhs(b)
+            H.solve(ex.SOLVE_FWD)
+            assert rel_err(H.get_rhs(), yr) < 1e-9
+            H.solve(ex.SOLVE_BWD)
+            assert rel_err(H.get_rhs(), xr) < 1e-8
+        st = H.stats()
+        assert st["launches_fwd"] == st["launches_bwd"] <= (2 if narrow else 1)
+        H.close()
+
+
 @pytest.mark.parametrize("case", [("2d5", 1000, 8, 1, 2), ("3d27", 64, 8, 1, 2)])
 def test_full_size_properties(case):
     """BASELINE.json configs 2 and 4 at full size: identities that need no CPU factorization."""
@@ -309,3 +334,110 @@ def test_sharded_factorization_emulated_on_one_gpu(world, top, dist_top):
         assert rel_err(h.get_factor(), ref) < TOL
     for h in h2 + h1:
         h.close()
+
+
+# ---- full system A x = b and Matrix-Market input (row 3) ---------------------------------
+def make_solver(S):
+    H = ex.Solver(S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                  S.levelPtr, S.parPtr, S.partition)
+    H.set_values(S.A2_x)
+    H.factor()
+    assert H.sync()
+    return H
+
+
+def original_matrix(n, Ap, Ai, Ax):
+    import scipy.sparse as sp
+    Lo = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
+    return Lo + sp.tril(Lo, -1).T
+
+
+@pytest.mark.parametrize("case,refine", [(("2d5", 60, 8, 1, 2), 0), (("3d27", 12, 8, 1, 2), 2), (("3d7", 16, 16, 1, 2), 1)])
+def test_solve_system_vs_oracle(case, refine):
+    """x = P'(LL')^-1 P b in the caller's ordering, right-hand side of the reference driver (choleskyTest01.cpp:428-432);
+    solution against the oracle's restated sweeps, residual within 10x of the oracle's (north star)."""
+    kind, N = case[0], case[1]
+    n, Ap, Ai, Ax = matrices.laplacian(kind, N)
+    S = inspector.analyze(n, Ap, Ai, Ax, *case[2:])
+    H = make_solver(S)
+    H.set_permutation(S.Perm)
+    b = 1.0 + np.arange(n) / n
+    x, rel = H.solve_system(b, refine_steps=refine, residuals=True)
+    xo, relo = orc.solve_system(S, orc.cholesky_left_par_05(S), b, refine_steps=refine)
+    assert rel.shape == (refine + 1,)
+    assert np.max(np.abs(x - xo)) <= 1e-9 * np.max(np.abs(xo))
+    A = original_matrix(n, Ap, Ai, Ax)
+    true_res = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
+    oracle_res = float(np.linalg.norm(A @ xo - b) / np.linalg.norm(b))
+    assert true_res <= 10 * max(oracle_res, 1e-16)
+    # the device-side residual is the residual
+    assert abs(rel[-1] - true_res) <= 0.5 * true_res + 1e-17
+    assert rel[-1] <= 10 * max(relo[-1], 1e-16)
+    H.close()
+
+
+def test_solve_system_many_right_hand_sides_and_identity_permutation():
+    S = analyze("2d5", 40, 8, 1, 2)
+    H = make_solver(S)
+    rng = np.random.default_rng(5)
+    B = rng.normal(size=(5, S.n))
+    # without set_permutation the system is the permuted one, P A P'
+    A2 = full_matrix(S)
+    X = H.solve_system(B)
+    assert X.shape == B.shape
+    for j in range(5):
+        assert np.linalg.norm(A2 @ X[j] - B[j]) <= 1e-12 * np.linalg.norm(B[j]) * 40
+    # same columns one at a time, and in the original ordering
+    H.set_permutation(S.Perm)
+    X2, rel = H.solve_system(B, refine_steps=1, residuals=True)
+    assert rel.shape == (5, 2) and np.all(rel[:, 1] <= rel[:, 0] * 1.0000001 + 1e-16)
+    for j in range(5):
+        xo, _ = orc.solve_system(S, orc.cholesky_left_par_05(S), B[j], refine_steps=1)
+        assert np.max(np.abs(X2[j] - xo)) <= 1e-9 * np.max(np.abs(xo))
+    # one column alone gives the same answer (up to the summation order of the atomics)
+    assert np.allclose(H.solve_system(B[0].copy()), X2[0], rtol=1e-10, atol=1e-12)
+    H.close()
+
+
+def test_solve_system_argument_errors():
+    S = analyze("2d5", 12, 8, 1, 2)
+    H = ex.Solver(S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                  S.levelPtr, S.parPtr, S.partition)
+    with pytest.raises(ex.ParsyCudaError) as e:
+        H.solve_system(np.ones(S.n))                      # before factor
+    assert e.value.code == ex.ERR_STATE
+    bad = S.Perm.copy()
+    bad[0] = bad[1]
+    with pytest.raises(ex.ParsyCudaError) as e:
+        H.set_permutation(bad)
+    assert e.value.code == ex.ERR_BAD_ARG
+    # a handle that only received a factor has no A: sweeps work, residuals do not
+    H.set_factor(orc.cholesky_left_par_05(S))
+    x = H.solve_system(np.ones(S.n))
+    assert np.linalg.norm(full_matrix(S) @ x - 1.0) < 1e-10 * np.sqrt(S.n)
+    with pytest.raises(ex.ParsyCudaError) as e:
+        H.solve_system(np.ones(S.n), refine_steps=1)
+    assert e.value.code == ex.ERR_STATE
+    H.close()
+
+
+def test_matrix_market_file_through_inspector_and_executor(tmp_path):
+    """A non-stencil SPD matrix written as a Matrix-Market lower half, read back with the restated readMatrix
+    (common/Util.h:77), analysed, factored on the GPU and compared with the oracle; then A x = b."""
+    from test_mmio import random_spd_lower
+    n, Ap, Ai, Ax = random_spd_lower(700, 3, seed=11)
+    f = tmp_path / "rand.mtx"
+    matrices.write_mtx(f, n, Ap, Ai, Ax)
+    n2, Bp, Bi, Bx = inspector.read_matrix(f)
+    assert n2 == n and np.array_equal(Bx, Ax)
+    S = inspector.analyze(n2, Bp, Bi, Bx, 16, 1, 2)
+    ok, lv = dropin_factor(S)
+    assert ok
+    assert rel_err(lv, orc.cholesky_left_par_05(S)) < TOL
+    H = make_solver(S)
+    H.set_permutation(S.Perm)
+    b = 1.0 + np.arange(n) / n
+    x = H.solve_system(b)
+    A = original_matrix(n, Ap, Ai, Ax)
+    assert np.linalg.norm(A @ x - b) <= 1e-12 * np.linalg.norm(b)
+    H.close()

@@ -94,3 +94,24 @@ def test_oracle_vs_live_reference(case):
     b = orc.rhs_init_blocked(S, R.valL)
     assert np.array_equal(b, R.b_L1)
     assert np.max(np.abs(orc.blockedLsolve(S, R.valL, b) - R.x_blocked)) < 1e-12
+
+
+def test_oracle_solve_system_solves_the_original_system():
+    """oracle.solve_system (the checker of parsy_cuda_solve_system): permutation + restated sweeps + refinement."""
+    import scipy.sparse as sp
+    from parsy_bench_b200 import inspector, matrices
+    n, Ap, Ai, Ax = matrices.laplacian("3d7", 9)
+    S = inspector.analyze(n, Ap, Ai, Ax, 8, 1, 2)
+    Lo = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
+    A = Lo + sp.tril(Lo, -1).T
+    b = 1.0 + np.arange(n) / n                      # examples/choleskyTest01.cpp:428-432
+    lv = orc.cholesky_left_par_05(S)
+    x, rel = orc.solve_system(S, lv, b, refine_steps=2)
+    true = np.linalg.norm(A @ x - b) / np.linalg.norm(b)
+    assert true < 1e-14 and len(rel) == 3
+    assert abs(rel[-1] - true) <= 0.5 * true + 1e-17
+    # the residual helper is b - (PAP')x
+    A2 = sp.csc_matrix((S.A2_x, S.A2_i, S.A2_p), shape=(n, n))
+    A2 = A2 + sp.tril(A2, -1).T
+    v = np.cos(np.arange(n))
+    assert np.allclose(orc.residual_sym_lower(S, v, b), b - A2 @ v, rtol=0, atol=1e-12)
