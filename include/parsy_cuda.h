@@ -180,6 +180,14 @@ int parsy_cuda_factor_profiled(parsy_cuda_solver* s, double* class_ms6, int64_t*
 int parsy_cuda_factor_trace(parsy_cuda_solver* s, int max_records, int* step, int* cls, float* ms);
 
 /* Introspection used by bench.py / tests (counts are exact, computed by the planner). */
+/* Diagnostics: timeline of the general sweep kernel (which = PARSY_CUDA_SOLVE_FWD or PARSY_CUDA_SOLVE_BWD).  Runs one
+ * un-captured sweep on the current right-hand side and reports, for each of its CTAs in plan order: kind (0 = up to
+ * eight narrow supernodes, 1 = one slice of a block column, 2 = one narrow supernode with a long panel), rows of the
+ * slice (kind 0: supernodes in the CTA), and the microseconds — relative to the first CTA's start — at which it started,
+ * saw its inputs complete (kinds 0 and 2: = start), and finished.  Returns the number of CTAs, or -1. */
+int parsy_cuda_sweep_trace(parsy_cuda_solver* s, int which, int max_records, int* kind, int* nrows, double* t_start_us,
+                           double* t_ready_us, double* t_end_us);
+
 typedef struct parsy_cuda_stats {
   int64_t n, nsuper, xsize, ssize, nnzA;
   int64_t n_pairs;            /* (supernode, descendant) update pairs, = sum of ereach_sn sizes   */

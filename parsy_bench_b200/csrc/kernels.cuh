@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128) k_update_small(const SmallTask* __restric
 // narrow supernodes: one warp each, POTRF (MyBLAS.h:10-25 semantics) + TRSM (MyBLAS.h:27-35) fused
 // ------------------------------------------------------------------------------------------------
 template <int WMAX>
-__global__ void __launch_bounds__(128) k_factor_small(const int* __restrict__ list, int count,
+__global__ void __launch_bounds__(128, WMAX > 8 ? 5 : 8) k_factor_small(const int* __restrict__ list, int count,
                                                        const SupInfo* __restrict__ sup, double* __restrict__ lv,
                                                        int* __restrict__ info) {
   constexpr int LDS = WMAX + 1;
@@ -890,6 +890,11 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void spin_until_ge_busy(const int* p, int target) {
   while (ld_acquire_gpu(p) < target) {}
 }
@@ -897,11 +902,285 @@ __device__ __forceinline__ void spin_until_ge_busy(const int* p, int target) {
 constexpr int SWEEP_THREADS = 256;
 constexpr size_t FWD_SWEEP_SMEM = (size_t)(NB_MAX * (NB_MAX + 1) / 2) * 8;   // packed lower triangle of one inverse block
 
+// ------------------------------------------------------------------------------------------------
+// Narrow supernodes (width <= SMALL_W) in the sweeps.  Two task shapes, shared by the general dataflow kernels and
+// the light narrow-only kernels below:
+//   * warp task   — one warp per supernode, eight per CTA (SolveCta kind 0);
+//   * tall task   — one CTA per supernode whose panel below the diagonal block is long (kind 2): warp 0 solves the
+//                   diagonal block, all eight warps stream the rows (256 per pass).  A single warp would walk such a
+//                   panel 32 rows at a time, ~1 us per pass, right on the dependency chain (measured with
+//                   parsy_cuda_sweep_trace: up to 114 us per task on the 2-D 1000x1000 grid).
+// The diagonal block sits in shared memory (packed lower triangle, column c at c*w - c(c-1)/2) with the reciprocal
+// diagonal beside it; it, the row indices and the first columns of the first pass are fetched BEFORE the task waits for
+// its inputs, and panel loads are issued in batches so that one memory latency covers several columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int NARROW_TRI = SMALL_W * (SMALL_W + 1) / 2;
+constexpr int NARROW_PF = 4;        // columns of the first 32 rows a warp task prefetches
+constexpr int TALL_PF = 8;          // columns of the first 256 rows a tall task prefetches
+constexpr int NARROW_SCRATCH = NARROW_TRI + SMALL_W;   // doubles of shared memory per warp task: L, R
+
+__device__ __forceinline__ void narrow_stage_diag(double* L, double* R, const double* __restrict__ P, int w, int r, int lane) {
+  for (int c0 = 0; c0 < w; c0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + u;
+      v[u] = (c < w && lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + u;
+      if (c < w && lane >= c && lane < w) L[c * w - (c * (c - 1)) / 2 + (lane - c)] = v[u];
+    }
+  }
+  __syncwarp();
+  if (lane < w) R[lane] = 1.0 / L[lane * w - (lane * (lane - 1)) / 2];
+  __syncwarp();
+}
+// x_b = inv(L11) y_b by one warp (lane = row), L11 and 1/diag in shared memory
+__device__ __forceinline__ double narrow_fwd_subst(double xv, const double* L, const double* R, int w, int lane) {
+  for (int c = 0; c < w; ++c) {
+    const double xc = __shfl_sync(0xffffffffu, xv, c) * R[c];
+    if (lane == c) xv = xc;
+    else if (lane > c && lane < w) xv = fma(-L[c * w - (c * (c - 1)) / 2 + (lane - c)], xc, xv);
+  }
+  return xv;
+}
+// x_b = inv(L11') t, column-oriented: x_c is final once every x_k, k > c, has been eliminated from it
+__device__ __forceinline__ double narrow_bwd_subst(double mine, const double* L, const double* R, int w, int lane) {
+  for (int c = w - 1; c >= 0; --c) {
+    const double xc = __shfl_sync(0xffffffffu, mine, c) * R[c];
+    if (lane == c) mine = xc;
+    else if (lane < c) mine = fma(-L[lane * w - (lane * (lane - 1)) / 2 + (c - lane)], xc, mine);
+  }
+  return mine;
+}
+
+__device__ __forceinline__ void fwd_narrow_warp_task(const SolveTask& T, const SupInfo& I, double* L, double* R, int lane,
+                                                     const int* __restrict__ targets, const int* __restrict__ need,
+                                                     int* __restrict__ done, const int* __restrict__ lR,
+                                                     const double* __restrict__ lv, double* __restrict__ y,
+                                                     double* __restrict__ xs) {
+  const int w = I.w, r = I.r;
+  const double* __restrict__ P = lv + I.valptr;
+  const int* __restrict__ rows = lR + I.rowptr;
+  const int ifirst = w + lane;
+  const int row_first = (ifirst < r) ? rows[ifirst] : -1;
+  double pf[NARROW_PF];
+#pragma unroll
+  for (int u = 0; u < NARROW_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
+  narrow_stage_diag(L, R, P, w, r, lane);
+  if (lane == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
+  __syncwarp();
+  double xv = (lane < w) ? __ldcg(&y[I.col0 + lane]) : 0.0;
+  xv = narrow_fwd_subst(xv, L, R, w, lane);
+  if (lane < w) xs[I.col0 + lane] = xv;
+  for (int i0 = w; i0 < r; i0 += 32) {
+    const int i = i0 + lane;
+    const bool firstc = i0 == w;
+    double t = 0.0;
+    int c = 0;
+    if (firstc) {
+#pragma unroll
+      for (int u = 0; u < NARROW_PF; ++u)
+        if (u < w) t = fma(pf[u], __shfl_sync(0xffffffffu, xv, u), t);
+      c = min(w, NARROW_PF);
+    }
+    for (; c < w; c += 4) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (c + u < w && i < r) ? P[(int64_t)(c + u) * r + i] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t = fma(v[u], __shfl_sync(0xffffffffu, xv, (c + u) & 31), t);
+    }
+    const int row = firstc ? row_first : (i < r ? rows[i] : -1);
+    if (row >= 0) atomicAdd(&y[row], -t);
+  }
+  __threadfence();
+  __syncwarp();
+  for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) atomicAdd(&done[targets[q]], 1);
+}
+
+// scratch: L[NARROW_TRI] R[SMALL_W] sxv[SMALL_W]
+__device__ __forceinline__ void fwd_narrow_tall_task(const SolveTask& T, const SupInfo& I, double* scratch, int tid,
+                                                     const int* __restrict__ targets, const int* __restrict__ need,
+                                                     int* __restrict__ done, const int* __restrict__ lR,
+                                                     const double* __restrict__ lv, double* __restrict__ y,
+                                                     double* __restrict__ xs) {
+  double* L = scratch;
+  double* R = scratch + NARROW_TRI;
+  double* sxv = R + SMALL_W;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int w = I.w, r = I.r;
+  const double* __restrict__ P = lv + I.valptr;
+  const int* __restrict__ rows = lR + I.rowptr;
+  const int ifirst = w + tid;
+  const int row_first = (ifirst < r) ? rows[ifirst] : -1;
+  double pf[TALL_PF];
+#pragma unroll
+  for (int u = 0; u < TALL_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
+  if (warp == 0) narrow_stage_diag(L, R, P, w, r, lane);
+  if (tid == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
+  __syncthreads();
+  if (warp == 0) {
+    double xv = (lane < w) ? __ldcg(&y[I.col0 + lane]) : 0.0;
+    xv = narrow_fwd_subst(xv, L, R, w, lane);
+    if (lane < w) xs[I.col0 + lane] = xv;
+    sxv[lane] = (lane < w) ? xv : 0.0;
+  }
+  __syncthreads();
+  for (int i0 = w; i0 < r; i0 += SWEEP_THREADS) {
+    const int i = i0 + tid;
+    const bool firstc = i0 == w;
+    double t = 0.0;
+    int c = 0;
+    if (firstc) {
+#pragma unroll
+      for (int u = 0; u < TALL_PF; ++u) t = fma(pf[u], sxv[u], t);
+      c = min(w, TALL_PF);
+    }
+    for (; c < w; c += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (c + u < w && i < r) ? P[(int64_t)(c + u) * r + i] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t = fma(v[u], sxv[(c + u) & (SMALL_W - 1)], t);
+    }
+    const int row = firstc ? row_first : (i < r ? rows[i] : -1);
+    if (row >= 0) atomicAdd(&y[row], -t);
+  }
+  __threadfence();
+  __syncthreads();
+  for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) atomicAdd(&done[targets[q]], 1);
+}
+
+__device__ __forceinline__ void bwd_narrow_warp_task(const SolveTask& T, const SupInfo& I, double* L, double* R, int lane,
+                                                     const int* __restrict__ targets, int* __restrict__ solved,
+                                                     const int* __restrict__ lR, const double* __restrict__ lv,
+                                                     double* __restrict__ x) {
+  const int w = I.w, r = I.r;
+  const double* __restrict__ P = lv + I.valptr;
+  const int* __restrict__ rows = lR + I.rowptr;
+  const int ifirst = w + lane;
+  const int row_first = (ifirst < r) ? rows[ifirst] : -1;
+  double pf[NARROW_PF];
+#pragma unroll
+  for (int u = 0; u < NARROW_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
+  narrow_stage_diag(L, R, P, w, r, lane);
+  for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) spin_until_ge_busy(&solved[targets[q]], 1);
+  __syncwarp();
+  double mine = (lane < w) ? __ldcg(&x[I.col0 + lane]) : 0.0;
+  const double xr_first = (row_first >= 0) ? __ldcg(&x[row_first]) : 0.0;
+  // t_c = sum_i L(i,c) x[rows[i]], four columns at a time: per-lane partial sums over the lane's rows, then one
+  // interleaved shuffle reduction per group
+  for (int c0 = 0; c0 < w; c0 += 4) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i0 = w; i0 < r; i0 += 32) {
+      const int ii = i0 + lane;
+      if (i0 == w) {
+        if (c0 == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fma(pf[u], xr_first, acc[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = (c0 + u < w && ii < r) ? fma(P[(int64_t)(c0 + u) * r + ii], xr_first, acc[u]) : acc[u];
+        }
+      } else {
+        const double xr = (ii < r) ? __ldcg(&x[rows[ii]]) : 0.0;
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (c0 + u < w && ii < r) ? P[(int64_t)(c0 + u) * r + ii] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(v[u], xr, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (lane == c0 + u) mine -= acc[u];
+  }
+  mine = narrow_bwd_subst(mine, L, R, w, lane);
+  if (lane < w) x[I.col0 + lane] = mine;
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(&solved[T.node], 1);
+}
+
+// scratch: L[NARROW_TRI] R[SMALL_W] sred[8 warps][8 columns]
+__device__ __forceinline__ void bwd_narrow_tall_task(const SolveTask& T, const SupInfo& I, double* scratch, int tid,
+                                                     const int* __restrict__ targets, int* __restrict__ solved,
+                                                     const int* __restrict__ lR, const double* __restrict__ lv,
+                                                     double* __restrict__ x) {
+  double* L = scratch;
+  double* R = scratch + NARROW_TRI;
+  double* sred = R + SMALL_W;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int w = I.w, r = I.r;
+  const double* __restrict__ P = lv + I.valptr;
+  const int* __restrict__ rows = lR + I.rowptr;
+  const int ifirst = w + tid;
+  const int row_first = (ifirst < r) ? rows[ifirst] : -1;
+  double pf[TALL_PF];
+#pragma unroll
+  for (int u = 0; u < TALL_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
+  if (warp == 0) narrow_stage_diag(L, R, P, w, r, lane);
+  for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) spin_until_ge_busy(&solved[targets[q]], 1);
+  __syncthreads();
+  double mine = (warp == 0 && lane < w) ? __ldcg(&x[I.col0 + lane]) : 0.0;
+  const double xr_first = (row_first >= 0) ? __ldcg(&x[row_first]) : 0.0;
+  for (int c0 = 0; c0 < w; c0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+    for (int i0 = w; i0 < r; i0 += SWEEP_THREADS) {
+      const int ii = i0 + tid;
+      if (i0 == w && c0 == 0) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = fma(pf[u], xr_first, acc[u]);
+      } else {
+        const double xr = (i0 == w) ? xr_first : ((ii < r) ? __ldcg(&x[rows[ii]]) : 0.0);
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (c0 + u < w && ii < r) ? P[(int64_t)(c0 + u) * r + ii] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = fma(v[u], xr, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sred[warp * 8 + u] = acc[u];
+    }
+    __syncthreads();
+    if (warp == 0 && lane >= c0 && lane < c0 + 8 && lane < w) {
+      double tsum = 0.0;
+#pragma unroll
+      for (int wp = 0; wp < SWEEP_THREADS / 32; ++wp) tsum += sred[wp * 8 + (lane - c0)];
+      mine -= tsum;
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    mine = narrow_bwd_subst(mine, L, R, w, lane);
+    if (lane < w) x[I.col0 + lane] = mine;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(&solved[T.node], 1);
+  }
+}
+
 __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
     const SolveCta* __restrict__ ctas, const SolveTask* __restrict__ tasks, const int* __restrict__ targets,
     const int* __restrict__ need, int* __restrict__ done, int* __restrict__ ticket, const SupInfo* __restrict__ sup,
     const int* __restrict__ lR, const double* __restrict__ lv, const double* __restrict__ linv,
-    double* __restrict__ y, double* __restrict__ xs) {
+    double* __restrict__ y, double* __restrict__ xs, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) double sX[];   // packed lower triangle of the inverse diagonal block (FWD_SWEEP_SMEM)
   __shared__ int s_cta;
   __shared__ double sy[NB_MAX], sx[NB_MAX], spart[SWEEP_THREADS];
@@ -909,40 +1188,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
   if (tid == 0) s_cta = atomicAdd(ticket, 1);
   __syncthreads();
   const SolveCta C = ctas[s_cta];
-  if (C.kind == 0) {
-    if (warp >= C.count) return;
-    const SolveTask T = tasks[C.first + warp];
-    const SupInfo I = sup[T.sup];
-    const int w = I.w, r = I.r;
-    const double* __restrict__ P = lv + I.valptr;
-    double lrow[SMALL_W];   // L(lane, c), c <= lane
-#pragma unroll
-    for (int c = 0; c < SMALL_W; ++c) lrow[c] = (c < w && lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 1.0;
-    if (lane == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
-    __syncwarp();
-    double xv = (lane < w) ? __ldcg(&y[I.col0 + lane]) : 0.0;
-#pragma unroll
-    for (int c = 0; c < SMALL_W; ++c) {
-      if (c < w) {
-        const double xc = __shfl_sync(0xffffffffu, xv, c) / __shfl_sync(0xffffffffu, lrow[c], c);
-        if (lane == c) xv = xc;
-        else if (lane > c && lane < w) xv = fma(-lrow[c], xc, xv);
-      }
+  // optional timeline (parsy_cuda_sweep_trace): per CTA the globaltimer at start / inputs ready / end
+  if (trace && tid == 0) trace[3 * s_cta] = globaltimer_ns();
+  if (C.kind != 1) {
+    // narrow supernodes above the leaf region: same task code as k_fwd_narrow, scratch in the dynamic shared memory
+    if (C.kind == 2) {
+      const SolveTask T = tasks[C.first];
+      fwd_narrow_tall_task(T, sup[T.sup], sX, tid, targets, need, done, lR, lv, y, xs);
+    } else if (warp < C.count) {
+      const SolveTask T = tasks[C.first + warp];
+      double* L = sX + warp * NARROW_SCRATCH;
+      fwd_narrow_warp_task(T, sup[T.sup], L, L + NARROW_TRI, lane, targets, need, done, lR, lv, y, xs);
     }
-    if (lane < w) xs[I.col0 + lane] = xv;
-    const int* __restrict__ rows = lR + I.rowptr;
-    for (int i0 = w; i0 < r; i0 += 32) {
-      const int i = i0 + lane;
-      double t = 0.0;
-      for (int c = 0; c < w; ++c) {
-        const double xc = __shfl_sync(0xffffffffu, xv, c);
-        if (i < r) t = fma(P[(int64_t)c * r + i], xc, t);
-      }
-      if (i < r) atomicAdd(&y[rows[i]], -t);
-    }
-    __threadfence();
-    __syncwarp();
-    for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) atomicAdd(&done[targets[q]], 1);
+    if (trace && tid == 0) { trace[3 * s_cta + 1] = trace[3 * s_cta]; trace[3 * s_cta + 2] = globaltimer_ns(); }
     return;
   }
   const SolveTask T = tasks[C.first];
@@ -973,6 +1231,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
     cp_async_commit();
   }
   if (tid == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
+  if (trace && tid == 0) trace[3 * s_cta + 1] = globaltimer_ns();
   __syncthreads();
   if (tid < nb) sy[tid] = __ldcg(&y[cbase + tid]);
   cp_async_wait<0>();
@@ -1022,18 +1281,25 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
       spart[tid] = t0 + t1;
       __syncthreads();
       if (tid < 64 && myrow >= 0) atomicAdd(&y[myrow], -(spart[tid] + spart[tid + 64] + spart[tid + 128] + spart[tid + 192]));
+      // publish this tile: the nodes its rows belong to may be the next link of the chain and must not wait for
+      // the rest of the task
+      __threadfence();
+      __syncthreads();
+      const int tile = sub / SOLVE_TILE_ROWS;
+      const int* __restrict__ tt = tasks[C.first].tile_tgt;   // from global: no dynamically indexed local copy
+      const int qb = tile ? tt[tile - 1] : T.tgt_begin, qe = tt[tile];
+      for (int q = qb + tid; q < qe; q += SWEEP_THREADS) atomicAdd(&done[targets[q]], 1);
     }
-    __threadfence();
-    __syncthreads();
-    for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) atomicAdd(&done[targets[q]], 1);
   }
+  if (trace && tid == 0) trace[3 * s_cta + 2] = globaltimer_ns();
 }
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
     const SolveCta* __restrict__ ctas, int nctas, const SolveTask* __restrict__ tasks,
     const int* __restrict__ targets, const int* __restrict__ ntiles, int* __restrict__ cnt, int* __restrict__ solved,
     int* __restrict__ ticket, const SupInfo* __restrict__ sup, const int* __restrict__ lR,
-    const double* __restrict__ lv, const double* __restrict__ linv, double* __restrict__ x) {
+    const double* __restrict__ lv, const double* __restrict__ linv, double* __restrict__ x,
+    unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) double sX[];   // packed lower triangle of the inverse diagonal block (FWD_SWEEP_SMEM)
   __shared__ int s_cta, s_last;
   __shared__ double sx[SOLVE_TILE_ROWS], sy[NB_MAX];
@@ -1041,44 +1307,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
   if (tid == 0) s_cta = nctas - 1 - atomicAdd(ticket, 1);
   __syncthreads();
   const SolveCta C = ctas[s_cta];
-  if (C.kind == 0) {
-    if (warp >= C.count) return;
-    const SolveTask T = tasks[C.first + warp];
-    const SupInfo I = sup[T.sup];
-    const int w = I.w, r = I.r;
-    const double* __restrict__ P = lv + I.valptr;
-    const int* __restrict__ rows = lR + I.rowptr;
-    double lrow[SMALL_W];   // L(lane, c), c <= lane
-#pragma unroll
-    for (int c = 0; c < SMALL_W; ++c) lrow[c] = (c < w && lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 0.0;
-    for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) spin_until_ge_busy(&solved[targets[q]], 1);
-    __syncwarp();
-    double mine = (lane < w) ? __ldcg(&x[I.col0 + lane]) : 0.0;
-    // t_c = sum_i L(i,c) x[rows[i]]: every lane gathers its rows once, then one shuffle reduction per column
-    for (int i0 = w; i0 < r; i0 += 32) {
-      const int ii = i0 + lane;
-      const double xr = (ii < r) ? __ldcg(&x[rows[ii]]) : 0.0;
-      for (int c = 0; c < w; ++c) {
-        double part = (ii < r) ? P[(int64_t)c * r + ii] * xr : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == c) mine -= part;
-      }
+  if (trace && tid == 0) trace[3 * s_cta] = globaltimer_ns();
+  if (C.kind != 1) {
+    if (C.kind == 2) {
+      const SolveTask T = tasks[C.first];
+      bwd_narrow_tall_task(T, sup[T.sup], sX, tid, targets, solved, lR, lv, x);
+    } else if (warp < C.count) {
+      const SolveTask T = tasks[C.first + warp];
+      double* L = sX + warp * NARROW_SCRATCH;
+      bwd_narrow_warp_task(T, sup[T.sup], L, L + NARROW_TRI, lane, targets, solved, lR, lv, x);
     }
-#pragma unroll
-    for (int c = SMALL_W - 1; c >= 0; --c) {
-      if (c < w) {
-        double part = (lane > c && lane < w) ? lrow[c] * mine : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        const double d = __shfl_sync(0xffffffffu, lrow[c], c);
-        if (lane == c) mine = (mine - part) / d;
-      }
-    }
-    if (lane < w) x[I.col0 + lane] = mine;
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) atomicExch(&solved[T.node], 1);
+    if (trace && tid == 0) { trace[3 * s_cta + 1] = trace[3 * s_cta]; trace[3 * s_cta + 2] = globaltimer_ns(); }
     return;
   }
   const SolveTask T = tasks[C.first];
@@ -1110,6 +1349,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
   }
   for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) spin_until_ge_busy(&solved[targets[q]], 1);
   __syncthreads();
+  if (trace && tid == 0) trace[3 * s_cta + 1] = globaltimer_ns();
   if (T.nrows > 0) {
     double part[16];
 #pragma unroll
@@ -1147,7 +1387,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&cnt[T.node], 1) == ntiles[T.node] - 1);
   __syncthreads();
-  if (!s_last) { cp_async_wait<0>(); return; }
+  if (!s_last) {
+    cp_async_wait<0>();
+    if (trace && tid == 0) trace[3 * s_cta + 2] = globaltimer_ns();
+    return;
+  }
   // every slice has added its partial: x_b = inv(L_bb)' x_b, one warp per column of the inverse
   __threadfence();
   if (tid < nb) sy[tid] = __ldcg(&x[cbase + tid]);
@@ -1165,170 +1409,56 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
   __threadfence();
   __syncthreads();
   if (tid == 0) atomicExch(&solved[T.node], 1);
+  if (trace && tid == 0) trace[3 * s_cta + 2] = globaltimer_ns();
 }
 
 // ------------------------------------------------------------------------------------------------
 // Narrow-only sweep kernels for the leaf region of the tree (the CTAs of the plan that come before the first
-// block-column task; on the 2-D problems > 95 % of all supernodes).  Same ticket / counter protocol as the kernels
-// above, but nothing of the block path: no 66 KB inverse block, ~40 registers, so 40-48 warps per SM are in flight
-// instead of 16 — these tasks are a chain of dependent L2/HBM round trips and their throughput is occupancy.
-// The diagonal block sits in shared memory (packed lower triangle, column c at c*w - c(c-1)/2) with the reciprocal
-// diagonal beside it; the first 32 rows below the block (indices and up to four columns) are fetched before the
-// wait as well.
+// block-column task; on the 2-D problems > 95 % of all supernodes).  Same ticket / counter protocol and the same task
+// code as the general kernels, but nothing of the block path: no 66 KB inverse block, ~48 registers, so 40 warps per
+// SM are in flight instead of 16 — these tasks are chains of dependent L2/HBM round trips and their throughput is
+// occupancy.
 // ------------------------------------------------------------------------------------------------
-constexpr int NARROW_TRI = SMALL_W * (SMALL_W + 1) / 2;
-constexpr int NARROW_PF = 4;
-
-__device__ __forceinline__ void narrow_stage_diag(double* L, double* R, const double* __restrict__ P, int w, int r, int lane) {
-  for (int c0 = 0; c0 < w; c0 += 8) {
-    double v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = c0 + u;
-      v[u] = (c < w && lane >= c && lane < w) ? P[(int64_t)c * r + lane] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = c0 + u;
-      if (c < w && lane >= c && lane < w) L[c * w - (c * (c - 1)) / 2 + (lane - c)] = v[u];
-    }
-  }
-  __syncwarp();
-  if (lane < w) R[lane] = 1.0 / L[lane * w - (lane * (lane - 1)) / 2];
-  __syncwarp();
-}
-
 __global__ void __launch_bounds__(SWEEP_THREADS, 5) k_fwd_narrow(
     const SolveCta* __restrict__ ctas, const SolveTask* __restrict__ tasks, const int* __restrict__ targets,
     const int* __restrict__ need, int* __restrict__ done, int* __restrict__ ticket, const SupInfo* __restrict__ sup,
     const int* __restrict__ lR, const double* __restrict__ lv, double* __restrict__ y, double* __restrict__ xs) {
-  __shared__ double sL[8][NARROW_TRI];
-  __shared__ double sR[8][SMALL_W];
+  __shared__ double sScr[8 * NARROW_SCRATCH];
   __shared__ int s_cta;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_cta = atomicAdd(ticket, 1);
   __syncthreads();
   const SolveCta C = ctas[s_cta];
+  if (C.kind == 2) {
+    const SolveTask T = tasks[C.first];
+    fwd_narrow_tall_task(T, sup[T.sup], sScr, tid, targets, need, done, lR, lv, y, xs);
+    return;
+  }
   if (warp >= C.count) return;
   const SolveTask T = tasks[C.first + warp];
-  const SupInfo I = sup[T.sup];
-  const int w = I.w, r = I.r;
-  const double* __restrict__ P = lv + I.valptr;
-  const int* __restrict__ rows = lR + I.rowptr;
-  double* L = sL[warp];
-  double* R = sR[warp];
-  // everything that does not depend on the right-hand side, ahead of the wait
-  const int ifirst = w + lane;
-  const int row_first = (ifirst < r) ? rows[ifirst] : -1;
-  double pf[NARROW_PF];
-#pragma unroll
-  for (int u = 0; u < NARROW_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
-  narrow_stage_diag(L, R, P, w, r, lane);
-  if (lane == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
-  __syncwarp();
-  double xv = (lane < w) ? __ldcg(&y[I.col0 + lane]) : 0.0;
-  for (int c = 0; c < w; ++c) {
-    const double xc = __shfl_sync(0xffffffffu, xv, c) * R[c];
-    if (lane == c) xv = xc;
-    else if (lane > c && lane < w) xv = fma(-L[c * w - (c * (c - 1)) / 2 + (lane - c)], xc, xv);
-  }
-  if (lane < w) xs[I.col0 + lane] = xv;
-  for (int i0 = w; i0 < r; i0 += 32) {
-    const int i = i0 + lane;
-    const bool firstc = i0 == w;
-    double t = 0.0;
-    int c = 0;
-    if (firstc) {
-#pragma unroll
-      for (int u = 0; u < NARROW_PF; ++u)
-        if (u < w) t = fma(pf[u], __shfl_sync(0xffffffffu, xv, u), t);
-      c = min(w, NARROW_PF);
-    }
-    for (; c < w; c += 4) {
-      double v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (c + u < w && i < r) ? P[(int64_t)(c + u) * r + i] : 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) t = fma(v[u], __shfl_sync(0xffffffffu, xv, (c + u) & 31), t);
-    }
-    const int row = firstc ? row_first : (i < r ? rows[i] : -1);
-    if (row >= 0) atomicAdd(&y[row], -t);
-  }
-  __threadfence();
-  __syncwarp();
-  for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) atomicAdd(&done[targets[q]], 1);
+  double* L = sScr + warp * NARROW_SCRATCH;
+  fwd_narrow_warp_task(T, sup[T.sup], L, L + NARROW_TRI, lane, targets, need, done, lR, lv, y, xs);
 }
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 5) k_bwd_narrow(
     const SolveCta* __restrict__ ctas, int nctas, const SolveTask* __restrict__ tasks, const int* __restrict__ targets,
     int* __restrict__ solved, int* __restrict__ ticket, const SupInfo* __restrict__ sup, const int* __restrict__ lR,
     const double* __restrict__ lv, double* __restrict__ x) {
-  __shared__ double sL[8][NARROW_TRI];
-  __shared__ double sR[8][SMALL_W];
+  __shared__ double sScr[8 * NARROW_SCRATCH];
   __shared__ int s_cta;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_cta = nctas - 1 - atomicAdd(ticket, 1);
   __syncthreads();
   const SolveCta C = ctas[s_cta];
+  if (C.kind == 2) {
+    const SolveTask T = tasks[C.first];
+    bwd_narrow_tall_task(T, sup[T.sup], sScr, tid, targets, solved, lR, lv, x);
+    return;
+  }
   if (warp >= C.count) return;
   const SolveTask T = tasks[C.first + warp];
-  const SupInfo I = sup[T.sup];
-  const int w = I.w, r = I.r;
-  const double* __restrict__ P = lv + I.valptr;
-  const int* __restrict__ rows = lR + I.rowptr;
-  double* L = sL[warp];
-  double* R = sR[warp];
-  const int ifirst = w + lane;
-  const int row_first = (ifirst < r) ? rows[ifirst] : -1;
-  double pf[NARROW_PF];
-#pragma unroll
-  for (int u = 0; u < NARROW_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
-  narrow_stage_diag(L, R, P, w, r, lane);
-  for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) spin_until_ge_busy(&solved[targets[q]], 1);
-  __syncwarp();
-  double mine = (lane < w) ? __ldcg(&x[I.col0 + lane]) : 0.0;
-  const double xr_first = (row_first >= 0) ? __ldcg(&x[row_first]) : 0.0;
-  // t_c = sum_i L(i,c) x[rows[i]], four columns at a time: per-lane partial sums over the lane's rows, then one
-  // interleaved shuffle reduction per group
-  for (int c0 = 0; c0 < w; c0 += 4) {
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i0 = w; i0 < r; i0 += 32) {
-      const int ii = i0 + lane;
-      if (i0 == w) {
-        if (c0 == 0) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) acc[u] = fma(pf[u], xr_first, acc[u]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) acc[u] = (c0 + u < w && ii < r) ? fma(P[(int64_t)(c0 + u) * r + ii], xr_first, acc[u]) : acc[u];
-        }
-      } else {
-        const double xr = (ii < r) ? __ldcg(&x[rows[ii]]) : 0.0;
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (c0 + u < w && ii < r) ? P[(int64_t)(c0 + u) * r + ii] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fma(v[u], xr, acc[u]);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (lane == c0 + u) mine -= acc[u];
-  }
-  // L11' x = t, column-oriented: x_c is final once every x_k, k > c, has been eliminated from it
-  for (int c = w - 1; c >= 0; --c) {
-    const double xc = __shfl_sync(0xffffffffu, mine, c) * R[c];
-    if (lane == c) mine = xc;
-    else if (lane < c) mine = fma(-L[lane * w - (lane * (lane - 1)) / 2 + (c - lane)], xc, mine);
-  }
-  if (lane < w) x[I.col0 + lane] = mine;
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) atomicExch(&solved[T.node], 1);
+  double* L = sScr + warp * NARROW_SCRATCH;
+  bwd_narrow_warp_task(T, sup[T.sup], L, L + NARROW_TRI, lane, targets, solved, lR, lv, x);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -474,48 +474,89 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     };
     P.node_need.assign(P.n_nodes, 0);
     P.node_tiles.assign(P.n_nodes, 1);
-    auto add_targets = [&](SolveTask& t, const SupInfo& I) {
+    // per_tile: one target entry (and one unit of `need`) per node AND 64-row tile, so that a tile can be published
+    // as soon as its own atomics are out
+    auto add_targets = [&](SolveTask& t, const SupInfo& I, bool per_tile) {
       t.tgt_begin = (int32_t)P.solve_targets.size();
       int last = -1;
       for (int i = t.row0; i < t.row0 + t.nrows; ++i) {
+        if (per_tile && i > t.row0 && (i - t.row0) % SOLVE_TILE_ROWS == 0) {
+          t.tile_tgt[(i - t.row0) / SOLVE_TILE_ROWS - 1] = (int32_t)P.solve_targets.size();
+          last = -1;
+        }
         const int nd = node_of_row(lR[I.rowptr + i]);
         if (nd != last) { P.solve_targets.push_back(nd); P.node_need[nd]++; last = nd; }
       }
       t.tgt_end = (int32_t)P.solve_targets.size();
+      for (int k = per_tile ? (t.nrows + SOLVE_TILE_ROWS - 1) / SOLVE_TILE_ROWS - 1 : 0; k < 4; ++k)
+        if (k >= 0) t.tile_tgt[k] = t.tgt_end;
     };
-    bool seen_block = false;
+    // Leaf region: narrow supernodes without a block-column supernode anywhere below them in the supernodal etree.
+    // It is closed under descendants, so its tasks can run first, on the light narrow-only kernels (backward sweep:
+    // last); everything else — block columns and the narrow supernodes above them — follows on the general kernels.
+    // Both parts keep the step order, which is a topological order of the dependencies.
+    std::vector<char> above_block(supNo, 0);
+    for (int s = 0; s < supNo; ++s) {
+      const SupInfo& I = P.sup[s];
+      if (!I.flags) above_block[s] = 1;
+      if (above_block[s] && I.r > I.w) above_block[col2Sup[lR[I.rowptr + I.w]]] = 1;   // etree parent: first row below the block
+    }
     P.n_narrow_prefix_ctas = 0;
+    for (int pass = 0; pass < 2; ++pass)
     for (int st = 0; st < nsteps; ++st) {
       const Step& S = P.steps[st];
-      if (S.blocks.begin < S.blocks.end) seen_block = true;
-      if (!seen_block) P.n_narrow_prefix_ctas += cdiv(S.small_sup.end - S.small_sup.begin, 8);
-      // narrow supernodes, eight per CTA
-      for (int i0 = S.small_sup.begin; i0 < S.small_sup.end; i0 += 8) {
-        SolveCta c; c.kind = 0; c.first = (int32_t)P.solve_tasks.size(); c.count = std::min(8, S.small_sup.end - i0); c.pad = 0;
-        for (int i = i0; i < i0 + c.count; ++i) {
-          const int s = P.small_list[i];
-          const SupInfo& I = P.sup[s];
-          SolveTask t; memset(&t, 0, sizeof(t));
-          t.sup = s; t.node = node_first[s]; t.j0 = 0; t.nb = I.w; t.slot = -1; t.row0 = I.w; t.nrows = I.r - I.w; t.first = 1;
-          add_targets(t, I);
-          P.solve_tasks.push_back(t);
-        }
+      const bool seen_block = pass == 1;
+      // narrow supernodes: long panels get a CTA each (kind 2), the others go eight per CTA (kind 0)
+      auto narrow_task = [&](int s) {
+        const SupInfo& I = P.sup[s];
+        SolveTask t; memset(&t, 0, sizeof(t));
+        t.sup = s; t.node = node_first[s]; t.j0 = 0; t.nb = I.w; t.slot = -1; t.row0 = I.w; t.nrows = I.r - I.w; t.first = 1;
+        add_targets(t, I, false);
+        P.solve_tasks.push_back(t);
+      };
+      auto is_tall = [&](int s) {
+        const SupInfo& I = P.sup[s];
+        return I.r - I.w > SOLVE_TALL_ROWS && (int64_t)(I.r - I.w) * I.w >= SOLVE_TALL_WORK;
+      };
+      std::vector<int> shortlist;
+      for (int i = S.small_sup.begin; i < S.small_sup.end; ++i) {
+        const int s = P.small_list[i];
+        if ((above_block[s] != 0) != (pass == 1)) continue;
+        if (!is_tall(s)) { shortlist.push_back(s); continue; }
+        SolveCta c; c.kind = 2; c.first = (int32_t)P.solve_tasks.size(); c.count = 1; c.pad = 0;
+        narrow_task(s);
         P.solve_ctas.push_back(c);
+        if (!seen_block) P.n_narrow_prefix_ctas++;
       }
-      for (int i = S.blocks.begin; i < S.blocks.end; ++i) {
+      for (size_t i0 = 0; i0 < shortlist.size(); i0 += 8) {
+        SolveCta c; c.kind = 0; c.first = (int32_t)P.solve_tasks.size(); c.count = (int32_t)std::min<size_t>(8, shortlist.size() - i0); c.pad = 0;
+        for (int i = 0; i < c.count; ++i) narrow_task(shortlist[i0 + i]);
+        P.solve_ctas.push_back(c);
+        if (!seen_block) P.n_narrow_prefix_ctas++;
+      }
+      for (int i = S.blocks.begin; pass == 1 && i < S.blocks.end; ++i) {
         const BlockTask& b = P.block_tasks[i];
         const SupInfo& I = P.sup[b.sup];
         const int below = I.r - b.j0 - b.nb;
-        const int ntile = std::max(1, cdiv(below, SOLVE_TASK_ROWS));
+        // graded slices: the rows right below the diagonal block belong to the next block column — the next link of
+        // the dependency chain — so they go into short tasks whose whole register tile is fetched ahead of the
+        // wait (SOLVE_CRITICAL_TASKS x SOLVE_TILE_ROWS rows); everything further down has slack and is cut into
+        // SOLVE_TASK_ROWS-row tasks that amortise the diagonal-block solve
+        std::vector<int> cut;   // first row (relative to the rows below the block) of every slice, plus the end
+        cut.push_back(0);
+        for (int k = 0; k < SOLVE_CRITICAL_TASKS && cut.back() + SOLVE_TILE_ROWS < below; ++k) cut.push_back(cut.back() + SOLVE_TILE_ROWS);
+        while (cut.back() + SOLVE_TASK_ROWS < below) cut.push_back(cut.back() + SOLVE_TASK_ROWS);
+        cut.push_back(std::max(below, 0));
+        const int ntile = (int)cut.size() - 1;
         const int nd = node_first[b.sup] + b.j0 / NB;
         P.node_tiles[nd] = ntile;
         for (int k = 0; k < ntile; ++k) {
           SolveTask t; memset(&t, 0, sizeof(t));
           t.sup = b.sup; t.node = nd; t.j0 = b.j0; t.nb = b.nb; t.slot = b.slot;
-          t.row0 = b.j0 + b.nb + k * SOLVE_TASK_ROWS;
-          t.nrows = std::max(0, std::min(SOLVE_TASK_ROWS, I.r - t.row0));
+          t.row0 = b.j0 + b.nb + cut[k];
+          t.nrows = cut[k + 1] - cut[k];
           t.first = k == 0;
-          add_targets(t, I);
+          add_targets(t, I, true);
           SolveCta c; c.kind = 1; c.first = (int32_t)P.solve_tasks.size(); c.count = 1; c.pad = 0;
           P.solve_tasks.push_back(t);
           P.solve_ctas.push_back(c);

@@ -75,6 +75,9 @@ static_assert(sizeof(BlockTask) == 32, "BlockTask layout");
 // warp (narrow supernode) or one CTA (128-row slice of a block column's rows below the diagonal block) does.
 constexpr int SOLVE_TILE_ROWS = 64;     // rows a sweep CTA holds in registers at a time
 constexpr int SOLVE_TASK_ROWS = 256;    // rows of one solve task (4 register tiles share one diagonal-block solve)
+constexpr int SOLVE_TALL_ROWS = 64;     // a narrow supernode with more rows below its diagonal block than this, and at
+constexpr int SOLVE_TALL_WORK = 768;    // least this many panel entries below it, gets a CTA of its own in the sweeps
+constexpr int SOLVE_CRITICAL_TASKS = 2; // leading one-tile tasks of a block column: the rows of the NEXT block column
 struct SolveTask {
   int32_t sup;        // supernode
   int32_t node;       // node this task belongs to (the one whose solution it consumes)
@@ -84,11 +87,15 @@ struct SolveTask {
   int32_t nrows;      // rows in the slice (may be 0: a block column with nothing below it)
   int32_t first;      // 1 = this task publishes the node's solution (slice 0)
   int32_t tgt_begin, tgt_end;   // range in solve_targets: nodes whose unknowns this task's rows touch
+  int32_t tile_tgt[4];          // block-column tasks: end of the targets of each SOLVE_TILE_ROWS-row tile (tile k owns
+                                // [k ? tile_tgt[k-1] : tgt_begin, tile_tgt[k])): the forward sweep publishes tile by tile
   int32_t pad[2];
 };
-static_assert(sizeof(SolveTask) == 48, "SolveTask layout");
+static_assert(sizeof(SolveTask) == 64, "SolveTask layout");
+static_assert(SOLVE_TASK_ROWS == 4 * SOLVE_TILE_ROWS, "SolveTask::tile_tgt holds four tiles");
 struct SolveCta {     // work of one CTA of the sweep kernel
-  int32_t kind;       // 0 = up to 8 narrow supernodes (one per warp), 1 = one slice
+  int32_t kind;       // 0 = up to 8 narrow supernodes (one per warp), 1 = one slice of a block column,
+                      // 2 = one narrow supernode with a long panel, all eight warps on its rows
   int32_t first;      // index of the first SolveTask
   int32_t count;
   int32_t pad;

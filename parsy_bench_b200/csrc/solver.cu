@@ -63,6 +63,7 @@ struct parsy_cuda_solver {
   int* d_need = nullptr;
   int* d_ntiles = nullptr;
   int* d_sync = nullptr;      // [ticket | done or cnt (n_nodes) | solved (n_nodes)]
+  unsigned long long* d_sweep_trace = nullptr;   // only during parsy_cuda_sweep_trace
   bool dataflow = true;
   bool narrow_sweeps = true;  // leaf region of the sweeps on the light narrow-only kernels (reserved[5] = 1 disables)
   int64_t device_bytes = 0;
@@ -259,7 +260,7 @@ static int64_t enqueue_fwd(parsy_cuda_solver* s) {
     if (total > npre) {
       k_fwd_dataflow<<<total - npre, SWEEP_THREADS, FWD_SWEEP_SMEM, st>>>(s->d_sctas + npre, s->d_stasks, s->d_stargets, s->d_need,
                                                                          s->d_sync + 1, ticket2, s->d_sup, s->d_lR, s->d_lv,
-                                                                         s->d_linv, s->d_rhs, s->d_xs);
+                                                                         s->d_linv, s->d_rhs, s->d_xs, s->d_sweep_trace);
       ++launches;
     }
     cudaMemcpyAsync(s->d_rhs, s->d_xs, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToDevice, st);
@@ -295,7 +296,7 @@ static int64_t enqueue_bwd(parsy_cuda_solver* s) {
       k_bwd_dataflow<<<total - npre, SWEEP_THREADS, FWD_SWEEP_SMEM, st>>>(s->d_sctas + npre, total - npre, s->d_stasks,
                                                                          s->d_stargets, s->d_ntiles, s->d_sync + 1,
                                                                          s->d_sync + 1 + P.n_nodes, s->d_sync, s->d_sup, s->d_lR,
-                                                                         s->d_lv, s->d_linv, s->d_rhs);
+                                                                         s->d_lv, s->d_linv, s->d_rhs, s->d_sweep_trace);
       ++launches;
     }
     if (npre > 0) {
@@ -741,6 +742,35 @@ extern "C" int parsy_cuda_solve_system(parsy_cuda_solver* s, const double* b, do
     for (int q = 0; q < per * nrhs; ++q) rel_residual[q] = h[2 * q + 1] > 0 ? std::sqrt(h[2 * q] / h[2 * q + 1]) : std::sqrt(h[2 * q]);
   }
   return PARSY_CUDA_OK;
+}
+
+// Timeline of the general sweep kernels (diagnostics): one un-graphed forward (or backward) sweep on the current
+// right-hand side; for every CTA of k_fwd_dataflow / k_bwd_dataflow (in plan order) kind, rows, and the nanoseconds at which it started, saw its
+// inputs complete and finished, relative to the first start.  Returns the number of CTAs (or -1).
+extern "C" int parsy_cuda_sweep_trace(parsy_cuda_solver* s, int which, int max_records, int* kind, int* nrows,
+                                      double* t_start_us, double* t_ready_us, double* t_end_us) {
+  if (!s || !s->factored || !s->dataflow) { fail(PARSY_CUDA_ERR_STATE, "needs a factored handle with dataflow sweeps"); return -1; }
+  if (cudaSetDevice(s->device) != cudaSuccess) return -1;
+  const Plan& P = s->plan;
+  const int total = (int)P.solve_ctas.size(), npre = s->narrow_sweeps ? P.n_narrow_prefix_ctas : 0, cnt = total - npre;
+  if (cnt <= 0) return 0;
+  if (cudaMalloc(&s->d_sweep_trace, sizeof(unsigned long long) * 3 * (size_t)cnt) != cudaSuccess) { fail(PARSY_CUDA_ERR_CUDA, "cudaMalloc"); return -1; }
+  cudaMemsetAsync(s->d_sweep_trace, 0, sizeof(unsigned long long) * 3 * (size_t)cnt, s->stream);
+  if (which == PARSY_CUDA_SOLVE_BWD) enqueue_bwd(s); else enqueue_fwd(s);
+  cudaStreamSynchronize(s->stream);
+  std::vector<unsigned long long> h((size_t)3 * cnt);
+  cudaMemcpy(h.data(), s->d_sweep_trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
+  cudaFree(s->d_sweep_trace);
+  s->d_sweep_trace = nullptr;
+  unsigned long long t0 = ~0ull;
+  for (int i = 0; i < cnt; ++i) if (h[3 * i] && h[3 * i] < t0) t0 = h[3 * i];
+  for (int i = 0; i < cnt && i < max_records; ++i) {
+    const SolveCta& C = P.solve_ctas[npre + i];
+    kind[i] = C.kind;
+    nrows[i] = C.kind ? P.solve_tasks[C.first].nrows : C.count;
+    t_start_us[i] = (h[3 * i] - t0) * 1e-3; t_ready_us[i] = (h[3 * i + 1] - t0) * 1e-3; t_end_us[i] = (h[3 * i + 2] - t0) * 1e-3;
+  }
+  return cudaGetLastError() == cudaSuccess ? cnt : -1;
 }
 
 extern "C" int parsy_cuda_factor_times(parsy_cuda_solver* s, double* out3) {
