@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="single stream, no overlap of POTRF/TRSM with the bulk updates")
     ap.add_argument("--ignore-hlevels", action="store_true", help="schedule by dependencies only (no LBC H-level barriers)")
+    ap.add_argument("--no-fan-out", action="store_true", help="kernel classes of a step on one stream (A/B)")
     ap.add_argument("--general-sweeps", action="store_true", help="leaf region of the sweeps on the general dataflow kernel (A/B)")
     ap.add_argument("--replicas", action="store_true", help="N>1: one full factorization per GPU instead of sharding")
     ap.add_argument("--replicate-top", action="store_true", help="N>1: every rank computes the top separators")
@@ -319,7 +320,7 @@ def main():
     t0 = time.time()
     H = ex.Solver(n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels, S.levelPtr,
                   S.parPtr, S.partition, device=local, block_cols=args.block_cols, ignore_hlevels=args.ignore_hlevels,
-                  lookahead=not args.no_lookahead, narrow_sweeps=not args.general_sweeps)
+                  lookahead=not args.no_lookahead, narrow_sweeps=not args.general_sweeps, fan_out=not args.no_fan_out)
     t_create = time.time() - t0
     st = H.stats()
     F = S.flops

@@ -114,7 +114,8 @@ typedef struct parsy_cuda_options {
   int world;           /* ... of `world` ranks (0/1 = single GPU)                                  */
   int reserved[10];    /* [0]=1 no look-ahead stream, [1]=1 per-step sweeps, [2] phase, [3] top H-levels kept shared,
                           [4]=1 replicate the top instead of distributing it,
-                          [5]=1 run the leaf region of the sweeps on the general dataflow kernel too */
+                          [5]=1 run the leaf region of the sweeps on the general dataflow kernel too,
+                          [6]=1 keep the kernel classes of a step on one stream (no fan-out over auxiliary streams) */
 } parsy_cuda_options;
 
 /* Builds the device-resident symbolic state from the inspector's arrays (all HOST pointers, copied):

@@ -29,6 +29,11 @@ struct parsy_cuda_solver {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_F[2] = {nullptr, nullptr}, ev_R[2] = {nullptr, nullptr};
   bool lookahead = true;
+  // kernel classes of one step are independent of each other (different supernodes, or red.add into L): they are
+  // fanned out over auxiliary streams — set 0 next to the side stream (high priority), set 1 next to the main stream
+  cudaStream_t aux[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+  cudaEvent_t ev_fan_fork[2] = {nullptr, nullptr}, ev_fan_join[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+  bool fan_out = true;        // reserved[6] = 1 keeps every class of a step on one stream
   int phase = 0;              // 0 single GPU, 1 owned bottom subtrees, 2 shared top (multi-GPU)
   bool owns_lv = true;
   int la_first = 0;
@@ -120,84 +125,122 @@ struct LaunchProfiler {
 #define PROF_BEGIN(c) do { if (prof) prof->begin(c); } while (0)
 #define PROF_END() do { if (prof) prof->end(); } while (0)
 
+// Fork/join of the independent kernel classes of one step: the first class stays on `st`, the others go to the
+// auxiliary streams of st's set and are joined back before the caller continues (works eagerly and under capture).
+struct Fan {
+  parsy_cuda_solver* s;
+  cudaStream_t st;
+  int set, used = 0, count = 0;
+  bool on;
+  Fan(parsy_cuda_solver* s_, cudaStream_t st_, bool on_) : s(s_), st(st_), set(st_ == s_->stream2 ? 0 : 1), on(on_ && s_->fan_out) {
+    if (on) cudaEventRecord(s->ev_fan_fork[set], st);
+  }
+  cudaStream_t pick() {
+    if (!on || count++ == 0 || used == 4) return st;
+    cudaStream_t q = s->aux[set][used++];
+    cudaStreamWaitEvent(q, s->ev_fan_fork[set], 0);
+    return q;
+  }
+  void join() {
+    for (int k = 0; k < used; ++k) {
+      cudaEventRecord(s->ev_fan_join[set][k], s->aux[set][k]);
+      cudaStreamWaitEvent(st, s->ev_fan_join[set][k], 0);
+    }
+    used = 0;
+  }
+};
+
 static int64_t launch_factor_phase(parsy_cuda_solver* s, const Step& S, cudaStream_t st, LaunchProfiler* prof) {
   int64_t launches = 0;
-  if (S.small_narrow > 0) {
-    PROF_BEGIN(0);
-    k_factor_small<SMALL_W_NARROW><<<cdivi(S.small_narrow, 4), 128, 0, st>>>(s->d_small_list + S.small_sup.begin,
-                                                                             S.small_narrow, s->d_sup, s->d_lv, s->d_info);
-    PROF_END();
-    ++launches;
-  }
-  if (S.small_sup.size() - S.small_narrow > 0) {
-    PROF_BEGIN(0);
-    const int cnt = S.small_sup.size() - S.small_narrow;
-    k_factor_small<SMALL_W><<<cdivi(cnt, 4), 128, 0, st>>>(s->d_small_list + S.small_sup.begin + S.small_narrow, cnt,
-                                                           s->d_sup, s->d_lv, s->d_info);
-    PROF_END();
-    ++launches;
-  }
+  Fan fan(s, st, prof == nullptr);
+  // the block columns first: POTRF -> TRSM is the latency-critical chain of the step
   if (S.blocks.size()) {
+    cudaStream_t q = fan.pick();
     PROF_BEGIN(1);
     const int cols = (S.max_nb + 15) & ~15;
-    k_potrf_block<<<S.blocks.size(), POTRF_THREADS, potrf_smem_bytes(cols), st>>>(s->d_blocks + S.blocks.begin, s->d_sup,
-                                                                                  s->d_lv, s->d_linv, s->d_info, cols);
+    k_potrf_block<<<S.blocks.size(), POTRF_THREADS, potrf_smem_bytes(cols), q>>>(s->d_blocks + S.blocks.begin, s->d_sup,
+                                                                                 s->d_lv, s->d_linv, s->d_info, cols);
+    PROF_END();
+    ++launches;
+    if (S.trsm_tiles) {
+      PROF_BEGIN(2);
+      const GemmTask* tk = s->d_gemm + S.trsm.begin;
+      if (S.trsm_tm == 64)
+        k_gemm_tiles<CfgTrsm><<<S.trsm_tiles, CfgTrsm::THREADS, CfgTrsm::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+      else if (S.trsm_tm == 32)
+        k_gemm_tiles<CfgTrsm32><<<S.trsm_tiles, CfgTrsm32::THREADS, CfgTrsm32::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+      else
+        k_gemm_tiles<CfgTrsm16><<<S.trsm_tiles, CfgTrsm16::THREADS, CfgTrsm16::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+      PROF_END();
+      ++launches;
+    }
+  }
+  if (S.small_sup.size() - S.small_narrow > 0) {
+    cudaStream_t q = fan.pick();
+    PROF_BEGIN(0);
+    const int cnt = S.small_sup.size() - S.small_narrow;
+    k_factor_small<SMALL_W><<<cdivi(cnt, 4), 128, 0, q>>>(s->d_small_list + S.small_sup.begin + S.small_narrow, cnt,
+                                                          s->d_sup, s->d_lv, s->d_info);
     PROF_END();
     ++launches;
   }
-  if (S.trsm_tiles) {
-    PROF_BEGIN(2);
-    const GemmTask* tk = s->d_gemm + S.trsm.begin;
-    if (S.trsm_tm == 64)
-      k_gemm_tiles<CfgTrsm><<<S.trsm_tiles, CfgTrsm::THREADS, CfgTrsm::SMEM, st>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
-    else if (S.trsm_tm == 32)
-      k_gemm_tiles<CfgTrsm32><<<S.trsm_tiles, CfgTrsm32::THREADS, CfgTrsm32::SMEM, st>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
-    else
-      k_gemm_tiles<CfgTrsm16><<<S.trsm_tiles, CfgTrsm16::THREADS, CfgTrsm16::SMEM, st>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+  if (S.small_narrow > 0) {
+    cudaStream_t q = fan.pick();
+    PROF_BEGIN(0);
+    k_factor_small<SMALL_W_NARROW><<<cdivi(S.small_narrow, 4), 128, 0, q>>>(s->d_small_list + S.small_sup.begin,
+                                                                            S.small_narrow, s->d_sup, s->d_lv, s->d_info);
     PROF_END();
     ++launches;
   }
+  fan.join();
   return launches;
 }
 
 static int64_t launch_update_group(parsy_cuda_solver* s, const UpdGroup& U, cudaStream_t st, LaunchProfiler* prof) {
   int64_t launches = 0;
+  Fan fan(s, st, prof == nullptr);
   if (U.tiles128) {
+    cudaStream_t q = fan.pick();
     PROF_BEGIN(3);
-    k_gemm_tiles<Cfg128><<<U.tiles128, Cfg128::THREADS, Cfg128::SMEM, st>>>(s->d_gemm + U.u128.begin, U.u128.size(),
-                                                                            s->d_lv, s->d_linv, s->d_rel);
+    k_gemm_tiles<Cfg128><<<U.tiles128, Cfg128::THREADS, Cfg128::SMEM, q>>>(s->d_gemm + U.u128.begin, U.u128.size(),
+                                                                           s->d_lv, s->d_linv, s->d_rel);
     PROF_END();
     ++launches;
   }
   if (U.tiles64) {
+    cudaStream_t q = fan.pick();
     PROF_BEGIN(4);
-    k_gemm_tiles<Cfg64><<<U.tiles64, Cfg64::THREADS, Cfg64::SMEM, st>>>(s->d_gemm + U.u64.begin, U.u64.size(), s->d_lv,
-                                                                        s->d_linv, s->d_rel);
+    k_gemm_tiles<Cfg64><<<U.tiles64, Cfg64::THREADS, Cfg64::SMEM, q>>>(s->d_gemm + U.u64.begin, U.u64.size(), s->d_lv,
+                                                                       s->d_linv, s->d_rel);
     PROF_END();
     ++launches;
   }
   if (U.tiles32) {
+    cudaStream_t q = fan.pick();
     PROF_BEGIN(4);
-    k_gemm_tiles<Cfg32><<<U.tiles32, Cfg32::THREADS, Cfg32::SMEM, st>>>(s->d_gemm + U.u32.begin, U.u32.size(), s->d_lv,
-                                                                        s->d_linv, s->d_rel);
-    PROF_END();
-    ++launches;
-  }
-  if (U.small_narrow > 0) {
-    PROF_BEGIN(5);
-    k_update_small<4><<<cdivi(U.small_narrow, 4), 128, 0, st>>>(s->d_small_tasks + U.small.begin, U.small_narrow,
-                                                                s->d_gemm, s->d_lv, s->d_rel);
+    k_gemm_tiles<Cfg32><<<U.tiles32, Cfg32::THREADS, Cfg32::SMEM, q>>>(s->d_gemm + U.u32.begin, U.u32.size(), s->d_lv,
+                                                                       s->d_linv, s->d_rel);
     PROF_END();
     ++launches;
   }
   if (U.small.size() - U.small_narrow > 0) {
+    cudaStream_t q = fan.pick();
     PROF_BEGIN(5);
     const int cnt = U.small.size() - U.small_narrow;
-    k_update_small<32><<<cdivi(cnt, 4), 128, 0, st>>>(s->d_small_tasks + U.small.begin + U.small_narrow, cnt, s->d_gemm,
-                                                      s->d_lv, s->d_rel);
+    k_update_small<32><<<cdivi(cnt, 4), 128, 0, q>>>(s->d_small_tasks + U.small.begin + U.small_narrow, cnt, s->d_gemm,
+                                                     s->d_lv, s->d_rel);
     PROF_END();
     ++launches;
   }
+  if (U.small_narrow > 0) {
+    cudaStream_t q = fan.pick();
+    PROF_BEGIN(5);
+    k_update_small<4><<<cdivi(U.small_narrow, 4), 128, 0, q>>>(s->d_small_tasks + U.small.begin, U.small_narrow,
+                                                               s->d_gemm, s->d_lv, s->d_rel);
+    PROF_END();
+    ++launches;
+  }
+  fan.join();
   return launches;
 }
 
@@ -359,6 +402,13 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {s->ev_fork, s->ev_join, s->ev_F[0], s->ev_F[1], s->ev_R[0], s->ev_R[1]}) if (e) cudaEventDestroy(e);
+  for (int set = 0; set < 2; ++set) {
+    if (s->ev_fan_fork[set]) cudaEventDestroy(s->ev_fan_fork[set]);
+    for (int k = 0; k < 4; ++k) {
+      if (s->ev_fan_join[set][k]) cudaEventDestroy(s->ev_fan_join[set][k]);
+      if (s->aux[set][k]) cudaStreamDestroy(s->aux[set][k]);
+    }
+  }
   if (s->stream2) cudaStreamDestroy(s->stream2);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -415,6 +465,18 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
   }
   for (cudaEvent_t* e : {&s->ev_fork, &s->ev_join, &s->ev_F[0], &s->ev_F[1], &s->ev_R[0], &s->ev_R[1]})
     TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  {
+    int lo = 0, hi = 0;
+    TRYCU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int set = 0; set < 2; ++set) {
+      TRYCU(cudaEventCreateWithFlags(&s->ev_fan_fork[set], cudaEventDisableTiming));
+      for (int k = 0; k < 4; ++k) {
+        TRYCU(cudaStreamCreateWithPriority(&s->aux[set][k], cudaStreamNonBlocking, set == 0 ? hi : lo));
+        TRYCU(cudaEventCreateWithFlags(&s->ev_fan_join[set][k], cudaEventDisableTiming));
+      }
+    }
+  }
+  s->fan_out = o.reserved[6] == 0;
   s->lookahead = o.reserved[0] == 0;   // reserved[0] = 1 disables the two-stream look-ahead
   for (auto& e : s->ev) TRYCU(cudaEventCreate(&e));
   TRY(dev_upload(s, &s->d_sup, P.sup.data(), P.sup.size()));

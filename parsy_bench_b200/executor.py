@@ -248,7 +248,7 @@ class Solver:
 
     def __init__(self, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
                  device=0, block_cols=0, use_graph=True, ignore_hlevels=False, lookahead=True, dataflow_sweeps=True,
-                 rank=0, world=1, phase=0, top_levels=1, top_distributed=True, narrow_sweeps=True):
+                 rank=0, world=1, phase=0, top_levels=1, top_distributed=True, narrow_sweeps=True, fan_out=True):
         L = lib()
         self._L = L
         self._h = c_void_p()
@@ -258,7 +258,7 @@ class Solver:
         opt.rank, opt.world = int(rank), int(world)
         opt.reserved[0], opt.reserved[1] = int(not lookahead), int(not dataflow_sweeps)
         opt.reserved[2], opt.reserved[3], opt.reserved[4] = int(phase), int(top_levels), int(not top_distributed)
-        opt.reserved[5] = int(not narrow_sweeps)
+        opt.reserved[5], opt.reserved[6] = int(not narrow_sweeps), int(not fan_out)
         f = L.parsy_cuda_create
         f.restype = c_int
         f.argtypes = [POINTER(c_void_p), c_int] + [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + \
