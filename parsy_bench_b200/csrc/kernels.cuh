@@ -956,6 +956,12 @@ __device__ __forceinline__ double narrow_bwd_subst(double mine, const double* L,
   return mine;
 }
 
+__device__ __forceinline__ SupInfo narrow_info(const SolveTask& T) {
+  SupInfo I;
+  I.rowptr = T.rowptr; I.valptr = T.valptr; I.col0 = T.col0; I.w = T.nb; I.r = T.r; I.flags = 1;
+  return I;
+}
+
 __device__ __forceinline__ void fwd_narrow_warp_task(const SolveTask& T, const SupInfo& I, double* L, double* R, int lane,
                                                      const int* __restrict__ targets, const int* __restrict__ need,
                                                      int* __restrict__ done, const int* __restrict__ lR,
@@ -969,8 +975,9 @@ __device__ __forceinline__ void fwd_narrow_warp_task(const SolveTask& T, const S
   double pf[NARROW_PF];
 #pragma unroll
   for (int u = 0; u < NARROW_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
+  const int tq = (T.tgt_begin + lane < T.tgt_end) ? targets[T.tgt_begin + lane] : -1;
   narrow_stage_diag(L, R, P, w, r, lane);
-  if (lane == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
+  if (lane == 0) spin_until_ge_busy(&done[T.node], T.need);
   __syncwarp();
   double xv = (lane < w) ? __ldcg(&y[I.col0 + lane]) : 0.0;
   xv = narrow_fwd_subst(xv, L, R, w, lane);
@@ -998,7 +1005,8 @@ __device__ __forceinline__ void fwd_narrow_warp_task(const SolveTask& T, const S
   }
   __threadfence();
   __syncwarp();
-  for (int q = T.tgt_begin + lane; q < T.tgt_end; q += 32) atomicAdd(&done[targets[q]], 1);
+  if (tq >= 0) atomicAdd(&done[tq], 1);
+  for (int q = T.tgt_begin + 32 + lane; q < T.tgt_end; q += 32) atomicAdd(&done[targets[q]], 1);
 }
 
 // scratch: L[NARROW_TRI] R[SMALL_W] sxv[SMALL_W]
@@ -1019,8 +1027,9 @@ __device__ __forceinline__ void fwd_narrow_tall_task(const SolveTask& T, const S
   double pf[TALL_PF];
 #pragma unroll
   for (int u = 0; u < TALL_PF; ++u) pf[u] = (u < w && ifirst < r) ? P[(int64_t)u * r + ifirst] : 0.0;
+  const int tq = (T.tgt_begin + tid < T.tgt_end) ? targets[T.tgt_begin + tid] : -1;
   if (warp == 0) narrow_stage_diag(L, R, P, w, r, lane);
-  if (tid == 0) spin_until_ge_busy(&done[T.node], need[T.node]);
+  if (tid == 0) spin_until_ge_busy(&done[T.node], T.need);
   __syncthreads();
   if (warp == 0) {
     double xv = (lane < w) ? __ldcg(&y[I.col0 + lane]) : 0.0;
@@ -1051,7 +1060,8 @@ __device__ __forceinline__ void fwd_narrow_tall_task(const SolveTask& T, const S
   }
   __threadfence();
   __syncthreads();
-  for (int q = T.tgt_begin + tid; q < T.tgt_end; q += SWEEP_THREADS) atomicAdd(&done[targets[q]], 1);
+  if (tq >= 0) atomicAdd(&done[tq], 1);
+  for (int q = T.tgt_begin + SWEEP_THREADS + tid; q < T.tgt_end; q += SWEEP_THREADS) atomicAdd(&done[targets[q]], 1);
 }
 
 __device__ __forceinline__ void bwd_narrow_warp_task(const SolveTask& T, const SupInfo& I, double* L, double* R, int lane,
@@ -1194,11 +1204,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_fwd_dataflow(
     // narrow supernodes above the leaf region: same task code as k_fwd_narrow, scratch in the dynamic shared memory
     if (C.kind == 2) {
       const SolveTask T = tasks[C.first];
-      fwd_narrow_tall_task(T, sup[T.sup], sX, tid, targets, need, done, lR, lv, y, xs);
+      fwd_narrow_tall_task(T, narrow_info(T), sX, tid, targets, need, done, lR, lv, y, xs);
     } else if (warp < C.count) {
       const SolveTask T = tasks[C.first + warp];
       double* L = sX + warp * NARROW_SCRATCH;
-      fwd_narrow_warp_task(T, sup[T.sup], L, L + NARROW_TRI, lane, targets, need, done, lR, lv, y, xs);
+      fwd_narrow_warp_task(T, narrow_info(T), L, L + NARROW_TRI, lane, targets, need, done, lR, lv, y, xs);
     }
     if (trace && tid == 0) { trace[3 * s_cta + 1] = trace[3 * s_cta]; trace[3 * s_cta + 2] = globaltimer_ns(); }
     return;
@@ -1302,7 +1312,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
     unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) double sX[];   // packed lower triangle of the inverse diagonal block (FWD_SWEEP_SMEM)
   __shared__ int s_cta, s_last;
-  __shared__ double sx[SOLVE_TILE_ROWS], sy[NB_MAX];
+  __shared__ double sx[SOLVE_TILE_ROWS], sy[NB_MAX], spart[SWEEP_THREADS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_cta = nctas - 1 - atomicAdd(ticket, 1);
   __syncthreads();
@@ -1311,11 +1321,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
   if (C.kind != 1) {
     if (C.kind == 2) {
       const SolveTask T = tasks[C.first];
-      bwd_narrow_tall_task(T, sup[T.sup], sX, tid, targets, solved, lR, lv, x);
+      bwd_narrow_tall_task(T, narrow_info(T), sX, tid, targets, solved, lR, lv, x);
     } else if (warp < C.count) {
       const SolveTask T = tasks[C.first + warp];
       double* L = sX + warp * NARROW_SCRATCH;
-      bwd_narrow_warp_task(T, sup[T.sup], L, L + NARROW_TRI, lane, targets, solved, lR, lv, x);
+      bwd_narrow_warp_task(T, narrow_info(T), L, L + NARROW_TRI, lane, targets, solved, lR, lv, x);
     }
     if (trace && tid == 0) { trace[3 * s_cta + 1] = trace[3 * s_cta]; trace[3 * s_cta + 2] = globaltimer_ns(); }
     return;
@@ -1397,15 +1407,27 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_bwd_dataflow(
   if (tid < nb) sy[tid] = __ldcg(&x[cbase + tid]);
   cp_async_wait<0>();
   __syncthreads();
-  for (int c = warp; c < nb; c += SWEEP_THREADS / 32) {
-    double part = 0.0;
-    const double* __restrict__ col = sX + (c * nb - (c * (c - 1)) / 2) - c;   // col[k] = X(k, c), k >= c
+  // x_c = sum_{k >= c} X(k, c) y_k: one thread per column and half of its k range (the same shape as the forward
+  // sweep's product; a warp-per-column reduction costs 16 dependent shuffle chains per warp on the critical path)
+  {
+    const int c = tid & 127, half = tid >> 7;
+    double a0 = 0.0, a1 = 0.0;
+    if (c < nb) {
+      const double* __restrict__ col = sX + (c * nb - (c * (c - 1)) / 2) - c;   // col[k] = X(k, c), k >= c
+      const int mid = (c + nb + 1) >> 1;
+      int k = half ? mid : c;
+      const int kend = half ? nb : mid;
 #pragma unroll 4
-    for (int k = c + lane; k < nb; k += 32) part = fma(col[k], sy[k], part);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) x[cbase + c] = part;
+      for (; k + 1 < kend; k += 2) {
+        a0 = fma(col[k], sy[k], a0);
+        a1 = fma(col[k + 1], sy[k + 1], a1);
+      }
+      if (k < kend) a0 = fma(col[k], sy[k], a0);
+    }
+    spart[tid] = a0 + a1;
   }
+  __syncthreads();
+  if (tid < nb) x[cbase + tid] = spart[tid] + spart[tid + 128];
   __threadfence();
   __syncthreads();
   if (tid == 0) atomicExch(&solved[T.node], 1);
@@ -1431,16 +1453,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 5) k_fwd_narrow(
   const SolveCta C = ctas[s_cta];
   if (C.kind == 2) {
     const SolveTask T = tasks[C.first];
-    fwd_narrow_tall_task(T, sup[T.sup], sScr, tid, targets, need, done, lR, lv, y, xs);
+    fwd_narrow_tall_task(T, narrow_info(T), sScr, tid, targets, need, done, lR, lv, y, xs);
     return;
   }
   if (warp >= C.count) return;
   const SolveTask T = tasks[C.first + warp];
   double* L = sScr + warp * NARROW_SCRATCH;
-  fwd_narrow_warp_task(T, sup[T.sup], L, L + NARROW_TRI, lane, targets, need, done, lR, lv, y, xs);
+  fwd_narrow_warp_task(T, narrow_info(T), L, L + NARROW_TRI, lane, targets, need, done, lR, lv, y, xs);
 }
 
-__global__ void __launch_bounds__(SWEEP_THREADS, 5) k_bwd_narrow(
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(SWEEP_THREADS, MIN_CTAS) k_bwd_narrow(
     const SolveCta* __restrict__ ctas, int nctas, const SolveTask* __restrict__ tasks, const int* __restrict__ targets,
     int* __restrict__ solved, int* __restrict__ ticket, const SupInfo* __restrict__ sup, const int* __restrict__ lR,
     const double* __restrict__ lv, double* __restrict__ x) {
@@ -1452,13 +1475,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 5) k_bwd_narrow(
   const SolveCta C = ctas[s_cta];
   if (C.kind == 2) {
     const SolveTask T = tasks[C.first];
-    bwd_narrow_tall_task(T, sup[T.sup], sScr, tid, targets, solved, lR, lv, x);
+    bwd_narrow_tall_task(T, narrow_info(T), sScr, tid, targets, solved, lR, lv, x);
     return;
   }
   if (warp >= C.count) return;
   const SolveTask T = tasks[C.first + warp];
   double* L = sScr + warp * NARROW_SCRATCH;
-  bwd_narrow_warp_task(T, sup[T.sup], L, L + NARROW_TRI, lane, targets, solved, lR, lv, x);
+  bwd_narrow_warp_task(T, narrow_info(T), L, L + NARROW_TRI, lane, targets, solved, lR, lv, x);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -564,6 +564,10 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       }
     }
   }
+  for (SolveTask& t : P.solve_tasks) {
+    const SupInfo& I = P.sup[t.sup];
+    t.rowptr = I.rowptr; t.valptr = I.valptr; t.col0 = I.col0; t.r = I.r; t.need = P.node_need[t.node]; t.pad2 = 0;
+  }
   return PARSY_CUDA_OK;
 }
 

@@ -90,8 +90,12 @@ struct SolveTask {
   int32_t tile_tgt[4];          // block-column tasks: end of the targets of each SOLVE_TILE_ROWS-row tile (tile k owns
                                 // [k ? tile_tgt[k-1] : tgt_begin, tile_tgt[k])): the forward sweep publishes tile by tile
   int32_t pad[2];
+  // copies of the supernode's descriptor and of the node's forward-sweep input count: a narrow task is a chain of
+  // dependent memory round trips, and these save two of them (sup[T.sup], need[T.node])
+  int64_t rowptr, valptr;
+  int32_t col0, r, need, pad2;
 };
-static_assert(sizeof(SolveTask) == 64, "SolveTask layout");
+static_assert(sizeof(SolveTask) == 96, "SolveTask layout");
 static_assert(SOLVE_TASK_ROWS == 4 * SOLVE_TILE_ROWS, "SolveTask::tile_tgt holds four tiles");
 struct SolveCta {     // work of one CTA of the sweep kernel
   int32_t kind;       // 0 = up to 8 narrow supernodes (one per warp), 1 = one slice of a block column,

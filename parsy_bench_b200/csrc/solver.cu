@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -343,8 +344,8 @@ static int64_t enqueue_bwd(parsy_cuda_solver* s) {
       ++launches;
     }
     if (npre > 0) {
-      k_bwd_narrow<<<npre, SWEEP_THREADS, 0, st>>>(s->d_sctas, npre, s->d_stasks, s->d_stargets, s->d_sync + 1 + P.n_nodes,
-                                                  ticket2, s->d_sup, s->d_lR, s->d_lv, s->d_rhs);
+      k_bwd_narrow<4><<<npre, SWEEP_THREADS, 0, st>>>(s->d_sctas, npre, s->d_stasks, s->d_stargets, s->d_sync + 1 + P.n_nodes,
+                                                     ticket2, s->d_sup, s->d_lR, s->d_lv, s->d_rhs);
       ++launches;
     }
     return launches;
