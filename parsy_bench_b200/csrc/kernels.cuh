@@ -212,7 +212,20 @@ __device__ __forceinline__ void small_update_rows(const GemmTask& T, int row0, i
     const int tr = rel[T.rel_off + i];
     const int jmax = min(T.N, i + 1);
     double* __restrict__ Cb = lv + T.c_off + tr;
-    for (int j = 0; j < jmax; ++j) {
+    // two target columns at a time: the dot products are dependent FMA chains of length KT, and a rolled j loop
+    // would run them one after the other
+    int j = 0;
+    for (; j + 1 < jmax; j += 2) {
+      double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        d0 = fma(a[k], Bs[k * 33 + j], d0);
+        d1 = fma(a[k], Bs[k * 33 + j + 1], d1);
+      }
+      atomicAdd(Cb + (int64_t)srelc[j] * T.ldc, -d0);
+      atomicAdd(Cb + (int64_t)srelc[j + 1] * T.ldc, -d1);
+    }
+    if (j < jmax) {
       double dot = 0.0;
 #pragma unroll
       for (int k = 0; k < KT; ++k) dot = fma(a[k], Bs[k * 33 + j], dot);
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(128) k_update_small(const SmallTask* __restric
   double* Bs = sB[warp];
   const double* __restrict__ src = lv + T.a_off;
   // rows K..KT of Bs are multiplied by a[k] = 0: they must hold zeros, not whatever the SM's shared memory kept
-  const int KT = KMAX <= 4 ? 4 : (T.K <= 4 ? 4 : (T.K <= 16 ? 16 : 32));
+  const int KT = KMAX <= 4 ? 4 : (T.K <= 4 ? 4 : (T.K <= 8 ? 8 : (T.K <= 16 ? 16 : (T.K <= 24 ? 24 : 32))));
   // batches of 8 independent loads (a rolled loop would pay one memory latency per k)
   for (int k0 = 0; k0 < KT; k0 += 8) {
     double v[8];
@@ -247,7 +260,9 @@ __global__ void __launch_bounds__(128) k_update_small(const SmallTask* __restric
   if (lane < T.N) sRelc[warp][lane] = rel[T.rel_off + lane];
   __syncwarp();
   if (KMAX <= 4 || T.K <= 4) small_update_rows<4>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
+  else if (T.K <= 8) small_update_rows<(KMAX < 8 ? KMAX : 8)>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
   else if (T.K <= 16) small_update_rows<(KMAX < 16 ? KMAX : 16)>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
+  else if (T.K <= 24) small_update_rows<(KMAX < 24 ? KMAX : 24)>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
   else small_update_rows<KMAX>(T, S.row0, S.nrows, lane, Bs, sRelc[warp], lv, rel);
 }
 
