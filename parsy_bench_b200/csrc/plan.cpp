@@ -2,6 +2,7 @@
 #include "plan.h"
 #include "../../include/parsy_cuda.h"
 #include <algorithm>
+#include <climits>
 #include <cstring>
 
 namespace parsy {
@@ -568,7 +569,54 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     const SupInfo& I = P.sup[t.sup];
     t.rowptr = I.rowptr; t.valptr = I.valptr; t.col0 = I.col0; t.r = I.r; t.need = P.node_need[t.node]; t.pad2 = 0;
   }
+  // the sweep kernels spin on counters: a task list that is not a topological order would hang the device
+  if (sweep_order_violations(P) != 0) { P.error = "internal error: sweep task order is not a topological order"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
   return PARSY_CUDA_OK;
+}
+
+// Deadlock-freedom of the dataflow sweeps, checked on the host.  CTAs are handed out in list order (backward sweep: in
+// reverse), resident CTAs spin until their inputs are complete, so every producer must come strictly earlier in the
+// order than its consumers (tasks inside one CTA run side by side and must not depend on each other):
+//   forward   a task that adds into node v (v in its target list) precedes every task of v, and the number of target
+//             entries naming v equals need[v];
+//   backward  every task of a node named in a task's target list comes later in the list (= earlier in the reverse walk);
+//   split     the leaf-region prefix only depends on itself (forward), nothing outside it depends on ... the prefix
+//             being run last (backward) — both follow from the two conditions above.
+int64_t sweep_order_violations(const Plan& P) {
+  const int64_t nct = (int64_t)P.solve_ctas.size();
+  std::vector<int32_t> first_cta(P.n_nodes, INT32_MAX), last_cta(P.n_nodes, -1), seen(P.n_nodes, 0);
+  std::vector<int32_t> cta_of(P.solve_tasks.size(), -1);
+  int64_t bad = 0;
+  for (int64_t c = 0; c < nct; ++c) {
+    const SolveCta& C = P.solve_ctas[c];
+    if (C.kind != 0 && C.count != 1) ++bad;
+    if (c < P.n_narrow_prefix_ctas && C.kind == 1) ++bad;          // the light kernels have no block path
+    for (int k = 0; k < C.count; ++k) {
+      const int64_t ti = (int64_t)C.first + k;
+      if (ti < 0 || ti >= (int64_t)P.solve_tasks.size() || cta_of[ti] != -1) { ++bad; continue; }
+      cta_of[ti] = (int32_t)c;
+      const int nd = P.solve_tasks[ti].node;
+      first_cta[nd] = std::min(first_cta[nd], (int32_t)c);
+      last_cta[nd] = std::max(last_cta[nd], (int32_t)c);
+    }
+  }
+  for (size_t ti = 0; ti < P.solve_tasks.size(); ++ti) {
+    const SolveTask& t = P.solve_tasks[ti];
+    if (cta_of[ti] < 0) { ++bad; continue; }
+    if (t.need != P.node_need[t.node]) ++bad;
+    int32_t prev = t.tgt_begin;
+    for (int k = 0; k < 4; ++k) { if (t.tile_tgt[k] < prev || t.tile_tgt[k] > t.tgt_end) ++bad; prev = t.tile_tgt[k]; }
+    if (t.tile_tgt[3] != t.tgt_end) ++bad;
+    for (int32_t q = t.tgt_begin; q < t.tgt_end; ++q) {
+      const int v = P.solve_targets[q];
+      if (v < 0 || v >= P.n_nodes) { ++bad; continue; }
+      ++seen[v];
+      if (!(cta_of[ti] < first_cta[v])) ++bad;     // forward: producer strictly before every task of v;
+                                                   // backward: every task of v strictly after this consumer
+    }
+  }
+  for (int v = 0; v < P.n_nodes; ++v) if (seen[v] != P.node_need[v]) ++bad;
+  return bad;
 }
 
 }  // namespace parsy

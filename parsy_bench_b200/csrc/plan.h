@@ -197,6 +197,8 @@ struct Plan {
 };
 
 // Returns 0 on success, PARSY_CUDA_ERR_* otherwise (message in plan.error).
+// Number of places where the sweep task lists violate the ordering the spinning kernels rely on (0 = deadlock-free).
+int64_t sweep_order_violations(const Plan& P);
 int build_plan(Plan& plan, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
                int supNo, const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
                const int* partition, const PlanOptions& opt);

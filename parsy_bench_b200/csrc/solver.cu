@@ -892,6 +892,9 @@ extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, con
     for (const BlockTask& b : P.block_tasks) if (b.j0 == 0) o->reserved[0]++;
     o->reserved[1] = (int64_t)P.gemm_tasks.size();
     o->reserved[4] = (int64_t)(P.class_flops[3] + P.class_flops[4] + P.class_flops[5]);   // flops of the update tasks this plan runs
+    // sweeps: reserved[5] = CTAs of one sweep, reserved[6] = of which leaf region (light kernels), reserved[7] = ordering
+    // violations of the task list (0 = the spinning kernels cannot deadlock)
+    o->reserved[5] = (int64_t)P.solve_ctas.size(); o->reserved[6] = P.n_narrow_prefix_ctas; o->reserved[7] = sweep_order_violations(P);
     for (int s2 = 0; s2 < P.nsuper; ++s2) { if (P.owner[s2] == po.rank) o->reserved[2]++; if (P.owner[s2] < 0) o->reserved[3]++; }
   }
   return PARSY_CUDA_OK;

@@ -97,3 +97,27 @@ def test_no_device_is_an_error_not_a_fallback():
     x = np.ones(G.n)
     assert ex.blockedLsolve(G.n, G.p, G.s, G.valL, 0, G.i_ptr, G.col2Sup, G.super, G.nsuper, x) == 0
     assert ex.blockedLsolve(G.n, None, G.s, G.valL, 0, G.i_ptr, G.col2Sup, G.super, G.nsuper, x) == 0  # NULL Lp
+
+
+@pytest.mark.parametrize("name", ["2d5_N30_c8_l1_d2", "2d5_N30_c64_l0_d4", "3d7_N7_c8_l1_d2", "3d27_N6_c4_l0_d2"])
+def test_sweep_task_lists_are_deadlock_free(name):
+    """The sweep kernels spin on counters, so their task lists must be topological orders (producers strictly before
+    consumers, leaf region closed under descendants): validated on the host by the planner itself
+    (plan.cpp: sweep_order_violations) and reported through parsy_cuda_plan_check."""
+    G = load_golden(name)
+    for nb in (0, 32):
+        rc, st = ex.plan_check(G.n, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.col2Sup, len(G.levelPtr) - 1, G.levelPtr,
+                               G.parPtr, G.partition, block_cols=nb)
+        assert rc == ex.OK
+        ctas, leaf, bad = st["reserved"][5], st["reserved"][6], st["reserved"][7]
+        assert bad == 0
+        assert 0 < leaf <= ctas
+
+
+def test_sweep_task_lists_on_a_larger_grid():
+    from parsy_bench_b200 import matrices
+    n, Ap, Ai, Ax = matrices.laplacian("2d5", 150)
+    S = inspector.analyze(n, Ap, Ai, Ax, 64, 1, 4)
+    rc, st = ex.plan_check(n, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.col2Sup, S.nLevels, S.levelPtr, S.parPtr, S.partition)
+    assert rc == ex.OK and st["reserved"][7] == 0
+    assert st["n_block_cols"] > 0 and 0 < st["reserved"][6] < st["reserved"][5]   # block columns exist: two launches per sweep
