@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -274,7 +274,7 @@ def sharded_arm(args, kind, N, desc, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="default: 100 (cfg1, cfg2), 20 (cfg4), 5 (cfg3), 2 (cfg5)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
@@ -291,6 +291,10 @@ def main():
     ap.add_argument("--replicate-top", action="store_true", help="N>1: every rank computes the top separators")
     ap.add_argument("--top-levels", type=int, default=1, help="N>1: LBC H-levels kept shared (computed by every rank)")
     args = ap.parse_args()
+    if args.steps is None:     # long enough a timed region for the clock sampler, short enough to end within a minute
+        args.steps = {"cfg1": 100, "cfg2": 100, "cfg4": 20, "cfg3": 5, "cfg5": 2}[args.config]
+        if args.impl == "reference":
+            args.steps = min(args.steps, 10)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     kind, N, desc = CONFIGS[args.config]
     if args.impl == "reference":
