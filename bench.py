@@ -36,6 +36,28 @@ FP64_PEAK_TFLOPS = 37.1      # tools/fp64_peak.cu on this pool's B200 (profiles/
 HBM_FALLBACK_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Everything but the final JSON line goes to stderr: libraries print banners on stdout (NCCL prints its version
+    there at communicator creation), and the contract is ONE JSON line on stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -166,7 +188,7 @@ def reference_arm(args, kind, N, desc):
             "cpu_baseline": cb, "sptrsv_ms": sptrsv,
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t_wall}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -265,7 +287,7 @@ def sharded_arm(args, kind, N, desc, rank, world, local):
             "cpu_baseline": None, "clocks": clocks, "fro2_over_trace": fro / trace, "factor_ok": bool(ok),
             "setup_s": {"inspector": t_insp, "create": t_create},
         }
-        print(json.dumps(line))
+        emit(line)
     SC.close()
     dist.destroy_process_group()
     return 0
@@ -287,10 +309,12 @@ def main():
     ap.add_argument("--ignore-hlevels", action="store_true", help="schedule by dependencies only (no LBC H-level barriers)")
     ap.add_argument("--no-fan-out", action="store_true", help="kernel classes of a step on one stream (A/B)")
     ap.add_argument("--general-sweeps", action="store_true", help="leaf region of the sweeps on the general dataflow kernel (A/B)")
-    ap.add_argument("--replicas", action="store_true", help="N>1: one full factorization per GPU instead of sharding")
+    ap.add_argument("--replicas", action="store_true", help="N>1: one full factorization per GPU (default for cfg1/cfg2/cfg4)")
+    ap.add_argument("--sharded", action="store_true", help="N>1: ONE factorization sharded over the GPUs (default for cfg3/cfg5)")
     ap.add_argument("--replicate-top", action="store_true", help="N>1: every rank computes the top separators")
     ap.add_argument("--top-levels", type=int, default=1, help="N>1: LBC H-levels kept shared (computed by every rank)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.steps is None:     # long enough a timed region for the clock sampler, short enough to end within a minute
         args.steps = {"cfg1": 100, "cfg2": 100, "cfg4": 20, "cfg3": 5, "cfg5": 2}[args.config]
         if args.impl == "reference":
@@ -313,7 +337,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    if world > 1 and not args.replicas:
+    # N > 1: a factorization that takes a few milliseconds on one GPU (cfg1/cfg2/cfg4) has nothing to gain from sharding —
+    # measured: cfg2 3.7 ms on one GPU, 4.8 ms sharded over two — so those configs run one independent
+    # factorization per GPU (weak scaling, no data-path collective); cfg3/cfg5, the configurations BASELINE.json names for
+    # multi-GPU, run ONE factorization sharded over the GPUs (strong scaling).  --sharded / --replicas override.
+    sharded = args.sharded or (args.config in ("cfg3", "cfg5") and not args.replicas)
+    if world > 1 and sharded:
         return sharded_arm(args, kind, N, desc, rank, world, local)
 
     # ---- setup (untimed): synthetic matrix, host inspector, device-resident structure -------------------------
@@ -468,8 +497,10 @@ def main():
                                "hlevels": int(S.nLevels), "wpartitions": int(S.nParts)},
                        "step": "zero L + scatter A + factor (all LBC levels) + forward sweep + backward sweep, resident",
                        "l2": f"working set {8 * S.xsize / 1e6:.0f} MB (factor) > 126 MB L2, no flush needed",
-                       "parallelism": "single GPU" if world == 1 else f"{world} replicas (one full factorization per GPU; "
-                                                                        "sharded factorization: DESIGN.md (e))"},
+                       "parallelism": "single GPU" if world == 1 else f"{world} replicas: one independent factorization + solve per GPU, "
+                                                                        "no data-path collective (sharding one factorization of "
+                                                                        "this size over GPUs is slower than one GPU: --sharded, "
+                                                                        "DESIGN.md §8)"},
             "breakdown_ms": {"factor": fac_ms, "fwd_solve": fwd_ms, "bwd_solve": bwd_ms,
                              "factor_levels": times["levels"] * 1e3, "factor_last_level": times["last_level"] * 1e3,
                              "assemble": times["assemble"] * 1e3},
@@ -488,7 +519,7 @@ def main():
             "setup_s": {"inspector": t_insp, "inspector_metis": S.t_ordering, "create": t_create},
             "device_bytes": st["device_bytes"],
         }
-        print(json.dumps(line))
+        emit(line)
     H.close()
     if world > 1:
         dist.destroy_process_group()
