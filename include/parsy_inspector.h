@@ -65,6 +65,13 @@ int parsy_ereach_sn(const parsy_symbolic* sym, int s, int* out);
  * leveledBlockedLsolve (examples/triangularTest02.cpp:218): returns the number of levels. */
 int parsy_etree_level_set(int nsuper, const int* sParent, int* levelPtr /*nsuper+1*/, int* levelSet /*nsuper*/);
 
+/* Level sets of the dependence DAG of a lower-triangular CSC matrix (diagonal first in each column) — replaces
+ * buildLevelSet_CSC (triangularSolve/Inspection_Level.h:12-59; call site examples/triangularTest_DAG.cpp:171-175), the
+ * inspector of lsolvePar for inputs that are not Cholesky factors.  levelPtr has n+1 entries (levels+1 are used),
+ * levelSet n; columns of a level are listed in increasing order, as the reference does.  Returns the number of levels,
+ * or -1 (missing diagonal, entry above the diagonal). */
+int parsy_build_level_set_csc(int n, const int* Lp, const int* Li, int* levelPtr, int* levelSet);
+
 /* BCSC -> CSC conversion of a supernodal factor (common/Util.h:311 bcsc2csc); Cp has n+1 entries; returns nnz.
  * Pass Ci = Cx = NULL to only count. */
 int64_t parsy_bcsc2csc(const parsy_symbolic* sym, const double* Lx, int* Cp, int* Ci, double* Cx);

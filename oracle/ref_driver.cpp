@@ -33,6 +33,7 @@
 #include "parallel_PB_Cholesky_05.h"
 #include "Triangular_BCSC.h"
 #include "Triangular_CSC.h"
+#include "Inspection_Level.h"
 
 static double now() {
   return std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
@@ -76,7 +77,7 @@ template <typename T> static void dump(const std::string& dir, const char* name,
 
 int main(int argc, char** argv) {
   int kind = 0, N = 100, costParam = 8, levelParam = 1, divRate = 2, threads = 1, blasThreads = -1, iters = 1;
-  int doFactor = 1, doSolve = 1, dumpL = 1, chunk = 1;
+  int doFactor = 1, doSolve = 1, dumpL = 1, chunk = 1, triOnly = 0;
   std::string dir, mtx;
   for (int a = 1; a < argc; ++a) {
     std::string s = argv[a];
@@ -94,6 +95,7 @@ int main(int argc, char** argv) {
     else if (s == "--no-solve") doSolve = 0;
     else if (s == "--no-dump-values") dumpL = 0;
     else if (s == "--mtx") mtx = nxt();
+    else if (s == "--tri-only") triOnly = 1;
     else { fprintf(stderr, "unknown arg %s\n", s.c_str()); return 2; }
   }
   if (blasThreads < 0) blasThreads = threads;
@@ -112,6 +114,23 @@ int main(int argc, char** argv) {
   gen_laplacian(kind, N, Ap, Ai, Ax);
   size_t n = Ap.size() - 1, nnzA = Ai.size();
   dump(dir, "A_p.i32", Ap.data(), n + 1); dump(dir, "A_i.i32", Ai.data(), nnzA); dump(dir, "A_x.f64", Ax.data(), nnzA);
+  if (triOnly) {
+    // The input itself is taken as a lower-triangular matrix in CSC (diagonal first): level sets of its DAG by the
+    // reference's buildLevelSet_CSC (triangularSolve/Inspection_Level.h:12) and the column solves of
+    // Triangular_CSC.h:14,50 on b_i = 1 + i/n, as examples/triangularTest_DAG.cpp:171-175 does.
+    int *lp = NULL, *ls = NULL;
+    int levels = buildLevelSet_CSC(n, nnzA, Ap.data(), Ai.data(), lp, ls);
+    dump(dir, "tri_levelPtr.i32", lp, (size_t)levels + 1); dump(dir, "tri_levelSet.i32", ls, n);
+    std::vector<double> x(n);
+    for (size_t i2 = 0; i2 < n; ++i2) x[i2] = 1.0 + (double)i2 / (double)n;
+    lsolve((int)n, Ap.data(), Ai.data(), Ax.data(), x.data());
+    dump(dir, "tri_x.f64", x.data(), n);
+    for (size_t i2 = 0; i2 < n; ++i2) x[i2] = 1.0 + (double)i2 / (double)n;
+    lsolvePar((int)n, Ap.data(), Ai.data(), Ax.data(), x.data(), levels, lp, ls, chunk);
+    dump(dir, "tri_x_par.f64", x.data(), n);
+    printf("{\"n\": %zu, \"nnz\": %zu, \"levels\": %d}\n", n, nnzA, levels);
+    return 0;
+  }
 
   int *prunePtr = NULL, *pruneSet = NULL, *levelPtr = NULL, *levelSet = NULL, *parPtr = NULL, *partition = NULL;
   int nLevels = 0, nPar = 0, status = 0, maxSupWid = 0, maxCol = 0;

@@ -415,6 +415,34 @@ template <class T> T* dup(const std::vector<T>& v) {
 
 }  // namespace
 
+// Level sets of the dependence DAG of a lower-triangular CSC matrix (diagonal first in every column), what
+// buildLevelSet_CSC (triangularSolve/Inspection_Level.h:12-59) hands to lsolvePar (examples/triangularTest_DAG.cpp:171-175).
+// The reference peels wavefronts: every round takes, in increasing index order, all columns with no unprocessed
+// off-diagonal entry in their row, then removes their edges.  A column's round is therefore 1 + the latest round among
+// the columns it depends on (longest path from a source), which is what is computed here in one pass over the columns —
+// same levelPtr / levelSet, no repeated scans of the index range.
+extern "C" int parsy_build_level_set_csc(int n, const int* Lp, const int* Li, int* levelPtr, int* levelSet) {
+  if (n < 0 || !Lp || !Li || !levelPtr || !levelSet) { g_err = "NULL argument"; return -1; }
+  std::vector<int> lev(n, 0);
+  int levels = 0;
+  for (int j = 0; j < n; ++j) {
+    if (Lp[j + 1] <= Lp[j] || Li[Lp[j]] != j) { g_err = "every column must start with its diagonal entry"; return -1; }
+    const int mine = lev[j];
+    levels = std::max(levels, mine + 1);
+    for (int p = Lp[j] + 1; p < Lp[j + 1]; ++p) {
+      const int i = Li[p];
+      if (i <= j || i >= n) { g_err = "matrix is not lower triangular"; return -1; }
+      lev[i] = std::max(lev[i], mine + 1);
+    }
+  }
+  std::fill(levelPtr, levelPtr + n + 1, 0);
+  for (int j = 0; j < n; ++j) levelPtr[lev[j] + 1]++;
+  for (int l = 0; l < levels; ++l) levelPtr[l + 1] += levelPtr[l];
+  std::vector<int> fill(levelPtr, levelPtr + levels);
+  for (int j = 0; j < n; ++j) levelSet[fill[lev[j]]++] = j;
+  return levels;
+}
+
 extern "C" const char* parsy_inspector_last_error(void) { return g_err.c_str(); }
 void parsy_inspector_set_error(const std::string& msg) { g_err = msg; }   // used by mmio.cpp
 

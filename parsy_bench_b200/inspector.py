@@ -43,6 +43,8 @@ def lib():
         L.parsy_etree_level_set.argtypes = [c_int, c_void_p, c_void_p, c_void_p]
         L.parsy_bcsc2csc.restype = c_int64
         L.parsy_bcsc2csc.argtypes = [POINTER(_Symbolic), c_void_p, c_void_p, c_void_p, c_void_p]
+        L.parsy_build_level_set_csc.restype = c_int
+        L.parsy_build_level_set_csc.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         L.parsy_read_matrix.restype = c_int
         L.parsy_read_matrix.argtypes = [ctypes.c_char_p, POINTER(c_int), POINTER(c_int64), POINTER(POINTER(c_int)),
                                         POINTER(POINTER(c_int)), POINTER(POINTER(c_double))]
@@ -175,3 +177,17 @@ def make_lower_half(in_path, out_path, tol=0.1):
     rc = L.parsy_make_lower_half(os.fsencode(in_path), os.fsencode(out_path), float(tol))
     if rc != 0:
         raise MatrixMarketError(rc, L.parsy_inspector_last_error().decode())
+
+
+def build_level_set_csc(n, Lp, Li):
+    """``buildLevelSet_CSC`` (triangularSolve/Inspection_Level.h:12): wavefront level sets of a lower-triangular CSC
+    matrix (diagonal first per column) for ``lsolvePar``.  Returns ``(levels, levelPtr[levels+1], levelSet[n])``."""
+    Lp = np.ascontiguousarray(Lp, np.int32)
+    Li = np.ascontiguousarray(Li, np.int32)
+    lp = np.zeros(int(n) + 1, np.int32)
+    ls = np.zeros(int(n), np.int32)
+    levels = lib().parsy_build_level_set_csc(int(n), Lp.ctypes.data_as(c_void_p), Li.ctypes.data_as(c_void_p),
+                                             lp.ctypes.data_as(c_void_p), ls.ctypes.data_as(c_void_p))
+    if levels < 0:
+        raise ValueError(f"parsy_build_level_set_csc: {lib().parsy_inspector_last_error().decode()}")
+    return levels, lp[:levels + 1].copy(), ls

@@ -441,3 +441,34 @@ def test_matrix_market_file_through_inspector_and_executor(tmp_path):
     A = original_matrix(n, Ap, Ai, Ax)
     assert np.linalg.norm(A @ x - b) <= 1e-12 * np.linalg.norm(b)
     H.close()
+
+
+@pytest.mark.parametrize("n,per_col,seed", [(3000, 4, 21), (500, 40, 22)])
+def test_csc_solves_of_a_general_triangular_matrix(tmp_path, n, per_col, seed):
+    """Non-chordal input (examples/triangularTest_DAG.cpp:171-175): a random lower-triangular CSC matrix that is not a
+    Cholesky factor; level sets from the restated buildLevelSet_CSC, column solves lsolve / lsolvePar on the GPU against
+    scipy's triangular solve and, where the compiled reference is present, against its own lsolve / lsolvePar."""
+    import subprocess
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import spsolve_triangular
+    import refdump
+    from test_mmio import random_lower_triangular
+    n, Lp, Li, Lx = random_lower_triangular(n, per_col, seed)
+    b = 1.0 + np.arange(n) / n
+    want = spsolve_triangular(sp.csc_matrix((Lx, Li, Lp), shape=(n, n)).tocsr(), b, lower=True)
+    x = b.copy()
+    assert ex.lsolve(n, Lp, Li, Lx, x) == 1
+    assert rel_err(x, want) < 1e-11
+    levels, lptr, lset = inspector.build_level_set_csc(n, Lp, Li)
+    assert levels > 1
+    x = b.copy()
+    assert ex.lsolvePar(n, Lp, Li, Lx, x, levels, lptr, lset, 1) == 1
+    assert rel_err(x, want) < 1e-11
+    if refdump.have_ref():
+        f = tmp_path / "tri.mtx"
+        matrices.write_mtx(f, n, Lp, Li, Lx, symmetric=False)
+        d = tmp_path / "dump"
+        d.mkdir()
+        subprocess.run([refdump.REF_BIN, "--mtx", str(f), "--tri-only", "--dump", str(d)], check=True, capture_output=True)
+        assert rel_err(x, np.fromfile(d / "tri_x.f64", np.float64)) < 1e-11
+        assert rel_err(x, np.fromfile(d / "tri_x_par.f64", np.float64)) < 1e-11

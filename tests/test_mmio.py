@@ -163,3 +163,62 @@ def test_make_lower_half_propagates_header_errors(tmp_path):
     with pytest.raises(inspector.MatrixMarketError) as e:
         inspector.make_lower_half(src, tmp_path / "o.mtx")
     assert e.value.code == 4
+
+
+# ---- level sets of a general lower-triangular CSC matrix (the inspector of lsolvePar, non-chordal inputs) --------------
+def random_lower_triangular(n, per_col, seed):
+    """Random lower-triangular pattern (diagonal first, rows ascending), well conditioned values; not a Cholesky factor:
+    its graph has no fill closure (a "non-chordal" input in the reference's terms)."""
+    rng = np.random.default_rng(seed)
+    Ap, Ai, Ax = [0], [], []
+    for j in range(n):
+        k = min(n - 1 - j, int(rng.integers(0, per_col + 1)))
+        rows = sorted(set(int(i) for i in rng.integers(j + 1, n, size=k))) if k else []
+        Ai += [j] + rows
+        Ax += [2.0 + rng.random()] + list(rng.uniform(-0.5, 0.5, size=len(rows)))
+        Ap.append(len(Ai))
+    return n, np.array(Ap, np.int32), np.array(Ai, np.int32), np.array(Ax)
+
+
+def check_level_sets(n, Lp, Li, levels, lptr, lset):
+    assert lptr[0] == 0 and lptr[-1] == n and len(lptr) == levels + 1 and sorted(lset.tolist()) == list(range(n))
+    lev = np.empty(n, np.int64)
+    for l in range(levels):
+        cols = lset[lptr[l]:lptr[l + 1]]
+        assert len(cols) > 0 and np.all(np.diff(cols) > 0)        # increasing inside a level, no empty level
+        lev[cols] = l
+    want = np.zeros(n, np.int64)
+    for j in range(n):                                             # level = 1 + latest level it depends on
+        rows = Li[Lp[j] + 1:Lp[j + 1]]
+        want[rows] = np.maximum(want[rows], want[j] + 1)
+    assert np.array_equal(lev, want)
+
+
+@pytest.mark.parametrize("n,per_col,seed", [(1, 0, 0), (50, 0, 1), (300, 2, 2), (2000, 4, 3), (500, 40, 4)])
+def test_level_sets_of_a_triangular_matrix(n, per_col, seed):
+    n, Lp, Li, _ = random_lower_triangular(n, per_col, seed)
+    levels, lptr, lset = inspector.build_level_set_csc(n, Lp, Li)
+    check_level_sets(n, Lp, Li, levels, lptr, lset)
+
+
+def test_level_sets_reject_bad_input():
+    with pytest.raises(ValueError):
+        inspector.build_level_set_csc(2, [0, 1, 2], [1, 1])         # column 0 does not start with its diagonal
+    with pytest.raises(ValueError):
+        inspector.build_level_set_csc(2, [0, 1, 3], [0, 1, 0])      # entry above the diagonal
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="compiled reference (oracle/_ref) not built")
+@pytest.mark.parametrize("n,per_col,seed", [(400, 3, 11), (1500, 6, 12), (64, 20, 13)])
+def test_level_sets_match_the_reference(tmp_path, n, per_col, seed):
+    """buildLevelSet_CSC of the reference (through oracle/_ref/parsy_ref --mtx ... --tri-only) on a triangular matrix
+    read from a Matrix-Market file: same levelPtr and levelSet, bit for bit."""
+    n, Lp, Li, Lx = random_lower_triangular(n, per_col, seed)
+    f = tmp_path / "tri.mtx"
+    matrices.write_mtx(f, n, Lp, Li, Lx, symmetric=False)
+    d = tmp_path / "dump"
+    d.mkdir()
+    subprocess.run([refdump.REF_BIN, "--mtx", str(f), "--tri-only", "--dump", str(d)], check=True, capture_output=True)
+    levels, lptr, lset = inspector.build_level_set_csc(n, Lp, Li)
+    assert np.array_equal(np.fromfile(d / "tri_levelPtr.i32", np.int32), lptr)
+    assert np.array_equal(np.fromfile(d / "tri_levelSet.i32", np.int32), lset)
