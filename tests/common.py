@@ -7,6 +7,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
 FULL_CASES = ["2d5_N12_c8_l1_d2", "2d5_N30_c8_l1_d2", "2d5_N30_c64_l0_d4", "3d7_N7_c8_l1_d2", "3d27_N6_c4_l0_d2"]
+# a matrix that is not a stencil: committed as a Matrix-Market file, golden arrays from the reference run on that file
+MTX_CASES = {"mtx_rand150_c8_l1_d2": "rand150.mtx"}
+CPU_CASES = FULL_CASES + sorted(MTX_CASES)
 INT_ARRAYS = ["Perm", "ColCount", "super", "sParent", "col2Sup", "pi", "s", "p", "i_ptr", "levelPtr", "parPtr",
               "partition", "A2_p", "A2_i", "A1_p", "A1_i"]
 
@@ -18,6 +21,8 @@ class View(dict):
 
 def parse_case(name):
     kind, N, c, l, d = name.split("_")
+    if kind == "mtx":
+        return kind, os.path.join(GOLDEN, MTX_CASES[name]), int(c[1:]), int(l[1:].replace("m", "-")), int(d[1:])
     return kind, int(N[1:]), int(c[1:]), int(l[1:].replace("m", "-")), int(d[1:])
 
 

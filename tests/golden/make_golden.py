@@ -12,9 +12,11 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from refdump import ref_case  # noqa: E402
 
 FULL = [("2d5", 12, 8, 1, 2), ("2d5", 30, 8, 1, 2), ("2d5", 30, 64, 0, 4), ("3d7", 7, 8, 1, 2), ("3d27", 6, 4, 0, 2)]
+MTX = {"mtx_rand150_c8_l1_d2": ("rand150.mtx", 8, 1, 2)}   # file written by write_rand_mtx() below
 DIGEST = [("2d5", 100, 8, 1, 2), ("2d5", 100, 592, 1, 4), ("3d7", 20, 8, 1, 2), ("3d27", 16, 8, 1, 2)]
 INT_ARRAYS = ["Perm", "ColCount", "super", "sParent", "col2Sup", "pi", "s", "p", "i_ptr", "levelPtr", "parPtr",
               "partition", "A2_p", "A2_i", "A1_p", "A1_i", "etree_levelPtr", "etree_levelSet"]
@@ -24,7 +26,22 @@ def name(c):
     return f"{c[0]}_N{c[1]}_c{c[2]}_l{c[3]}_d{c[4]}".replace("-", "m")
 
 
+def write_rand_mtx():
+    """A random-pattern, strictly diagonally dominant SPD matrix (not a stencil) as a lower-half Matrix-Market file."""
+    from test_mmio import random_spd_lower
+    from parsy_bench_b200 import matrices
+    n, Ap, Ai, Ax = random_spd_lower(150, 2, seed=5)
+    matrices.write_mtx(os.path.join(HERE, "rand150.mtx"), n, Ap, Ai, Ax, comment="random_spd_lower(150, 2, seed=5)")
+
+
 def main():
+    write_rand_mtx()
+    for nm, (f, c, l, d) in MTX.items():
+        R = ref_case("2d5", 0, cost=c, level=l, div=d, threads=1, mtx=os.path.join(HERE, f))
+        arrays = {k: v for k, v in R.items() if isinstance(v, np.ndarray)}
+        arrays["s"] = arrays["s"][:R.meta["ssize"]]
+        np.savez_compressed(os.path.join(HERE, nm + ".npz"), meta=json.dumps(R.meta), **arrays)
+        print("wrote", nm, {k: R.meta[k] for k in ("n", "nsuper", "xsize")})
     for c in FULL:
         R = ref_case(c[0], c[1], cost=c[2], level=c[3], div=c[4], threads=1)
         arrays = {k: v for k, v in R.items() if isinstance(v, np.ndarray)}

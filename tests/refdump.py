@@ -21,13 +21,16 @@ class RefCase(dict):
     __getattr__ = dict.__getitem__
 
 
-def ref_case(kind, N, cost=8, level=1, div=2, threads=1, factor=True, solve=True, iters=1, keep_values=True):
-    key = (kind, N, cost, level, div, threads, factor, solve)
+def ref_case(kind, N, cost=8, level=1, div=2, threads=1, factor=True, solve=True, iters=1, keep_values=True, mtx=None):
+    """mtx: path of a lower-half Matrix-Market file read by the reference's readMatrix instead of the synthetic grid."""
+    key = (kind, N, cost, level, div, threads, factor, solve, mtx)
     if key in _CACHE:
         return _CACHE[key]
     d = tempfile.mkdtemp(prefix="parsy_ref_")
     cmd = [REF_BIN, "--kind", kind, "--N", str(N), "--cost", str(cost), "--level", str(level), "--div", str(div),
            "--threads", str(threads), "--iters", str(iters), "--dump", d]
+    if mtx is not None:
+        cmd += ["--mtx", str(mtx)]
     if not factor:
         cmd.append("--no-factor")
     if not solve:

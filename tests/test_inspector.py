@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-from common import FULL_CASES, INT_ARRAYS, load_golden, digests, parse_case, View
+from common import CPU_CASES, FULL_CASES, INT_ARRAYS, load_golden, digests, parse_case, View
 from refdump import have_ref, ref_case
 from parsy_bench_b200 import inspector, matrices
 
@@ -16,11 +16,14 @@ import parsy_oracle as orc  # noqa: E402
 
 def run_inspector(name):
     kind, N, c, l, d = parse_case(name)
-    n, Ap, Ai, Ax = matrices.laplacian(kind, N)
+    if kind == "mtx":      # committed Matrix-Market file (N is its path): restated readMatrix, then the inspector
+        n, Ap, Ai, Ax = inspector.read_matrix(N)
+    else:
+        n, Ap, Ai, Ax = matrices.laplacian(kind, N)
     return inspector.analyze(n, Ap, Ai, Ax, c, l, d)
 
 
-@pytest.mark.parametrize("name", FULL_CASES)
+@pytest.mark.parametrize("name", CPU_CASES)
 def test_bit_exact_vs_golden(name):
     G = load_golden(name)
     S = run_inspector(name)
@@ -45,7 +48,7 @@ def test_bit_exact_vs_digest(name):
     assert S.flops == D["flops"] and S.xsize == D["xsize"] and S.nLevels == D["nLevels"] and S.nParts == D["nParts"]
 
 
-@pytest.mark.parametrize("name", FULL_CASES[:2] + FULL_CASES[3:])
+@pytest.mark.parametrize("name", FULL_CASES[:2] + FULL_CASES[3:] + CPU_CASES[len(FULL_CASES):])
 def test_ereach_sn_order(name):
     """parsy_ereach_sn returns ereach_sn's stack (common/Reach.h:112) in the reference's order."""
     S = run_inspector(name)

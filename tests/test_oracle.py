@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-from common import FULL_CASES, load_golden, rel_err, parse_case, View
+from common import CPU_CASES, FULL_CASES, load_golden, rel_err, parse_case, View
 from refdump import have_ref, ref_case
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
@@ -17,7 +17,7 @@ import parsy_oracle as orc  # noqa: E402
 TOL_FACTOR = 1e-12
 
 
-@pytest.mark.parametrize("name", FULL_CASES)
+@pytest.mark.parametrize("name", CPU_CASES)
 def test_factor_matches_reference_golden(name):
     G = load_golden(name)
     lv = orc.cholesky_left_par_05(G)
@@ -31,7 +31,7 @@ def test_factor_matches_reference_golden(name):
     assert np.array_equal(lv == 0.0, G.valL == 0.0)
 
 
-@pytest.mark.parametrize("name", FULL_CASES)
+@pytest.mark.parametrize("name", CPU_CASES)
 def test_solves_match_reference_golden(name):
     G = load_golden(name)
     b = orc.rhs_init_blocked(G, G.valL)
@@ -48,7 +48,7 @@ def test_solves_match_reference_golden(name):
     assert np.array_equal(yc, G.y_ramp_csc)                # same loop, same order: bit-exact
 
 
-@pytest.mark.parametrize("name", FULL_CASES)
+@pytest.mark.parametrize("name", CPU_CASES)
 def test_backward_sweep_residual(name):
     """The reference has no L' solve: the restated backward sweep is pinned by the residual of L L' x = b."""
     import scipy.sparse as sp
