@@ -77,7 +77,7 @@ template <typename T> static void dump(const std::string& dir, const char* name,
 
 int main(int argc, char** argv) {
   int kind = 0, N = 100, costParam = 8, levelParam = 1, divRate = 2, threads = 1, blasThreads = -1, iters = 1;
-  int doFactor = 1, doSolve = 1, dumpL = 1, chunk = 1, triOnly = 0;
+  int doFactor = 1, doSolve = 1, dumpL = 1, chunk = 1, triOnly = 0, doCsc = 1;
   std::string dir, mtx;
   for (int a = 1; a < argc; ++a) {
     std::string s = argv[a];
@@ -96,6 +96,7 @@ int main(int argc, char** argv) {
     else if (s == "--no-dump-values") dumpL = 0;
     else if (s == "--mtx") mtx = nxt();
     else if (s == "--tri-only") triOnly = 1;
+    else if (s == "--no-csc") doCsc = 0;   // skip bcsc2csc + lsolve (full-size configs: saves nnz(L) * 12 B of dump)
     else { fprintf(stderr, "unknown arg %s\n", s.c_str()); return 2; }
   }
   if (blasThreads < 0) blasThreads = threads;
@@ -258,7 +259,7 @@ int main(int argc, char** argv) {
       nnzC += w * r - w * (w - 1) / 2;
     }
     double tcsc = -1;
-    if (nnzC < (size_t)INT_MAX) {
+    if (doCsc && nnzC < (size_t)INT_MAX) {
       int* Cp = new int[n + 1]; int* Ci = new int[nnzC]; double* Cx = new double[nnzC];
       bcsc2csc(n, nsuper, L->p, L->s, L->i_ptr, sup2col, valL, Cp, Ci, Cx);
       dump(dir, "Lcsc_p.i32", Cp, n + 1);

@@ -40,6 +40,15 @@ def digests():
         return json.load(f)
 
 
+def digests_large():
+    """BASELINE.json configs 2-4 at full size (inspector arrays only; tests/golden/make_golden.py --large)."""
+    p = os.path.join(GOLDEN, "digests_large.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        return json.load(f)
+
+
 def as_view(S):
     """inspector.Symbolic -> View (plain arrays)"""
     keys = INT_ARRAYS + ["A2_x", "nsuper", "n", "xsize", "nLevels"]

@@ -18,6 +18,11 @@ from refdump import ref_case  # noqa: E402
 FULL = [("2d5", 12, 8, 1, 2), ("2d5", 30, 8, 1, 2), ("2d5", 30, 64, 0, 4), ("3d7", 7, 8, 1, 2), ("3d27", 6, 4, 0, 2)]
 MTX = {"mtx_rand150_c8_l1_d2": ("rand150.mtx", 8, 1, 2)}   # file written by write_rand_mtx() below
 DIGEST = [("2d5", 100, 8, 1, 2), ("2d5", 100, 592, 1, 4), ("3d7", 20, 8, 1, 2), ("3d27", 16, 8, 1, 2)]
+# BASELINE.json configs 2, 3 and 4 at full size: inspector only (sizes + SHA-256 of every integer array), with the
+# LBC triple bench.py hands to the GPU executor and, for cfg2 / cfg4, the reference's CPU convention as well.  These
+# are the sizes where the int-overflow / INT_MAX paths of SURVEY.md App. B.8 and B.10 bite.
+DIGEST_LARGE = [("2d5", 1000, 592, 1, 4), ("2d5", 1000, 8, 1, 2), ("3d27", 64, 592, 1, 4), ("3d27", 64, 8, 1, 2),
+                ("3d7", 100, 592, 1, 4)]
 INT_ARRAYS = ["Perm", "ColCount", "super", "sParent", "col2Sup", "pi", "s", "p", "i_ptr", "levelPtr", "parPtr",
               "partition", "A2_p", "A2_i", "A1_p", "A1_i", "etree_levelPtr", "etree_levelSet"]
 
@@ -34,7 +39,26 @@ def write_rand_mtx():
     matrices.write_mtx(os.path.join(HERE, "rand150.mtx"), n, Ap, Ai, Ax, comment="random_spd_lower(150, 2, seed=5)")
 
 
+def large_digests(path):
+    """digests_large.json: run with `python tests/golden/make_golden.py --large` (cfg3 alone is ~35 s of the reference
+    inspector and a few GB of RAM)."""
+    dig = {}
+    ints = [k for k in INT_ARRAYS if not k.startswith("etree_")]
+    for c in DIGEST_LARGE:
+        R = ref_case(c[0], c[1], cost=c[2], level=c[3], div=c[4], threads=1, factor=False, solve=False)
+        m = R.meta
+        d = {k: m[k] for k in ("n", "nnzA", "nsuper", "xsize", "ssize", "nLevels", "nParts", "maxSupWid", "maxCol", "flops")}
+        R["s"] = R["s"][:m["ssize"]]
+        d["sha256"] = {k: hashlib.sha256(np.ascontiguousarray(R[k]).tobytes()).hexdigest() for k in ints}
+        dig[name(c)] = d
+        print("digest", name(c), flush=True)
+        with open(path, "w") as f:
+            json.dump(dig, f, indent=1)
+
+
 def main():
+    if "--large" in sys.argv:
+        return large_digests(os.path.join(HERE, "digests_large.json"))
     write_rand_mtx()
     for nm, (f, c, l, d) in MTX.items():
         R = ref_case("2d5", 0, cost=c, level=l, div=d, threads=1, mtx=os.path.join(HERE, f))

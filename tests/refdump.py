@@ -21,16 +21,23 @@ class RefCase(dict):
     __getattr__ = dict.__getitem__
 
 
-def ref_case(kind, N, cost=8, level=1, div=2, threads=1, factor=True, solve=True, iters=1, keep_values=True, mtx=None):
-    """mtx: path of a lower-half Matrix-Market file read by the reference's readMatrix instead of the synthetic grid."""
-    key = (kind, N, cost, level, div, threads, factor, solve, mtx)
-    if key in _CACHE:
+def ref_case(kind, N, cost=8, level=1, div=2, threads=1, factor=True, solve=True, iters=1, keep_values=True, mtx=None,
+             blas_threads=None, csc=True, cache=True):
+    """mtx: path of a lower-half Matrix-Market file read by the reference's readMatrix instead of the synthetic grid.
+    blas_threads: BLAS threads of the LAST (sequential) H-level only (parallel_PB_Cholesky_05.h:271); the parallel levels
+    stay on `threads` OpenMP threads — 1 for goldens, because of the `top` race (:43,69,115)."""
+    key = (kind, N, cost, level, div, threads, factor, solve, mtx, blas_threads, csc)
+    if cache and key in _CACHE:
         return _CACHE[key]
     d = tempfile.mkdtemp(prefix="parsy_ref_")
     cmd = [REF_BIN, "--kind", kind, "--N", str(N), "--cost", str(cost), "--level", str(level), "--div", str(div),
            "--threads", str(threads), "--iters", str(iters), "--dump", d]
     if mtx is not None:
         cmd += ["--mtx", str(mtx)]
+    if blas_threads is not None:
+        cmd += ["--blas-threads", str(blas_threads)]
+    if not csc:
+        cmd.append("--no-csc")
     if not factor:
         cmd.append("--no-factor")
     if not solve:
@@ -44,7 +51,8 @@ def ref_case(kind, N, cost=8, level=1, div=2, threads=1, factor=True, solve=True
         case[name] = np.fromfile(os.path.join(d, f), dtype=_DT[dt])
         os.unlink(os.path.join(d, f))
     os.rmdir(d)
-    _CACHE[key] = case
+    if cache:
+        _CACHE[key] = case
     return case
 
 

@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-from common import CPU_CASES, FULL_CASES, INT_ARRAYS, load_golden, digests, parse_case, View
+from common import CPU_CASES, FULL_CASES, INT_ARRAYS, load_golden, digests, digests_large, parse_case, View
 from refdump import have_ref, ref_case
 from parsy_bench_b200 import inspector, matrices
 
@@ -46,6 +46,22 @@ def test_bit_exact_vs_digest(name):
         h = hashlib.sha256(np.ascontiguousarray(getattr(S, k)).tobytes()).hexdigest()
         assert h == D["sha256"][k], k
     assert S.flops == D["flops"] and S.xsize == D["xsize"] and S.nLevels == D["nLevels"] and S.nParts == D["nParts"]
+
+
+@pytest.mark.parametrize("name", sorted(digests_large().keys()))
+def test_bit_exact_vs_digest_full_size_configs(name):
+    """BASELINE.json configs 2, 3, 4 at full size (n = 1e6 / 1e6 / 262144): every integer array of the inspector against
+    the SHA-256 the compiled reference produced (analyze_p2, cholesky/LSparsity.h:256) — the sizes at which the
+    int/double zero counts of the relaxed amalgamation (Inspection_BlockC.h:430-469) and the int cost accumulator
+    (InspectionLevel_06.h:197) leave the small-case regime."""
+    D = digests_large()[name]
+    S = run_inspector(name)
+    assert (S.n, S.nsuper, S.xsize, S.ssize) == (D["n"], D["nsuper"], D["xsize"], D["ssize"])
+    assert (S.nLevels, S.nParts, S.maxSupWid, S.maxCol) == (D["nLevels"], D["nParts"], D["maxSupWid"], D["maxCol"])
+    assert S.flops == D["flops"]
+    for k in INT_ARRAYS:
+        h = hashlib.sha256(np.ascontiguousarray(getattr(S, k)).tobytes()).hexdigest()
+        assert h == D["sha256"][k], k
 
 
 @pytest.mark.parametrize("name", FULL_CASES[:2] + FULL_CASES[3:] + CPU_CASES[len(FULL_CASES):])
