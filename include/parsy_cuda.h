@@ -63,6 +63,12 @@ int parsy_cuda_cholesky_left_par_05(int n, int* c, int* r, double* values, size_
                                     int* parPtr, int* partition, int chunk, int threads, int super_max, int col_max,
                                     double* nodCost);
 
+/* The drop-in entry points keep the resident state of the last few structures they were called with (keyed by a hash
+ * over the content of every structure array), because the reference's drivers call them repeatedly on one structure
+ * (examples/choleskyTest01.cpp:199-222): a repeated call only moves values.  This releases that state (device memory);
+ * PARSY_CUDA_DROPIN_CACHE=0 in the environment disables the cache altogether. */
+void parsy_cuda_dropin_cache_clear(void);
+
 /* Replaces  bool cholesky_left_sn_07(...)   cholesky/PB_Cholesky.h:16-19  (serial twin driven by a prune set).
  * prunePtr/pruneSet (descendant lists per supernode) are accepted and validated against the factor
  * structure; map/contribs scratch arguments are ignored (may be NULL). Runs the same device executor with
@@ -104,19 +110,21 @@ int parsy_cuda_lsolveParH2(int n, int* Lp, int* Li, double* Lx, double* x, int l
 /* ------------------------------------------------------------------------------------------------ */
 typedef struct parsy_cuda_solver parsy_cuda_solver;
 
-/* Options; zero-initialise and override what you need. */
+/* Options: initialise with parsy_cuda_options_default() (a zero-filled struct would switch the CUDA graphs off), then
+ * override what you need; passing NULL to parsy_cuda_create means the defaults. */
 typedef struct parsy_cuda_options {
   int device;          /* CUDA device ordinal                                                     */
   int block_cols;      /* NB: block-column width wide supernodes are factored in (0 = default 128) */
   int use_graph;       /* 1 = capture the factorization / sweeps into CUDA graphs (default)        */
   int ignore_hlevels;  /* 1 = schedule by etree dependencies only, not by LBC H-level barriers     */
-  int rank;            /* multi-GPU: this process' rank ...                                        */
-  int world;           /* ... of `world` ranks (0/1 = single GPU)                                  */
-  int reserved[10];    /* [0]=1 no look-ahead stream, [1]=1 per-step sweeps, [2] phase, [3] top H-levels kept shared,
-                          [4]=1 replicate the top instead of distributing it,
+  int rank;            /* parsy_cuda_sharded_create: this process' rank ...                        */
+  int world;           /* ... of `world` ranks (parsy_cuda_create: must be 0 or 1)                 */
+  int reserved[10];    /* [0]=1 no look-ahead stream, [1]=1 per-step sweeps, [2] internal (phase), [3] top H-levels kept
+                          shared, [4]=1 replicate the top instead of distributing it,
                           [5]=1 run the leaf region of the sweeps on the general dataflow kernel too,
                           [6]=1 keep the kernel classes of a step on one stream (no fan-out over auxiliary streams) */
 } parsy_cuda_options;
+void parsy_cuda_options_default(parsy_cuda_options* opt);
 
 /* Builds the device-resident symbolic state from the inspector's arrays (all HOST pointers, copied):
  *   n, c, r           tril(P A P') pattern (values come later)
@@ -131,7 +139,9 @@ int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, const int* r
                       const parsy_cuda_options* opt);
 void parsy_cuda_destroy(parsy_cuda_solver* s);
 
-/* A values: nnz(A) doubles in the order of c/r. Host -> device. */
+/* A values: nnz(A) doubles in the order of c/r. Host -> device, asynchronous on the handle's stream: the host buffer
+ * must stay untouched until parsy_cuda_sync (or any download) returns.  The same holds for parsy_cuda_set_rhs and
+ * parsy_cuda_set_factor. */
 int parsy_cuda_set_values(parsy_cuda_solver* s, const double* values);
 /* Numeric factorization on the device: zero L, scatter A, run every H-level. Asynchronous on the solver's
  * stream; parsy_cuda_sync() or any download waits for it. */
@@ -218,45 +228,64 @@ double* parsy_cuda_device_rhs(parsy_cuda_solver* s);      /* n doubles     */
 double* parsy_cuda_device_values(parsy_cuda_solver* s);   /* nnzA doubles  */
 void* parsy_cuda_stream(parsy_cuda_solver* s);            /* cudaStream_t  */
 
-/* Multi-GPU sharding (one process per GPU).  The bottom of the tree — every LBC H-level except the
- * last options.reserved[3] (default 1) — is a forest of subtrees; they are dealt to the ranks in contiguous column order,
- * balanced by cost, and need no communication.  Each rank creates two handles on the same arrays:
- *   phase 1 (options.world = G, options.rank = r, options.reserved[2] = 1): zero + scatter A + the subtrees rank r owns
- *   phase 2 (… reserved[2] = 2): the shared top, with every update into it — run after the exchange, on every rank
- * Between the phases the host moves the owners' panels over NVLink: parsy_cuda_owned_ranges() lists, for any rank, the
- * contiguous runs of lValues it owns (broadcast them from that rank with NCCL / torch.distributed on
- * parsy_cuda_device_factor()).  parsy_cuda_adopt_factor() lets the phase-2 handle work on the phase-1 handle's buffer. */
+/* ------------------------------------------------------------------------------------------------ */
+/* 3. sharded factorization + solve over the GPUs of one node (one process per GPU)     */
+/* ------------------------------------------------------------------------------------------------ */
+/* The reference has no multi-device path; this layer follows SURVEY.md §8(e).  The bottom of the tree —
+ * every LBC H-level except the last options.reserved[3] (default 1) — is a forest of subtrees hanging off the top
+ * separators (cholesky/InspectionLevel_06.h:208-216); they are dealt to the ranks in contiguous column order, balanced
+ * by the flops their owner executes.  Per factorization:
+ *   phase 1  no communication: each rank zeroes and assembles what it owns, factors its subtrees and applies every update
+ *            they generate — also those into the top separators, accumulated in the rank's own copy of the top panels
+ *            (fan-in);
+ *   sum      one ncclAllReduce per contiguous run of top panels (traffic ~ size of the separators);
+ *   top      block columns of the top separators are owned round-robin: the owner applies the updates into its block
+ *            columns, factors them (POTRF + TRSM) and ncclBroadcasts the finished panel, step by step with a two-stream
+ *            look-ahead.
+ * All kernels and collectives of a factorization are captured into CUDA graphs at creation; NCCL (libnccl.so.2) is
+ * loaded with dlopen on first use.  Factor memory: a rank touches only its own subtrees and the top.
+ *
+ * parsy_cuda_nccl_unique_id: call on rank 0, hand the 128 bytes to every rank (MPI / torch.distributed / a file).
+ * parsy_cuda_sharded_create: arguments as parsy_cuda_create; options.rank / options.world / options.device select the
+ *   rank; options.reserved[3] = top H-levels kept shared, reserved[4] = 1 replicates the top instead of distributing it.
+ *   nccl_unique_id == NULL emulates all `world` ranks inside this process on options.device (device copies instead of
+ *   NCCL, one stream, no overlap) — used by the single-GPU parity tests.
+ * The solve keeps the same ownership: subtree sweeps on the owner, one all-reduce of the top part of the right-hand side,
+ * the top separators on every rank, one all-reduce that leaves the full solution on every rank. */
+typedef struct parsy_cuda_sharded parsy_cuda_sharded;
+int parsy_cuda_nccl_unique_id(void* out128);
+int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const int* c, const int* r, const size_t* lC, const int* lR,
+                              const size_t* Li_ptr, const int* blockSet, int supNo, const int* aTree, const int* col2Sup,
+                              int nLevels, const int* levelPtr, const int* parPtr, const int* partition,
+                              const parsy_cuda_options* opt, const void* nccl_unique_id);
+void parsy_cuda_sharded_destroy(parsy_cuda_sharded* s);
+int parsy_cuda_sharded_set_values(parsy_cuda_sharded* s, const double* values);   /* nnz(A) doubles, host, every rank */
+int parsy_cuda_sharded_factor(parsy_cuda_sharded* s);                             /* asynchronous                    */
+int parsy_cuda_sharded_sync(parsy_cuda_sharded* s);                               /* PARSY_CUDA_ERR_NOT_SPD on a bad pivot seen by this rank */
+int parsy_cuda_sharded_set_rhs(parsy_cuda_sharded* s, const double* b);           /* n doubles, host, every rank     */
+int parsy_cuda_sharded_solve(parsy_cuda_sharded* s, int which);                   /* FWD|BWD: x on every rank        */
+int parsy_cuda_sharded_get_rhs(parsy_cuda_sharded* s, double* x);
+/* writes the panels this process holds complete (its subtrees + the top separators) into the host array, reference layout */
+int parsy_cuda_sharded_get_factor(parsy_cuda_sharded* s, double* lValues);
+/* seconds of the last factorization on this rank: [0] phase 1, [1] sum of the top panels, [2] distributed top */
+int parsy_cuda_sharded_phase_times(parsy_cuda_sharded* s, double* out3);
+/* [0] kernel launches per factorization, [1]/[2] NCCL broadcasts / all-reduces per factorization, [3]/[4] their bytes,
+ * [5] HBM held on this device, [6] dependency steps of the top chain, [7] NCCL version, [8]/[9] launches per forward /
+ * backward sweep, [10] supernodes owned by this rank, [11] shared top supernodes */
+int parsy_cuda_sharded_stats(parsy_cuda_sharded* s, int64_t* out12);
+double* parsy_cuda_sharded_device_factor(parsy_cuda_sharded* s);
+double* parsy_cuda_sharded_device_rhs(parsy_cuda_sharded* s);
+void* parsy_cuda_sharded_stream(parsy_cuda_sharded* s);
+/* the phase-1 / phase-2 plan of this process' rank (emulation: of `emulated_rank`), for parsy_cuda_get_stats and
+ * parsy_cuda_owned_ranges; owned by the sharded handle */
+parsy_cuda_solver* parsy_cuda_sharded_plan(parsy_cuda_sharded* s, int emulated_rank, int phase);
+/* contiguous runs of lValues owned by `rank` (begin, end pairs in doubles); returns their number */
 int parsy_cuda_owned_ranges(parsy_cuda_solver* s, int rank, int64_t* begin_end_pairs, int max_pairs);
 /* HOST-ONLY twin (no device): plans for `world` ranks and returns the runs owned by `for_rank`; -1 on error. */
 int parsy_cuda_plan_owned_ranges(int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
                                  int supNo, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
                                  const int* partition, int world, int top_levels, int for_rank,
                                  int64_t* begin_end_pairs, int max_pairs);
-int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase);   /* checks that the handle was planned for `phase` */
-int parsy_cuda_adopt_factor(parsy_cuda_solver* s, parsy_cuda_solver* src);
-/* Distributed top (default for phase 2; options.reserved[4] = 1 replicates the top instead): the block columns of the
- * shared top separators are owned round-robin; every rank factors every top block column but applies only the updates
- * into the ones it owns, so before a step is enqueued the owners broadcast the panels that step factors:
- *   for step in 0..parsy_cuda_num_steps:  for (owner, begin, end) in parsy_cuda_step_bcasts(step): broadcast lValues[begin,end)
- *                                         parsy_cuda_factor_steps(h, step, step + 1)
- * Steps before parsy_cuda_first_top_step() have no broadcasts (they only carry updates from the bottom into the top)
- * and can be enqueued in one call. */
-int parsy_cuda_num_steps(parsy_cuda_solver* s);
-int parsy_cuda_first_top_step(parsy_cuda_solver* s);
-int parsy_cuda_step_bcasts(parsy_cuda_solver* s, int step, int64_t* owner_begin_end_triples, int max_triples);
-int parsy_cuda_factor_steps(parsy_cuda_solver* s, int step_begin, int step_end);
-/* Look-ahead form of the same loop (the bulk updates R_i run on the main stream while the side stream carries
- * broadcast -> POTRF/TRSM -> updates into the next block column):
- *   parsy_cuda_factor_steps(h, 0, first_top);
- *   for i in first_top..n:  parsy_cuda_step_begin(h, i, i == first_top);  <broadcasts on parsy_cuda_stream2(h)>;
- *                           parsy_cuda_step_run(h, i);
- *   parsy_cuda_steps_end(h); */
-int parsy_cuda_step_begin(parsy_cuda_solver* s, int step, int first);
-int parsy_cuda_step_run(parsy_cuda_solver* s, int step);
-int parsy_cuda_steps_end(parsy_cuda_solver* s);
-void* parsy_cuda_stream2(parsy_cuda_solver* s);   /* cudaStream_t of the side (high-priority) stream */
-/* dst.lValues[begin,end) = src.lValues[begin,end), device to device (emulates the exchange between ranks on one GPU). */
-int parsy_cuda_copy_range(parsy_cuda_solver* dst, parsy_cuda_solver* src, int64_t begin, int64_t end);
 
 #ifdef __cplusplus
 }

@@ -703,9 +703,11 @@ __global__ void k_build_rel(int64_t total, int npairs, const int64_t* __restrict
 }
 
 // a_pos[p]: offset in lValues of A entry p (column j, row r[p]) — the `map` of parallel_PB_Cholesky_05.h:100-112
+// skip[s] != 0: this handle does not assemble supernode s (sharded plans) — position -1
 __global__ void k_build_apos(int64_t nnz, int n, const int* __restrict__ c, const int* __restrict__ r,
                              const int* __restrict__ col2sup, const SupInfo* __restrict__ sup,
-                             const int* __restrict__ lR, int64_t* __restrict__ apos) {
+                             const int* __restrict__ lR, const unsigned char* __restrict__ skip,
+                             int64_t* __restrict__ apos) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
     int lo = 0, hi = n - 1;
     while (lo < hi) {
@@ -713,6 +715,7 @@ __global__ void k_build_apos(int64_t nnz, int n, const int* __restrict__ c, cons
       if (c[mid] <= p) lo = mid; else hi = mid - 1;
     }
     const int j = lo;
+    if (skip && skip[col2sup[j]]) { apos[p] = -1; continue; }
     const SupInfo I = sup[col2sup[j]];
     const int row = r[p];
     int pos;
@@ -724,8 +727,22 @@ __global__ void k_build_apos(int64_t nnz, int n, const int* __restrict__ c, cons
 
 __global__ void k_assemble(int64_t nnz, const int64_t* __restrict__ apos, const double* __restrict__ vals,
                            double* __restrict__ lv) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
-    lv[apos[p]] = vals[p];
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = apos[p];
+    if (q >= 0) lv[q] = vals[p];
+  }
+}
+
+// dst[i] += sum over the other buffers (single-process emulation of the ranks' all-reduce; tests only)
+__global__ void k_sum_buffers(int64_t count, double* __restrict__ dst, const double* const* __restrict__ src, int nsrc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    double a = 0.0;
+    for (int k = 0; k < nsrc; ++k) a += src[k][i];
+    dst[i] = a;
+  }
+}
+__global__ void k_zero_range(double* __restrict__ x, int b, int e) {
+  for (int i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) x[i] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------

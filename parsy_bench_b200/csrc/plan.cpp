@@ -81,6 +81,11 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         hl[s] = H; part[s] = j1; pos[s] = (int)order.size(); order.push_back(s);
       }
   if ((int)order.size() != supNo) { P.error = "schedule does not cover every supernode"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
+  // sharded plans with a distributed top: every top supernode takes the block-column path (its block columns are the
+  // units of ownership); set for both phases, so that their node numbering agrees
+  const int first_top_level = std::max(0, nLevels - std::max(1, opt.top_levels));
+  if (opt.world > 1 && opt.top_distributed)
+    for (int s = 0; s < supNo; ++s) if (hl[s] >= first_top_level) P.sup[s].flags = 0;
   // every update pair (target, descendant) must run the descendant first: an earlier H-level, or earlier in
   // the same w-partition (SURVEY.md Appendix E legality condition)
   enumerate_pairs(P.pairs, supNo, blockSet, Li_ptr, lR, col2Sup);
@@ -118,7 +123,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   // ---- ownership for the sharded factorization ----------------------------------------------------------
   P.owner.assign(supNo, opt.world > 1 ? -1 : 0);
   if (opt.world > 1) {
-    const int first_top = std::max(0, nLevels - std::max(1, opt.top_levels));
+    const int first_top = first_top_level;
     std::vector<int32_t> par(supNo, -1), root(supNo, -1);
     for (int s = 0; s < supNo; ++s) {
       const SupInfo& I = P.sup[s];
@@ -131,9 +136,19 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       const int p2 = par[s];
       root[s] = (p2 < 0 || hl[p2] >= first_top) ? s : root[p2];
     }
+    // cost of a subtree = flops its owner executes: POTRF + TRSM of its supernodes and EVERY update they push
+    // (into the subtree and, fan-in, into the top separators)
     std::vector<double> rcost(supNo, 0.0);
-    for (int s = 0; s < supNo; ++s)
-      if (root[s] >= 0) rcost[root[s]] += (double)P.sup[s].w * P.sup[s].w * P.sup[s].r;
+    for (int s = 0; s < supNo; ++s) {
+      if (root[s] < 0) continue;
+      const double w = P.sup[s].w, r = P.sup[s].r;
+      double c = w * w * w / 3.0 + w * w * (r - w);
+      for (int64_t e = src_ptr[s]; e < src_ptr[s + 1]; ++e) {
+        const double nd1 = P.pairs[e].nd1, nd3 = P.pairs[e].m - P.pairs[e].nd1;
+        c += nd1 * nd1 * w + 2.0 * nd3 * nd1 * w;
+      }
+      rcost[root[s]] += c;
+    }
     double total = 0;
     for (int s = 0; s < supNo; ++s) if (root[s] == s) { roots.push_back(s); total += rcost[s]; }
     std::vector<int32_t> rown(supNo, -1);
@@ -166,9 +181,12 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     if (opt.phase == 2) return P.owner[s] < 0;
     return true;
   };
+  // fan-in: an update runs where its SOURCE lives — bottom sources on their owner (targets: the same subtree or the
+  // top separators, accumulated locally and summed over the ranks afterwards), top sources in phase 2
   auto pair_active = [&](int src, int tgt) {
-    if (opt.phase == 1) return P.owner[src] == opt.rank && P.owner[tgt] == opt.rank;
-    if (opt.phase == 2) return P.owner[tgt] < 0;
+    (void)tgt;
+    if (opt.phase == 1) return P.owner[src] == opt.rank;
+    if (opt.phase == 2) return P.owner[src] < 0;
     return true;
   };
 
@@ -223,33 +241,51 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
 
   std::vector<int32_t> f_small(nsteps, 0), f_blk(nsteps, 0);
   int32_t slot = 0;
+  // distributed top: the block columns this rank owns come first in every step's list (the factor launches take that
+  // prefix; the sweeps and the inverse blocks need all of them), hence two passes
+  for (int pass = 0; pass < (dist_top ? 2 : 1); ++pass)
   for (int s = 0; s < supNo; ++s) {
     const SupInfo& I = P.sup[s];
     if (!sup_active(s)) continue;
     if (I.flags) {
+      if (pass) continue;
       P.small_list[o_small[step0[s]] + f_small[step0[s]]++] = s;
       P.class_flops[0] += (double)I.w * I.w * I.w / 3.0 + (double)I.w * I.w * (I.r - I.w);
       continue;
     }
     for (int b2 = 0; b2 < nblk[s]; ++b2) {
+      const bool mine = !dist_top || P.node_owner[node_first[s] + b2] == opt.rank;
+      if (dist_top && mine != (pass == 0)) continue;
       const int st = step0[s] + b2, j0 = b2 * NB, nb = std::min(NB, I.w - j0);
       Step& S = P.steps[st];
       BlockTask bt; memset(&bt, 0, sizeof(bt));
       bt.sup = s; bt.j0 = j0; bt.nb = nb; bt.slot = slot;
       P.block_tasks[o_blk[st] + f_blk[st]++] = bt;
-      P.class_flops[1] += (double)nb * nb * nb / 3.0;
       S.max_nb = std::max(S.max_nb, nb);
+      ++slot;
+      if (!mine) { P.invert_tasks.push_back(bt); continue; }
+      S.blocks_owned++;
+      P.class_flops[1] += (double)nb * nb * nb / 3.0;
       const int Mb = I.r - j0 - nb;
       if (Mb > 0) {
         Gen g; memset(&g.t, 0, sizeof(g.t));
         GemmTask& t = g.t;
-        t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = (int64_t)slot * NB_MAX * NB_MAX; t.c_off = t.a_off;
+        t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = (int64_t)bt.slot * NB_MAX * NB_MAX; t.c_off = t.a_off;
         t.rel_off = -1; t.lda = I.r; t.ldb = NB_MAX; t.ldc = I.r; t.M = Mb; t.N = nb; t.K = nb;
         t.flags = GF_OVERWRITE | GF_B_LINV;
         g.step = st; g.cls = 0; g.grp = 0;
         gen.push_back(g);
         P.class_flops[2] += (double)Mb * nb * nb;
       }
+    }
+  }
+  // trailing updates inside a supernode: block column b2's panel into the later block columns
+  for (int s = 0; s < supNo; ++s) {
+    const SupInfo& I = P.sup[s];
+    if (!sup_active(s) || I.flags) continue;
+    for (int b2 = 0; b2 < nblk[s]; ++b2) {
+      const int st = step0[s] + b2, j0 = b2 * NB, nb = std::min(NB, I.w - j0);
+      const int Mb = I.r - j0 - nb;
       const int Nt = I.w - j0 - nb;   // trailing columns of the same supernode
       if (Nt > 0 && dist_top) {
         // one task per later block column, kept only if this rank owns that block column
@@ -276,7 +312,6 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
           emit_update(u, st, 1, false);
         }
       }
-      ++slot;
     }
   }
   P.n_slots = slot; P.n_block_cols = slot;
@@ -563,6 +598,36 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
           P.solve_ctas.push_back(c);
         }
       }
+    }
+  }
+  // ---- what a factorization zeroes / assembles, what the ranks sum, which columns the sweeps solve ---------------
+  {
+    auto runs_of = [&](auto pred, std::vector<int64_t>& out) {
+      int64_t b = -1, e = -1;
+      for (int s = 0; s <= supNo; ++s) {
+        const bool in = s < supNo && pred(s);
+        if (in) {
+          const SupInfo& I = P.sup[s];
+          if (b >= 0 && I.valptr != e) { out.push_back(b); out.push_back(e); b = -1; }
+          if (b < 0) b = I.valptr;
+          e = I.valptr + (int64_t)I.w * I.r;
+        } else if (b >= 0) { out.push_back(b); out.push_back(e); b = -1; }
+      }
+    };
+    P.skip_assemble.assign(supNo, 0);
+    if (opt.world <= 1 || opt.phase == 0) { P.zero_runs = {0, P.xsize}; }
+    else {
+      // phase 1 prepares the buffer for both phases: the owned subtrees and the whole top are zeroed; A is scattered
+      // into the owned subtrees and, on rank 0 only, into the top (the sum over the ranks must count A_top once)
+      runs_of([&](int s) { return P.owner[s] == opt.rank || P.owner[s] < 0; }, P.zero_runs);
+      for (int s = 0; s < supNo; ++s) P.skip_assemble[s] = !(P.owner[s] == opt.rank || (P.owner[s] < 0 && opt.rank == 0));
+      runs_of([&](int s) { return P.owner[s] < 0; }, P.top_runs);
+    }
+    int32_t cb = -1, ce = -1;
+    for (int s = 0; s <= supNo; ++s) {
+      const bool in = s < supNo && sup_active(s);
+      if (in) { if (cb < 0) cb = P.sup[s].col0; ce = P.sup[s].col0 + P.sup[s].w; }
+      else if (cb >= 0) { P.col_runs.push_back(cb); P.col_runs.push_back(ce); cb = -1; }
     }
   }
   for (SolveTask& t : P.solve_tasks) {

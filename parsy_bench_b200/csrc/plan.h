@@ -132,6 +132,7 @@ struct Step {
   Range small_sup;   // into small_list, sorted by width; the first small_narrow have width <= SMALL_W_NARROW
   int32_t small_narrow = 0;
   Range blocks;      // into block_tasks
+  int32_t blocks_owned = 0;  // leading block tasks this rank factors itself (distributed top: the owner's; else all)
   Range trsm;        // into gemm_tasks (T128, GF_OVERWRITE|GF_B_LINV)
   int32_t trsm_tiles = 0;
   int32_t trsm_tm = 64;      // row-tile height of this step's TRSM launch (64, 32 or 16)
@@ -144,13 +145,16 @@ struct PlanOptions {
   int nb = 128;
   bool ignore_hlevels = false;
   // multi-GPU sharding: the bottom of the tree (every H-level but the last `top_levels`) is a forest
-  // of subtrees, dealt to the ranks in contiguous column order balanced by cost; the top is computed by every rank.
-  //   phase 0: everything (single GPU)   phase 1: only what `rank` owns   phase 2: the shared top + every update
-  //   into it (run after the owners' panels have been exchanged)
+  // of subtrees, dealt to the ranks in contiguous column order balanced by their flops; the top separators are shared.
+  //   phase 0: everything (single GPU)
+  //   phase 1: the subtrees `rank` owns AND every update they push into the top separators (fan-in: each rank
+  //            accumulates the contributions of its own descendants in its copy of the top panels; a sum over the
+  //            ranks then delivers A_top - sum of all bottom updates)
+  //   phase 2: the top separators and the updates between them
   int phase = 0, rank = 0, world = 1, top_levels = 1;
-  // phase 2: 1 = the top separators are distributed too (1-D block-cyclic by target block column: every rank
-  // factors every top block column, but applies only the updates into the block columns it owns; the owner broadcasts
-  // a block column's panel right before it is factored), 0 = the top is computed redundantly by every rank
+  // phase 2: 1 = the top separators are distributed (1-D block-cyclic by block column: the owner of a block column
+  // applies every update into it, factors it (POTRF + TRSM) and broadcasts the finished panel), 0 = the top is
+  // computed redundantly by every rank
   int top_distributed = 1;
 };
 
@@ -176,7 +180,14 @@ struct Plan {
   std::vector<int32_t> owner;               // per supernode: owning rank, -1 = shared top (world > 1 only)
   std::vector<int32_t> node_owner;          // per node (narrow supernode / block column) of the top: owning rank
   std::vector<int32_t> bcast_ptr;           // per step: range in bcast (phase 2, distributed top)
-  std::vector<int64_t> bcast;               // triples (owner, begin, end) in doubles: panels to broadcast before the step
+  std::vector<int64_t> bcast;               // triples (owner, begin, end) in doubles: panels the owner broadcasts once the
+                                            // step's block columns are factored
+  std::vector<BlockTask> invert_tasks;      // phase 2, distributed top: block columns factored by OTHER ranks; their inverse
+                                            // diagonal blocks (diagonal solves of the sweeps) are rebuilt locally
+  std::vector<int64_t> zero_runs;           // pairs (begin, end) in doubles: what a factorization zeroes first
+  std::vector<int64_t> top_runs;            // pairs (begin, end): panels of the shared top (summed over the ranks)
+  std::vector<int32_t> col_runs;            // pairs (begin, end): columns solved by this plan's sweeps
+  std::vector<uint8_t> skip_assemble;       // per supernode: 1 = entries of A are NOT scattered by this plan
   int32_t first_top_step = 0;
   // dataflow sweeps
   int32_t n_nodes = 0;

@@ -1,6 +1,7 @@
 // libparsy_cuda: resident solver object + C ABI (include/parsy_cuda.h).
 #include <cuda_runtime.h>
 #include <cmath>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -36,9 +37,11 @@ struct parsy_cuda_solver {
   cudaEvent_t ev_fan_fork[2] = {nullptr, nullptr}, ev_fan_join[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
   bool fan_out = true;        // reserved[6] = 1 keeps every class of a step on one stream
   int phase = 0;              // 0 single GPU, 1 owned bottom subtrees, 2 shared top (multi-GPU)
-  bool owns_lv = true;
-  int la_first = 0;
-  bool dist_top = false;      // phase 2 with block-cyclic top: stepwise API, broadcasts between steps
+  bool borrowed = false;      // streams and events belong to another handle (parsy_cuda_sharded: the phase-1 handle) ...
+  bool borrowed_buffers = false;   // ... and so do the factor / right-hand-side / info buffers (same rank)
+  int* d_sync_init = nullptr; // sharded plans, backward sweep: initial counters with solved = 1 for the nodes of other plans
+  bool dist_top = false;      // phase 2 with block-cyclic top: driven by parsy_cuda_sharded (broadcast after every step)
+  BlockTask* d_invert = nullptr;   // phase 2, distributed top: block columns factored by other ranks
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device arrays
   SupInfo* d_sup = nullptr;
@@ -96,6 +99,8 @@ template <class T> static int dev_upload(parsy_cuda_solver* s, T** p, const T* h
 static int ensure_kernel_attrs(int device) {
   // opt-in shared-memory sizes are per device (per context)
   static bool done[64] = {false};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
   if (device >= 0 && device < 64 && done[device]) return 0;
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg128::SMEM));
   CU(cudaFuncSetAttribute(k_gemm_tiles<Cfg64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg64::SMEM));
@@ -155,11 +160,11 @@ static int64_t launch_factor_phase(parsy_cuda_solver* s, const Step& S, cudaStre
   int64_t launches = 0;
   Fan fan(s, st, prof == nullptr);
   // the block columns first: POTRF -> TRSM is the latency-critical chain of the step
-  if (S.blocks.size()) {
+  if (S.blocks_owned) {
     cudaStream_t q = fan.pick();
     PROF_BEGIN(1);
     const int cols = (S.max_nb + 15) & ~15;
-    k_potrf_block<<<S.blocks.size(), POTRF_THREADS, potrf_smem_bytes(cols), q>>>(s->d_blocks + S.blocks.begin, s->d_sup,
+    k_potrf_block<<<S.blocks_owned, POTRF_THREADS, potrf_smem_bytes(cols), q>>>(s->d_blocks + S.blocks.begin, s->d_sup,
                                                                                  s->d_lv, s->d_linv, s->d_info, cols);
     PROF_END();
     ++launches;
@@ -253,10 +258,20 @@ static int64_t launch_update_group(parsy_cuda_solver* s, const UpdGroup& U, cuda
 //     R_s  = the remaining updates (targets at steps >= s+2) — red.global.add, so they commute with A_{s+1}
 //   F_{s+1} needs A_s (same stream) and R_{s-1} (event); R_s needs F_s (event).  The bulk trailing update R_s thus
 //   overlaps the latency-bound POTRF/TRSM of the next block column (look-ahead of depth one).
+static bool step_has_work(const Step& S) {
+  if (S.blocks_owned || S.small_sup.size() || S.trsm_tiles) return true;
+  for (int g = 0; g < 2; ++g)
+    if (S.upd[g].tiles128 || S.upd[g].tiles64 || S.upd[g].tiles32 || S.upd[g].small.size()) return true;
+  return false;
+}
+
 static int64_t enqueue_factor_steps(parsy_cuda_solver* s, int step_begin, int step_end, LaunchProfiler* prof = nullptr) {
   int64_t launches = 0;
   const Plan& P = s->plan;
   cudaStream_t mainst = s->stream;
+  // sharded plans: the steps of the other phase carry no work for this handle
+  while (step_begin < step_end && !step_has_work(P.steps[step_begin])) ++step_begin;
+  while (step_end > step_begin && !step_has_work(P.steps[step_end - 1])) --step_end;
   if (step_end <= step_begin) return 0;
   if (prof || !s->lookahead) {
     for (int i = step_begin; i < step_end; ++i) {
@@ -285,6 +300,16 @@ static int64_t enqueue_factor_steps(parsy_cuda_solver* s, int step_begin, int st
   return launches;
 }
 
+// forward sweep epilogue: the solved unknowns replace the right-hand side (sharded plans: only this plan's columns —
+// the others still carry partial sums another sweep or another rank completes)
+static void copy_solution_back(parsy_cuda_solver* s, cudaStream_t st) {
+  const Plan& P = s->plan;
+  if (s->phase == 0) { cudaMemcpyAsync(s->d_rhs, s->d_xs, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToDevice, st); return; }
+  for (size_t k = 0; k + 1 < P.col_runs.size(); k += 2)
+    cudaMemcpyAsync(s->d_rhs + P.col_runs[k], s->d_xs + P.col_runs[k], sizeof(double) * (size_t)(P.col_runs[k + 1] - P.col_runs[k]),
+                    cudaMemcpyDeviceToDevice, st);
+}
+
 static int64_t enqueue_fwd(parsy_cuda_solver* s) {
   int64_t launches = 0;
   const Plan& P = s->plan;
@@ -307,7 +332,7 @@ static int64_t enqueue_fwd(parsy_cuda_solver* s) {
                                                                          s->d_linv, s->d_rhs, s->d_xs, s->d_sweep_trace);
       ++launches;
     }
-    cudaMemcpyAsync(s->d_rhs, s->d_xs, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToDevice, st);
+    copy_solution_back(s, st);
     return launches;
   }
   for (size_t i = 0; i < P.steps.size(); ++i) {
@@ -323,7 +348,7 @@ static int64_t enqueue_fwd(parsy_cuda_solver* s) {
       ++launches;
     }
   }
-  cudaMemcpyAsync(s->d_rhs, s->d_xs, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToDevice, st);
+  copy_solution_back(s, st);
   return launches;
 }
 
@@ -333,7 +358,10 @@ static int64_t enqueue_bwd(parsy_cuda_solver* s) {
   cudaStream_t st = s->stream;
   if (s->dataflow) {
     if (P.solve_ctas.empty()) return 0;
-    cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 2), st);
+    // sharded plans: rows of this plan's supernodes also belong to nodes solved by another plan (the top separators,
+    // done before the owned subtrees start) — their "solved" flags start at 1
+    if (s->d_sync_init) cudaMemcpyAsync(s->d_sync, s->d_sync_init, sizeof(int) * ((size_t)2 * P.n_nodes + 2), cudaMemcpyDeviceToDevice, st);
+    else cudaMemsetAsync(s->d_sync, 0, sizeof(int) * ((size_t)2 * P.n_nodes + 2), st);
     const int total = (int)P.solve_ctas.size(), npre = s->narrow_sweeps ? P.n_narrow_prefix_ctas : 0;
     int* ticket2 = s->d_sync + 1 + 2 * (size_t)P.n_nodes;
     if (total > npre) {
@@ -396,11 +424,12 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
   if (s->g_last) cudaGraphExecDestroy(s->g_last);
   if (s->g_fwd) cudaGraphExecDestroy(s->g_fwd);
   if (s->g_bwd) cudaGraphExecDestroy(s->g_bwd);
-  if (!s->owns_lv) s->d_lv = nullptr;   // adopted from another handle (parsy_cuda_adopt_factor)
+  if (s->borrowed_buffers) { s->d_lv = nullptr; s->d_rhs = nullptr; s->d_xs = nullptr; s->d_info = nullptr; }
   void* ptrs[] = {s->d_sup, s->d_lR, s->d_small_list, s->d_blocks, s->d_gemm, s->d_small_tasks, s->d_rel, s->d_apos,
                   s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info, s->d_stasks, s->d_sctas, s->d_stargets,
-                  s->d_need, s->d_ntiles, s->d_sync, s->d_Ac, s->d_Ar, s->d_perm, s->d_sys, s->d_norms};
+                  s->d_need, s->d_ntiles, s->d_sync, s->d_Ac, s->d_Ar, s->d_perm, s->d_sys, s->d_norms, s->d_invert, s->d_sync_init};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (s->borrowed) { delete s; return; }
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {s->ev_fork, s->ev_join, s->ev_F[0], s->ev_F[1], s->ev_R[0], s->ev_R[1]}) if (e) cudaEventDestroy(e);
   for (int set = 0; set < 2; ++set) {
@@ -415,16 +444,23 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
   delete s;
 }
 
-extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, const int* r, const size_t* lC,
-                                 const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo, const int* aTree,
-                                 const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
-                                 const int* partition, const parsy_cuda_options* opt) {
+extern "C" void parsy_cuda_options_default(parsy_cuda_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->use_graph = 1;
+}
+
+// parent != NULL: a second plan of the same rank (parsy_cuda_sharded: phase 2 next to phase 1) that works on the
+// parent's factor / right-hand-side buffers, streams and events instead of creating its own
+static int create_impl(parsy_cuda_solver** out, int n, const int* c, const int* r, const size_t* lC, const int* lR,
+                       const size_t* Li_ptr, const int* blockSet, int supNo, const int* aTree, const int* col2Sup,
+                       int nLevels, const int* levelPtr, const int* parPtr, const int* partition,
+                       const parsy_cuda_options* opt, parsy_cuda_solver* parent, bool share_buffers) {
   if (!out) return fail(PARSY_CUDA_ERR_BAD_ARG, "out is NULL");
   *out = nullptr;
   if (parsy_cuda_device_count() <= 0) return fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
   parsy_cuda_options o;
-  memset(&o, 0, sizeof(o));
-  o.use_graph = 1;
+  parsy_cuda_options_default(&o);
   if (opt) o = *opt;
   if (o.device < 0 || o.device >= parsy_cuda_device_count()) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad device ordinal");
   CU(cudaSetDevice(o.device));
@@ -457,6 +493,15 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
   Plan& P = s->plan;
 #define TRY(x) do { rc = (x); if (rc) { parsy_cuda_destroy(s); return rc; } } while (0)
 #define TRYCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { parsy_cuda_destroy(s); return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  if (parent) {
+    s->borrowed = true;
+    s->stream = parent->stream; s->stream2 = parent->stream2;
+    s->ev_fork = parent->ev_fork; s->ev_join = parent->ev_join;
+    for (int k = 0; k < 2; ++k) { s->ev_F[k] = parent->ev_F[k]; s->ev_R[k] = parent->ev_R[k]; s->ev_fan_fork[k] = parent->ev_fan_fork[k]; }
+    for (int set = 0; set < 2; ++set)
+      for (int k = 0; k < 4; ++k) { s->aux[set][k] = parent->aux[set][k]; s->ev_fan_join[set][k] = parent->ev_fan_join[set][k]; }
+    for (int k = 0; k < 4; ++k) s->ev[k] = parent->ev[k];
+  } else {
   TRYCU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   {
     // the latency-critical chain (POTRF/TRSM of the next block column) must win SM slots against the bulk update
@@ -477,29 +522,44 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
       }
     }
   }
+  for (auto& e : s->ev) TRYCU(cudaEventCreate(&e));
+  }
   s->fan_out = o.reserved[6] == 0;
   s->lookahead = o.reserved[0] == 0;   // reserved[0] = 1 disables the two-stream look-ahead
-  for (auto& e : s->ev) TRYCU(cudaEventCreate(&e));
   TRY(dev_upload(s, &s->d_sup, P.sup.data(), P.sup.size()));
   TRY(dev_upload(s, &s->d_lR, lR, (size_t)P.ssize));
   TRY(dev_upload(s, &s->d_small_list, P.small_list.data(), P.small_list.size()));
   TRY(dev_upload(s, &s->d_blocks, P.block_tasks.data(), P.block_tasks.size()));
   TRY(dev_upload(s, &s->d_gemm, P.gemm_tasks.data(), P.gemm_tasks.size()));
   TRY(dev_upload(s, &s->d_small_tasks, P.small_tasks.data(), P.small_tasks.size()));
-  TRY(dev_alloc(s, &s->d_lv, (size_t)P.xsize));
+  if (parent && share_buffers) {
+    if (parent->plan.xsize != P.xsize || parent->plan.n != P.n) { parsy_cuda_destroy(s); return fail(PARSY_CUDA_ERR_BAD_ARG, "parent handle has another structure"); }
+    s->borrowed_buffers = true;
+    s->d_lv = parent->d_lv; s->d_rhs = parent->d_rhs; s->d_xs = parent->d_xs; s->d_info = parent->d_info;
+  } else {
+    TRY(dev_alloc(s, &s->d_lv, (size_t)P.xsize));
+    TRY(dev_alloc(s, &s->d_rhs, (size_t)n));
+    TRY(dev_alloc(s, &s->d_xs, (size_t)n));
+    TRY(dev_alloc(s, &s->d_info, 1));
+    TRYCU(cudaMemset(s->d_info, 0, sizeof(int)));
+  }
   TRY(dev_alloc(s, &s->d_linv, (size_t)P.n_slots * NB_MAX * NB_MAX));
-  TRY(dev_alloc(s, &s->d_rhs, (size_t)n));
-  TRY(dev_alloc(s, &s->d_xs, (size_t)n));
-  TRY(dev_alloc(s, &s->d_info, 1));
+  TRY(dev_upload(s, &s->d_invert, P.invert_tasks.data(), P.invert_tasks.size()));
   TRY(dev_upload(s, &s->d_stasks, P.solve_tasks.data(), P.solve_tasks.size()));
   TRY(dev_upload(s, &s->d_sctas, P.solve_ctas.data(), P.solve_ctas.size()));
   TRY(dev_upload(s, &s->d_stargets, P.solve_targets.data(), P.solve_targets.size()));
   TRY(dev_upload(s, &s->d_need, P.node_need.data(), P.node_need.size()));
   TRY(dev_upload(s, &s->d_ntiles, P.node_tiles.data(), P.node_tiles.size()));
   TRY(dev_alloc(s, &s->d_sync, (size_t)2 * P.n_nodes + 2));
-  s->dataflow = o.reserved[1] == 0;   // reserved[1] = 1: one launch per dependency step instead
+  if (s->phase != 0) {
+    std::vector<int> init((size_t)2 * P.n_nodes + 2, 0);
+    std::vector<char> mine((size_t)P.n_nodes, 0);
+    for (const SolveTask& t : P.solve_tasks) mine[t.node] = 1;
+    for (int v = 0; v < P.n_nodes; ++v) if (!mine[v]) init[1 + (size_t)P.n_nodes + v] = 1;
+    TRY(dev_upload(s, &s->d_sync_init, init.data(), init.size()));
+  }
+  s->dataflow = o.reserved[1] == 0 || s->phase != 0;   // reserved[1] = 1: one launch per dependency step instead
   s->narrow_sweeps = o.reserved[5] == 0;
-  TRYCU(cudaMemset(s->d_info, 0, sizeof(int)));
   TRYCU(cudaMemset(s->d_linv, 0, std::max<size_t>((size_t)P.n_slots * NB_MAX * NB_MAX, 1) * 8));
   // the blocking uploads above ran on the legacy stream; the solver's stream is non-blocking, so order them explicitly
   TRYCU(cudaDeviceSynchronize());
@@ -529,9 +589,14 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
     const int64_t nnz = c[n];
     P.nnzA = nnz;
     int *d_c = nullptr, *d_r = nullptr, *d_c2s = nullptr;
+    unsigned char* d_skip = nullptr;
     TRY(dev_alloc(s, &s->d_Ac, (size_t)(n + 1))); TRY(dev_alloc(s, &s->d_Ar, (size_t)nnz));   // kept: residual of A x = b
     d_c = s->d_Ac; d_r = s->d_Ar;
     TRYCU(cudaMalloc(&d_c2s, std::max<size_t>(n, 1) * 4));
+    if (s->phase == 1) {
+      TRYCU(cudaMalloc(&d_skip, std::max<size_t>(P.skip_assemble.size(), 1)));
+      TRYCU(cudaMemcpy(d_skip, P.skip_assemble.data(), P.skip_assemble.size(), cudaMemcpyHostToDevice));
+    }
     TRYCU(cudaMemcpy(d_c, c, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
     TRYCU(cudaMemcpy(d_r, r, (size_t)nnz * 4, cudaMemcpyHostToDevice));
     TRYCU(cudaMemcpy(d_c2s, col2Sup, (size_t)n * 4, cudaMemcpyHostToDevice));
@@ -540,21 +605,20 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
     TRYCU(cudaDeviceSynchronize());
     if (nnz > 0) {
       const int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 32);
-      k_build_apos<<<grid, 256, 0, s->stream>>>(nnz, n, d_c, d_r, d_c2s, s->d_sup, s->d_lR, s->d_apos);
+      k_build_apos<<<grid, 256, 0, s->stream>>>(nnz, n, d_c, d_r, d_c2s, s->d_sup, s->d_lR, d_skip, s->d_apos);
     }
     TRYCU(cudaStreamSynchronize(s->stream));
     cudaFree(d_c2s);
+    if (d_skip) cudaFree(d_skip);
     s->has_A = true;
   }
   // CUDA graphs: all H-levels but the last / the last H-level / forward sweep / backward sweep
   const int nst = (int)P.steps.size();
   const int last_begin = P.nlevels > 0 ? P.hlevel_first_step[P.nlevels - 1] : 0;
-  if (s->use_graph) {
+  if (s->use_graph && s->phase == 0) {
     int64_t l0 = 0, l1 = 0;
-    if (!s->dist_top) {
-      TRY(capture(s, &s->g_levels, &l0, [&] { return enqueue_factor_steps(s, 0, last_begin); }));
-      TRY(capture(s, &s->g_last, &l1, [&] { return enqueue_factor_steps(s, last_begin, nst); }));
-    }
+    TRY(capture(s, &s->g_levels, &l0, [&] { return enqueue_factor_steps(s, 0, last_begin); }));
+    TRY(capture(s, &s->g_last, &l1, [&] { return enqueue_factor_steps(s, last_begin, nst); }));
     s->launches_factor = l0 + l1 + (s->has_A ? 1 : 0);
     TRY(capture(s, &s->g_fwd, &s->launches_fwd, [&] { return enqueue_fwd(s); }));
     TRY(capture(s, &s->g_bwd, &s->launches_bwd, [&] { return enqueue_bwd(s); }));
@@ -566,6 +630,16 @@ extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, c
 #undef TRYCU
 }
 
+extern "C" int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, const int* r, const size_t* lC,
+                                 const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo, const int* aTree,
+                                 const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                                 const int* partition, const parsy_cuda_options* opt) {
+  if (opt && opt->world > 1)
+    return fail(PARSY_CUDA_ERR_BAD_ARG, "world > 1: sharded factorizations are created with parsy_cuda_sharded_create");
+  return create_impl(out, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
+                     opt, nullptr, false);
+}
+
 extern "C" int parsy_cuda_set_values(parsy_cuda_solver* s, const double* values) {
   if (!s || !values) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
   if (!s->has_A) return fail(PARSY_CUDA_ERR_STATE, "handle was created without the pattern of A");
@@ -575,21 +649,28 @@ extern "C" int parsy_cuda_set_values(parsy_cuda_solver* s, const double* values)
   return PARSY_CUDA_OK;
 }
 
+// zero L (the reference's caller zeroes valL, choleskyTest01.cpp:202) and scatter A's values into it; sharded plans
+// touch only what this rank owns plus the shared top (Plan::zero_runs, Plan::skip_assemble)
+static void enqueue_assemble(parsy_cuda_solver* s, cudaStream_t st) {
+  const Plan& P = s->plan;
+  cudaMemsetAsync(s->d_info, 0, sizeof(int), st);
+  for (size_t k = 0; k + 1 < P.zero_runs.size(); k += 2)
+    cudaMemsetAsync(s->d_lv + P.zero_runs[k], 0, sizeof(double) * (size_t)(P.zero_runs[k + 1] - P.zero_runs[k]), st);
+  if (P.nnzA > 0) {
+    const int grid = (int)std::min<int64_t>((P.nnzA + 255) / 256, 148 * 16);
+    k_assemble<<<grid, 256, 0, st>>>(P.nnzA, s->d_apos, s->d_vals, s->d_lv);
+  }
+}
+
 extern "C" int parsy_cuda_factor(parsy_cuda_solver* s) {
   if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
-  if (s->phase != 2 && (!s->has_A || !s->has_values)) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
-  if (s->dist_top) return fail(PARSY_CUDA_ERR_STATE, "distributed top: drive it with parsy_cuda_factor_steps and the per-step broadcasts");
+  if (s->phase != 0) return fail(PARSY_CUDA_ERR_STATE, "sharded plan: use parsy_cuda_sharded_factor");
+  if (!s->has_A || !s->has_values) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
   CU(cudaSetDevice(s->device));
   const Plan& P = s->plan;
   cudaStream_t st = s->stream;
   CU(cudaEventRecord(s->ev[0], st));
-  CU(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
-  // phase 2 continues on the factor phase 1 (and the exchange) left in place
-  if (s->phase != 2) CU(cudaMemsetAsync(s->d_lv, 0, sizeof(double) * (size_t)P.xsize, st));   // the reference's caller zeroes valL
-  if (s->phase != 2 && P.nnzA > 0) {
-    const int grid = (int)std::min<int64_t>((P.nnzA + 255) / 256, 148 * 16);
-    k_assemble<<<grid, 256, 0, st>>>(P.nnzA, s->d_apos, s->d_vals, s->d_lv);
-  }
+  enqueue_assemble(s, st);
   CU(cudaEventRecord(s->ev[1], st));
   const int nst = (int)P.steps.size();
   const int last_begin = P.nlevels > 0 ? P.hlevel_first_step[P.nlevels - 1] : 0;
@@ -614,16 +695,12 @@ extern "C" int parsy_cuda_factor(parsy_cuda_solver* s) {
 // class_ms[6] / class_launches[6] / class_flops[6]: 0 factor_small, 1 potrf_block, 2 trsm tiles (DMMA), 3 update
 // tiles 128 (DMMA), 4 update tiles 64 (DMMA), 5 update_small.
 static int factor_profiled_impl(parsy_cuda_solver* s, LaunchProfiler& prof, std::vector<float>& ms) {
-  if (s->phase != 2 && (!s->has_A || !s->has_values)) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
+  if (s->phase != 0) return fail(PARSY_CUDA_ERR_STATE, "sharded plan: profile the ranks through parsy_cuda_sharded_factor's phase times");
+  if (!s->has_A || !s->has_values) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
   CU(cudaSetDevice(s->device));
   const Plan& P = s->plan;
   cudaStream_t st = s->stream;
-  CU(cudaMemsetAsync(s->d_info, 0, sizeof(int), st));
-  if (s->phase != 2) CU(cudaMemsetAsync(s->d_lv, 0, sizeof(double) * (size_t)P.xsize, st));
-  if (s->phase != 2 && P.nnzA > 0) {
-    const int grid = (int)std::min<int64_t>((P.nnzA + 255) / 256, 148 * 16);
-    k_assemble<<<grid, 256, 0, st>>>(P.nnzA, s->d_apos, s->d_vals, s->d_lv);
-  }
+  enqueue_assemble(s, st);
   prof.st = st;
   enqueue_factor_steps(s, 0, (int)P.steps.size(), &prof);
   CU(cudaStreamSynchronize(st));
@@ -709,6 +786,7 @@ extern "C" int parsy_cuda_get_rhs(parsy_cuda_solver* s, double* x) {
 
 extern "C" int parsy_cuda_solve(parsy_cuda_solver* s, int which) {
   if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  if (s->phase != 0) return fail(PARSY_CUDA_ERR_STATE, "sharded plan: use parsy_cuda_sharded_solve");
   if (!s->factored) return fail(PARSY_CUDA_ERR_STATE, "solve before factor / set_factor");
   if (!(which & (PARSY_CUDA_SOLVE_FWD | PARSY_CUDA_SOLVE_BWD))) return fail(PARSY_CUDA_ERR_BAD_ARG, "which must be FWD, BWD or both");
   CU(cudaSetDevice(s->device));
@@ -754,6 +832,7 @@ extern "C" int parsy_cuda_solve_system(parsy_cuda_solver* s, const double* b, do
   if (!s || !b || !x) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
   const int n = s->plan.n;
   if (nrhs < 0 || refine_steps < 0 || (nrhs > 1 && ld < n)) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad nrhs / ld / refine_steps");
+  if (s->phase != 0) return fail(PARSY_CUDA_ERR_STATE, "sharded plan: use parsy_cuda_sharded_solve");
   if (!s->factored) return fail(PARSY_CUDA_ERR_STATE, "solve before factor / set_factor");
   const bool need_res = refine_steps > 0 || rel_residual != nullptr;
   if (need_res && (!s->has_A || !s->has_values)) return fail(PARSY_CUDA_ERR_STATE, "the residual needs A: create the handle with c, r and call set_values");
@@ -906,6 +985,122 @@ extern "C" double* parsy_cuda_device_values(parsy_cuda_solver* s) { return s ? s
 extern "C" void* parsy_cuda_stream(parsy_cuda_solver* s) { return s ? (void*)s->stream : nullptr; }
 
 // ---- C ABI: drop-in entry points ------------------------------------------------------------------------
+// The reference's drivers call the executor repeatedly on one structure (five factorizations per matrix,
+// examples/choleskyTest01.cpp:199-222; the solves of triangularTest02.cpp:160-266 on one factor), and every call hands
+// over the whole structure again.  Planning it and building the device-side lists costs far more than the numeric
+// work, so the drop-in entry points keep the last few handles alive, keyed by a 64-bit hash over the CONTENT of every
+// structure array (pointer identity is not trusted): a repeated call re-uses the resident plan and only moves values.
+// PARSY_CUDA_DROPIN_CACHE=0 in the environment (or parsy_cuda_dropin_cache_clear) restores "nothing survives the call".
+#include <mutex>
+namespace {
+struct Hasher {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  void word(uint64_t v) { h = (h ^ v) * 0xFF51AFD7ED558CCDull; h ^= h >> 32; }
+  void bytes(const void* p, size_t nbytes) {
+    word(nbytes);
+    if (!p) { word(0x6E756C6C); return; }
+    const unsigned char* q = (const unsigned char*)p;
+    size_t i = 0;
+    uint64_t a = h, b = ~h;   // two independent lanes, merged at the end
+    for (; i + 16 <= nbytes; i += 16) {
+      uint64_t x, y;
+      memcpy(&x, q + i, 8); memcpy(&y, q + i + 8, 8);
+      a = (a ^ x) * 0xFF51AFD7ED558CCDull; a ^= a >> 29;
+      b = (b ^ y) * 0xC4CEB9FE1A85EC53ull; b ^= b >> 31;
+    }
+    uint64_t tail = 0;
+    if (i < nbytes) memcpy(&tail, q + i, std::min<size_t>(8, nbytes - i));
+    word(a); word(b); word(tail);
+    if (i + 8 < nbytes) { tail = 0; memcpy(&tail, q + i + 8, nbytes - i - 8); word(tail); }
+  }
+  template <class T> void arr(const T* p, size_t count) { bytes(p, p ? count * sizeof(T) : 0); }
+};
+struct CacheEntry { uint64_t key = 0; parsy_cuda_solver* h = nullptr; uint64_t stamp = 0; };
+constexpr int DROPIN_CACHE_SLOTS = 4;
+CacheEntry g_cache[DROPIN_CACHE_SLOTS];
+uint64_t g_cache_clock = 0;
+std::mutex g_cache_mu;
+bool dropin_cache_enabled() {
+  const char* e = getenv("PARSY_CUDA_DROPIN_CACHE");
+  return !(e && e[0] == '0');
+}
+uint64_t structure_key(int kind, int n, const int* c, const int* r, const size_t* lC, const int* lR, const size_t* Li_ptr,
+                       const int* blockSet, int supNo, const int* col2Sup, int nLevels, const int* levelPtr,
+                       const int* parPtr, const int* partition) {
+  Hasher H;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  H.word((uint64_t)kind); H.word((uint64_t)n); H.word((uint64_t)supNo); H.word((uint64_t)nLevels); H.word((uint64_t)dev);
+  const size_t ssize = (Li_ptr && n >= 0) ? Li_ptr[n] : 0;
+  H.arr(c, c ? (size_t)n + 1 : 0); H.arr(r, (c && r) ? (size_t)c[n] : 0);
+  H.arr(lC, (size_t)n + 1); H.arr(lR, ssize); H.arr(Li_ptr, (size_t)n + 1);
+  H.arr(blockSet, (size_t)supNo + 1); H.arr(col2Sup, (size_t)n);
+  const size_t nparts = (levelPtr && nLevels >= 0) ? (size_t)levelPtr[nLevels] : 0;
+  H.arr(levelPtr, levelPtr ? (size_t)nLevels + 1 : 0); H.arr(parPtr, parPtr ? nparts + 1 : 0);
+  H.arr(partition, (parPtr && partition) ? (size_t)parPtr[nparts] : 0);
+  return H.h ? H.h : 1;
+}
+// takes the handle out of the cache (the caller owns it until cache_put / destroy)
+parsy_cuda_solver* cache_take(uint64_t key) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (CacheEntry& e : g_cache)
+    if (e.h && e.key == key) { parsy_cuda_solver* h = e.h; e.h = nullptr; return h; }
+  return nullptr;
+}
+void cache_put(uint64_t key, parsy_cuda_solver* h) {
+  parsy_cuda_solver* evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CacheEntry* slot = &g_cache[0];
+    for (CacheEntry& e : g_cache) { if (!e.h) { slot = &e; break; } if (e.stamp < slot->stamp) slot = &e; }
+    evict = slot->h;
+    slot->h = h; slot->key = key; slot->stamp = ++g_cache_clock;
+  }
+  if (evict) parsy_cuda_destroy(evict);
+}
+// Device -> pageable host through two pinned staging buffers: the copy of chunk k+1 over PCIe overlaps the host-side
+// memcpy of chunk k into the caller's array (a plain cudaMemcpy into pageable memory serialises the two)
+int download_chunked(parsy_cuda_solver* s, double* dst, const double* d_src, size_t count) {
+  constexpr size_t CH = (size_t)4 << 20;   // doubles per chunk (32 MiB)
+  if (count <= CH) {
+    CU(cudaMemcpyAsync(dst, d_src, count * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+  }
+  double* stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  int rc = 0;
+  for (int k = 0; k < 2 && !rc; ++k) {
+    if (cudaMallocHost((void**)&stage[k], CH * 8) != cudaSuccess || cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(PARSY_CUDA_ERR_CUDA, "pinned staging buffer");
+  }
+  const size_t nch = (count + CH - 1) / CH;
+  for (size_t k = 0; k <= nch && !rc; ++k) {
+    if (k < nch) {
+      const size_t off = k * CH, len = std::min(CH, count - off);
+      if (cudaMemcpyAsync(stage[k & 1], d_src + off, len * 8, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+          cudaEventRecord(done[k & 1], s->stream) != cudaSuccess) rc = fail(PARSY_CUDA_ERR_CUDA, "chunked download");
+    }
+    if (k > 0 && !rc) {
+      const size_t off = (k - 1) * CH, len = std::min(CH, count - off);
+      if (cudaEventSynchronize(done[(k - 1) & 1]) != cudaSuccess) rc = fail(PARSY_CUDA_ERR_CUDA, "chunked download");
+      else memcpy(dst + off, stage[(k - 1) & 1], len * 8);
+    }
+  }
+  for (int k = 0; k < 2; ++k) { if (stage[k]) cudaFreeHost(stage[k]); if (done[k]) cudaEventDestroy(done[k]); }
+  return rc;
+}
+}  // namespace
+
+extern "C" void parsy_cuda_dropin_cache_clear(void) {
+  parsy_cuda_solver* hs[DROPIN_CACHE_SLOTS];
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (int k = 0; k < DROPIN_CACHE_SLOTS; ++k) { hs[k] = g_cache[k].h; g_cache[k] = CacheEntry(); }
+  }
+  for (parsy_cuda_solver* h : hs) if (h) parsy_cuda_destroy(h);
+}
+
 extern "C" int parsy_cuda_cholesky_left_par_05(int n, int* c, int* r, double* values, size_t* lC, int* lR,
                                                size_t* Li_ptr, double* lValues, int* blockSet, int supNo,
                                                double* timing, int* aTree, int* cT, int* rT, int* col2Sup, int nLevels,
@@ -913,20 +1108,30 @@ extern "C" int parsy_cuda_cholesky_left_par_05(int n, int* c, int* r, double* va
                                                int chunk, int threads, int super_max, int col_max, double* nodCost) {
   (void)cT; (void)rT; (void)levelSet; (void)nPar; (void)chunk; (void)threads; (void)super_max; (void)col_max; (void)nodCost;
   if (!c || !r || !values || !lValues) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  if (!lC || !lR || !Li_ptr || !blockSet || !col2Sup || n < 0 || supNo < 0) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  if (parsy_cuda_device_count() <= 0) { fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)"); return 0; }
+  const bool cache = dropin_cache_enabled();
+  uint64_t key = 0;
   parsy_cuda_solver* s = nullptr;
-  int rc = parsy_cuda_create(&s, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr,
-                             partition, nullptr);
+  if (cache) {
+    key = structure_key(1, n, c, r, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition);
+    s = cache_take(key);
+  }
+  int rc = 0;
+  if (!s) rc = parsy_cuda_create(&s, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr,
+                                 partition, nullptr);
   if (rc) return 0;
   rc = parsy_cuda_set_values(s, values);
   if (!rc) rc = parsy_cuda_factor(s);
   if (!rc) rc = parsy_cuda_sync(s);
-  if (!rc) rc = parsy_cuda_get_factor(s, lValues);
+  if (!rc) rc = download_chunked(s, lValues, s->d_lv, (size_t)s->plan.xsize);
   if (!rc && timing) {
     double t[3];
     if (!parsy_cuda_factor_times(s, t)) { timing[0] = t[0] + t[2]; timing[1] = t[1]; }
   }
   const std::string keep = g_err;
-  parsy_cuda_destroy(s);
+  if (cache && (rc == PARSY_CUDA_OK || rc == PARSY_CUDA_ERR_NOT_SPD)) cache_put(key, s);
+  else parsy_cuda_destroy(s);
   g_err = keep;
   return rc == PARSY_CUDA_OK ? 1 : 0;
 }
@@ -957,16 +1162,25 @@ static int dropin_solve(int n, size_t* Lp, int* Li, double* Lx, size_t* Li_ptr, 
                         double* x, int nLevels, const int* levelPtr, const int* parPtr, const int* partition, int which) {
   if (!Lp || !Li || !x) return 0;   // Triangular_BCSC.h:24,185
   if (!Lx || !Li_ptr || !col2sup || !sup2col) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  if (parsy_cuda_device_count() <= 0) { fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)"); return 0; }
+  const bool cache = dropin_cache_enabled();
+  uint64_t key = 0;
   parsy_cuda_solver* s = nullptr;
-  int rc = parsy_cuda_create(&s, n, nullptr, nullptr, Lp, Li, Li_ptr, sup2col, supNo, nullptr, col2sup, nLevels,
-                             levelPtr, parPtr, partition, nullptr);
+  if (cache) {
+    key = structure_key(2, n, nullptr, nullptr, Lp, Li, Li_ptr, sup2col, supNo, col2sup, nLevels, levelPtr, parPtr, partition);
+    s = cache_take(key);
+  }
+  int rc = 0;
+  if (!s) rc = parsy_cuda_create(&s, n, nullptr, nullptr, Lp, Li, Li_ptr, sup2col, supNo, nullptr, col2sup, nLevels,
+                                 levelPtr, parPtr, partition, nullptr);
   if (rc) return 0;
   rc = parsy_cuda_set_factor(s, Lx);
   if (!rc) rc = parsy_cuda_set_rhs(s, x);
   if (!rc) rc = parsy_cuda_solve(s, which);
   if (!rc) rc = parsy_cuda_get_rhs(s, x);
   const std::string keep = g_err;
-  parsy_cuda_destroy(s);
+  if (cache && rc == PARSY_CUDA_OK) cache_put(key, s);
+  else parsy_cuda_destroy(s);
   g_err = keep;
   return rc == PARSY_CUDA_OK ? 1 : 0;
 }
@@ -1114,116 +1328,456 @@ extern "C" int parsy_cuda_owned_ranges(parsy_cuda_solver* s, int rank, int64_t* 
   if (!s) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle"); return -1; }
   return owned_ranges_of(s->plan, rank, begin_end_pairs, max_pairs);
 }
-// ---- stepwise execution (distributed top) ------------------------------------------------------------------
-extern "C" int parsy_cuda_num_steps(parsy_cuda_solver* s) { return s ? (int)s->plan.steps.size() : -1; }
-extern "C" int parsy_cuda_first_top_step(parsy_cuda_solver* s) { return s ? s->plan.first_top_step : -1; }
-// Panels that must be broadcast from their owner before `step` is enqueued: triples (owner, begin, end) in doubles.
-extern "C" int parsy_cuda_step_bcasts(parsy_cuda_solver* s, int step, int64_t* triples, int max_triples) {
-  if (!s || step < 0 || step >= (int)s->plan.steps.size()) { fail(PARSY_CUDA_ERR_BAD_ARG, "bad step"); return -1; }
-  const Plan& P = s->plan;
-  const int b = P.bcast_ptr[step], e = P.bcast_ptr[step + 1];
-  for (int i = b; i < e && triples && i - b < max_triples; ++i)
-    for (int k = 0; k < 3; ++k) triples[3 * (i - b) + k] = P.bcast[3 * i + k];
-  return e - b;
+// =====================================================================================================================
+// Sharded factorization + solve over the GPUs of one node.  One process per GPU, NCCL over NVLink, every
+// collective issued from here and captured into the same CUDA graphs as the kernels.
+//
+//   phase 1   each rank: zero + scatter A into what it owns, factor its bottom subtrees (the lower LBC levels are
+//             disjoint subtrees, cholesky/InspectionLevel_06.h:208-216) and push EVERY update of those subtrees —
+//             also the ones into the top separators, which accumulate in the rank's own copy of the top panels (fan-in)
+//   sum       one all-reduce per contiguous run of top panels: A_top - (all bottom updates); traffic is proportional
+//             to the separators, not to the descendants' panels
+//   top       block columns of the top separators are owned round-robin.  Per dependency step: the owner factors its
+//             block columns (POTRF + TRSM), broadcasts the finished panels, and every rank applies the updates into
+//             the block columns it owns; the two-stream look-ahead keeps the chain POTRF -> TRSM -> broadcast -> next-column update
+//             on the high-priority stream while the bulk of the trailing updates runs on the main stream.
+//   solve     forward: owned subtrees (partial sums into the top part of y), all-reduce of the top part of y, top
+//             separators on every rank (their factor is complete everywhere after the broadcasts); backward: top, then
+//             the owned subtrees; one all-reduce assembles x on every rank.
+// NCCL is opened with dlopen on first use (libnccl.so.2: the copy PyTorch already loaded, else the system's), so the
+// single-GPU library has no link-time dependency on it.
+// =====================================================================================================================
+#include <dlfcn.h>
+#include <mutex>
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return;
+#define SYM(name) *(void**)(&api.name) = dlsym(h, "nccl" #name)
+    SYM(GetVersion); SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Broadcast);
+    SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+#undef SYM
+    if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Broadcast && api.GroupStart &&
+        api.GroupEnd && api.GetErrorString)
+      api.lib = h;
+  });
+  return api.lib ? &api : nullptr;
 }
-// Enqueues steps [begin, end) on the handle's stream (no graph, no look-ahead stream).
-extern "C" int parsy_cuda_factor_steps(parsy_cuda_solver* s, int begin, int end) {
-  if (!s || begin < 0 || end > (int)s->plan.steps.size() || begin > end) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad step range");
-  CU(cudaSetDevice(s->device));
-  if (begin == 0) CU(cudaMemsetAsync(s->d_info, 0, sizeof(int), s->stream));
-  const bool la = s->lookahead;
-  s->lookahead = false;
-  const int64_t l = enqueue_factor_steps(s, begin, end);
-  s->lookahead = la;
-  if (begin == 0) s->launches_factor = 0;
-  s->launches_factor += l;
-  CU(cudaGetLastError());
-  if (end == (int)s->plan.steps.size()) s->factored = true;
+}  // namespace
+#define NC(call)                                                                                          \
+  do {                                                                                                    \
+    ncclResult_t r_ = (call);                                                                             \
+    if (r_ != ncclSuccess) return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + nccl_api()->GetErrorString(r_)); \
+  } while (0)
+
+struct ShardRank {
+  int rank = 0;
+  parsy_cuda_solver *h1 = nullptr, *h2 = nullptr;
+  std::vector<int32_t> gather_zero;   // column runs this rank zeroes before x is summed over the ranks
+};
+
+struct parsy_cuda_sharded {
+  int world = 1, device = 0;
+  bool local = false;                 // every rank emulated in this process on one device (tests; no NCCL)
+  bool use_graph = true;
+  std::vector<ShardRank> rs;          // NCCL mode: this process' rank only
+  ncclComm_t comm = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t g_p1 = nullptr, g_sum = nullptr, g_top = nullptr, g_fwd = nullptr, g_bwd = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  const double** d_srcs = nullptr;    // local mode: the ranks' factor / rhs buffers (k_sum_buffers)
+  int64_t launches_factor = 0, launches_fwd = 0, launches_bwd = 0;
+  int64_t n_bcast = 0, n_allreduce = 0, bytes_bcast = 0, bytes_sum = 0;
+  bool factored = false, timed = false, has_values = false;
+  int rc_enqueue = 0;                 // first error seen while enqueueing (capture lambdas cannot return it)
+};
+
+extern "C" int parsy_cuda_nccl_unique_id(void* out128) {
+  if (!out128) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  NcclApi* N = nccl_api();
+  if (!N) return fail(PARSY_CUDA_ERR_CUDA, std::string("libnccl.so.2 could not be loaded: ") + (dlerror() ? dlerror() : "missing symbols"));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NC(N->GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
   return PARSY_CUDA_OK;
 }
-// Look-ahead variant of the stepwise API (two streams, same dependency rules as enqueue_factor_steps):
-//   parsy_cuda_step_begin(h, i, first)  side stream waits for everything block column i depends on from the main stream
-//   <host: broadcasts of step i's panels on the side stream>
-//   parsy_cuda_step_run(h, i)           side: F_i, A_i      main: R_i (after F_i)
-//   parsy_cuda_steps_end(h)             main waits for the side stream
-extern "C" int parsy_cuda_step_begin(parsy_cuda_solver* s, int step, int first) {
-  if (!s || step < 0 || step >= (int)s->plan.steps.size()) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad step");
-  CU(cudaSetDevice(s->device));
-  if (first) {
-    CU(cudaEventRecord(s->ev_fork, s->stream));
-    CU(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
-    s->la_first = step;
-  } else if (step - 2 >= s->la_first) {
-    CU(cudaStreamWaitEvent(s->stream2, s->ev_R[(step - 1) & 1], 0));
+
+// ---- collectives (NCCL, or device copies between the emulated ranks) --------------------------------------------
+// sum over the ranks of buffer[begin, end) (which = 0: factor, 1: right-hand side), in place
+static void sh_allreduce(parsy_cuda_sharded* sh, int which, int64_t begin, int64_t end, cudaStream_t st) {
+  if (end <= begin) return;
+  auto buf = [&](const ShardRank& R) { return which == 0 ? R.h1->d_lv : R.h1->d_rhs; };
+  if (!sh->local) {
+    double* p = buf(sh->rs[0]) + begin;
+    const ncclResult_t r = nccl_api()->AllReduce(p, p, (size_t)(end - begin), ncclDouble, ncclSum, sh->comm, st);
+    if (r != ncclSuccess && !sh->rc_enqueue) sh->rc_enqueue = fail(PARSY_CUDA_ERR_CUDA, std::string("ncclAllReduce: ") + nccl_api()->GetErrorString(r));
+  } else {
+    std::vector<const double*> h;
+    for (const ShardRank& R : sh->rs) h.push_back(buf(R) + begin);
+    cudaMemcpyAsync(sh->d_srcs, h.data(), sizeof(double*) * h.size(), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);   // h is a stack vector (emulation only, never captured)
+    const int grid = (int)std::min<int64_t>((end - begin + 255) / 256, 148 * 8);
+    k_sum_buffers<<<grid, 256, 0, st>>>(end - begin, buf(sh->rs[0]) + begin, sh->d_srcs, (int)h.size());
+    for (size_t k = 1; k < sh->rs.size(); ++k)
+      cudaMemcpyAsync(buf(sh->rs[k]) + begin, buf(sh->rs[0]) + begin, sizeof(double) * (size_t)(end - begin), cudaMemcpyDeviceToDevice, st);
   }
-  return PARSY_CUDA_OK;
+  sh->n_allreduce++; sh->bytes_sum += 8 * (end - begin);
 }
-extern "C" int parsy_cuda_step_run(parsy_cuda_solver* s, int step) {
-  if (!s || step < 0 || step >= (int)s->plan.steps.size()) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad step");
-  CU(cudaSetDevice(s->device));
-  const Step& S = s->plan.steps[step];
-  int64_t l = launch_factor_phase(s, S, s->stream2, nullptr);
-  CU(cudaEventRecord(s->ev_F[step & 1], s->stream2));
-  l += launch_update_group(s, S.upd[0], s->stream2, nullptr);
-  CU(cudaStreamWaitEvent(s->stream, s->ev_F[step & 1], 0));
-  l += launch_update_group(s, S.upd[1], s->stream, nullptr);
-  CU(cudaEventRecord(s->ev_R[(step + 1) & 1], s->stream));
-  s->launches_factor += l;
-  CU(cudaGetLastError());
-  if (step + 1 == (int)s->plan.steps.size()) s->factored = true;
-  return PARSY_CUDA_OK;
-}
-extern "C" int parsy_cuda_steps_end(parsy_cuda_solver* s) {
-  if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
-  CU(cudaEventRecord(s->ev_join, s->stream2));
-  CU(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
-  return PARSY_CUDA_OK;
-}
-extern "C" void* parsy_cuda_stream2(parsy_cuda_solver* s) { return s ? (void*)s->stream2 : nullptr; }
-
-// dst.lValues[begin, end) = src.lValues[begin, end) (device to device; used to emulate the exchange on one GPU)
-extern "C" int parsy_cuda_copy_range(parsy_cuda_solver* dst, parsy_cuda_solver* src, int64_t begin, int64_t end) {
-  if (!dst || !src || begin < 0 || end > dst->plan.xsize || end > src->plan.xsize || begin > end) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad range");
-  CU(cudaSetDevice(dst->device));
-  CU(cudaStreamSynchronize(src->stream));
-  CU(cudaMemcpyAsync(dst->d_lv + begin, src->d_lv + begin, sizeof(double) * (size_t)(end - begin), cudaMemcpyDeviceToDevice, dst->stream));
-  // a broadcast is ordered on the owner's stream as well: the owner factors the panel in place right afterwards, so
-  // its stream must not run ahead of this read (write-after-read hazard of the emulation; NCCL orders it by itself)
-  cudaEvent_t done;
-  CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-  CU(cudaEventRecord(done, dst->stream));
-  CU(cudaStreamWaitEvent(src->stream, done, 0));
-  CU(cudaEventDestroy(done));
-  return PARSY_CUDA_OK;
+static void sh_bcast(parsy_cuda_sharded* sh, int root, int64_t begin, int64_t end, cudaStream_t st) {
+  if (end <= begin) return;
+  if (!sh->local) {
+    double* p = sh->rs[0].h1->d_lv + begin;
+    const ncclResult_t r = nccl_api()->Broadcast(p, p, (size_t)(end - begin), ncclDouble, root, sh->comm, st);
+    if (r != ncclSuccess && !sh->rc_enqueue) sh->rc_enqueue = fail(PARSY_CUDA_ERR_CUDA, std::string("ncclBroadcast: ") + nccl_api()->GetErrorString(r));
+  } else {
+    for (const ShardRank& R : sh->rs)
+      if (R.rank != root)
+        cudaMemcpyAsync(R.h1->d_lv + begin, sh->rs[root].h1->d_lv + begin, sizeof(double) * (size_t)(end - begin), cudaMemcpyDeviceToDevice, st);
+  }
+  sh->n_bcast++; sh->bytes_bcast += 8 * (end - begin);
 }
 
-// Makes `s` (a phase-2 handle) work on the factor buffer of `src` (the phase-1 handle of the same rank).
-extern "C" int parsy_cuda_factor_phase(parsy_cuda_solver* s, int phase) {
-  if (!s) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
-  return s->phase == phase ? PARSY_CUDA_OK : fail(PARSY_CUDA_ERR_STATE, "handle was planned for another phase");
+// ---- enqueue: the three parts of a factorization ------------------------------------------------------------------
+static int64_t sh_enqueue_phase1(parsy_cuda_sharded* sh) {
+  int64_t l = 0;
+  for (ShardRank& R : sh->rs) {
+    enqueue_assemble(R.h1, sh->stream);
+    l += 1 + enqueue_factor_steps(R.h1, 0, (int)R.h1->plan.steps.size());
+  }
+  return l;
 }
-extern "C" int parsy_cuda_adopt_factor(parsy_cuda_solver* s, parsy_cuda_solver* src) {
-  if (!s || !src) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
-  if (s->plan.xsize != src->plan.xsize || s->device != src->device) return fail(PARSY_CUDA_ERR_BAD_ARG, "handles differ");
-  CU(cudaSetDevice(s->device));
-  CU(cudaStreamSynchronize(s->stream));
-  if (s->owns_lv && s->d_lv) { cudaFree(s->d_lv); s->device_bytes -= (int64_t)sizeof(double) * s->plan.xsize; }
-  s->d_lv = src->d_lv;
-  s->owns_lv = false;
-  // the captured graphs hold the old pointer: re-capture
-  if (s->use_graph && !s->dist_top) {
-    if (s->g_levels) { cudaGraphExecDestroy(s->g_levels); s->g_levels = nullptr; }
-    if (s->g_last) { cudaGraphExecDestroy(s->g_last); s->g_last = nullptr; }
+static int64_t sh_enqueue_sum(parsy_cuda_sharded* sh) {
+  const Plan& P = sh->rs[0].h1->plan;
+  if (!sh->local) nccl_api()->GroupStart();
+  for (size_t k = 0; k + 1 < P.top_runs.size(); k += 2) sh_allreduce(sh, 0, P.top_runs[k], P.top_runs[k + 1], sh->stream);
+  if (!sh->local) nccl_api()->GroupEnd();
+  return 0;
+}
+static void sh_step_bcasts(parsy_cuda_sharded* sh, int step, cudaStream_t st) {
+  const Plan& P = sh->rs[0].h2->plan;
+  for (int i = P.bcast_ptr[step]; i < P.bcast_ptr[step + 1]; ++i)
+    sh_bcast(sh, (int)P.bcast[3 * i], P.bcast[3 * i + 1], P.bcast[3 * i + 2], st);
+}
+static int64_t sh_enqueue_top(parsy_cuda_sharded* sh) {
+  int64_t l = 0;
+  parsy_cuda_solver* h0 = sh->rs[0].h2;
+  const int nst = (int)h0->plan.steps.size(), first = h0->plan.first_top_step;
+  const bool dist = h0->dist_top;
+  if (!dist) {
+    // replicated top: every rank computes the whole top on its own copy
+    for (ShardRank& R : sh->rs) l += enqueue_factor_steps(R.h2, 0, nst);
+    return l;
+  }
+  if (sh->local || !h0->lookahead) {
+    cudaStream_t st = sh->stream;
+    for (int i = first; i < nst; ++i) {
+      for (ShardRank& R : sh->rs) l += launch_factor_phase(R.h2, R.h2->plan.steps[i], st, nullptr);
+      sh_step_bcasts(sh, i, st);
+      for (ShardRank& R : sh->rs) {
+        l += launch_update_group(R.h2, R.h2->plan.steps[i].upd[0], st, nullptr);
+        l += launch_update_group(R.h2, R.h2->plan.steps[i].upd[1], st, nullptr);
+      }
+    }
+  } else {
+    // side (high priority): [F_i on the owner] -> broadcast_i -> A_i     main: R_i after broadcast_i
+    // F_i needs A_{i-1} (stream order) and R_{i-2} (event) — all updates into a block column run on its owner
+    parsy_cuda_solver* s = h0;
     const Plan& P = s->plan;
-    const int nst = (int)P.steps.size();
-    const int last_begin = P.nlevels > 0 ? P.hlevel_first_step[P.nlevels - 1] : 0;
-    int64_t l0 = 0, l1 = 0;
-    int rc = capture(s, &s->g_levels, &l0, [&] { return enqueue_factor_steps(s, 0, last_begin); });
-    if (rc) return rc;
-    rc = capture(s, &s->g_last, &l1, [&] { return enqueue_factor_steps(s, last_begin, nst); });
-    if (rc) return rc;
-    s->launches_factor = l0 + l1;
+    cudaStream_t mainst = s->stream, side = s->stream2;
+    cudaEventRecord(s->ev_fork, mainst);
+    cudaStreamWaitEvent(side, s->ev_fork, 0);
+    for (int i = first; i < nst; ++i) {
+      const Step& S = P.steps[i];
+      if (i - 2 >= first) cudaStreamWaitEvent(side, s->ev_R[(i - 1) & 1], 0);
+      l += launch_factor_phase(s, S, side, nullptr);
+      sh_step_bcasts(sh, i, side);
+      cudaEventRecord(s->ev_F[i & 1], side);
+      l += launch_update_group(s, S.upd[0], side, nullptr);
+      cudaStreamWaitEvent(mainst, s->ev_F[i & 1], 0);
+      l += launch_update_group(s, S.upd[1], mainst, nullptr);
+      cudaEventRecord(s->ev_R[(i + 1) & 1], mainst);
+    }
+    cudaEventRecord(s->ev_join, side);
+    cudaStreamWaitEvent(mainst, s->ev_join, 0);
   }
-  s->factored = false;
+  // inverse diagonal blocks of the block columns other ranks factored (the sweeps solve with them)
+  for (ShardRank& R : sh->rs)
+    if (!R.h2->plan.invert_tasks.empty()) {
+      k_invert_block<<<(int)R.h2->plan.invert_tasks.size(), POTRF_THREADS, POTRF_SMEM, sh->stream>>>(R.h2->d_invert, R.h2->d_sup,
+                                                                                                 R.h2->d_lv, R.h2->d_linv);
+      ++l;
+    }
+  return l;
+}
+
+static int64_t sh_enqueue_fwd(parsy_cuda_sharded* sh) {
+  int64_t l = 0;
+  cudaStream_t st = sh->stream;
+  const Plan& T = sh->rs[0].h2->plan;
+  // the top part of y is summed over the ranks after the subtree sweeps: only rank 0 brings b's entries
+  for (ShardRank& R : sh->rs)
+    if (R.rank != 0)
+      for (size_t k = 0; k + 1 < T.col_runs.size(); k += 2) { k_zero_range<<<32, 256, 0, st>>>(R.h1->d_rhs, T.col_runs[k], T.col_runs[k + 1]); ++l; }
+  for (ShardRank& R : sh->rs) l += enqueue_fwd(R.h1);
+  if (!sh->local) nccl_api()->GroupStart();
+  for (size_t k = 0; k + 1 < T.col_runs.size(); k += 2) sh_allreduce(sh, 1, T.col_runs[k], T.col_runs[k + 1], st);
+  if (!sh->local) nccl_api()->GroupEnd();
+  for (ShardRank& R : sh->rs) l += enqueue_fwd(R.h2);
+  return l;
+}
+static int64_t sh_enqueue_bwd(parsy_cuda_sharded* sh) {
+  int64_t l = 0;
+  cudaStream_t st = sh->stream;
+  for (ShardRank& R : sh->rs) { l += enqueue_bwd(R.h2); l += enqueue_bwd(R.h1); }
+  // x on every rank: each rank keeps what it solved (rank 0 also the top), zeroes the rest, one sum
+  for (ShardRank& R : sh->rs)
+    for (size_t k = 0; k + 1 < R.gather_zero.size(); k += 2) { k_zero_range<<<64, 256, 0, st>>>(R.h1->d_rhs, R.gather_zero[k], R.gather_zero[k + 1]); ++l; }
+  sh_allreduce(sh, 1, 0, sh->rs[0].h1->plan.n, st);
+  return l;
+}
+
+template <class F> static int sh_capture(parsy_cuda_sharded* sh, cudaGraphExec_t* out, int64_t* launches, F enqueue) {
+  cudaGraph_t g = nullptr;
+  CU(cudaStreamBeginCapture(sh->stream, cudaStreamCaptureModeThreadLocal));
+  *launches = enqueue();
+  CU(cudaStreamEndCapture(sh->stream, &g));
+  CU(cudaGetLastError());
+  if (sh->rc_enqueue) { cudaGraphDestroy(g); return sh->rc_enqueue; }
+  CU(cudaGraphInstantiate(out, g, 0));
+  CU(cudaGraphDestroy(g));
+  return 0;
+}
+
+extern "C" void parsy_cuda_sharded_destroy(parsy_cuda_sharded* sh) {
+  if (!sh) return;
+  cudaSetDevice(sh->device);
+  if (sh->stream) cudaStreamSynchronize(sh->stream);
+  for (cudaGraphExec_t g : {sh->g_p1, sh->g_sum, sh->g_top, sh->g_fwd, sh->g_bwd}) if (g) cudaGraphExecDestroy(g);
+  if (sh->comm) nccl_api()->CommDestroy(sh->comm);
+  for (auto& e : sh->ev) if (e) cudaEventDestroy(e);
+  if (sh->d_srcs) cudaFree(sh->d_srcs);
+  // phase-2 handles and the other emulated ranks borrow streams from the first phase-1 handle: destroy it last
+  for (size_t k = sh->rs.size(); k-- > 0;) { parsy_cuda_destroy(sh->rs[k].h2); if (k) parsy_cuda_destroy(sh->rs[k].h1); }
+  if (!sh->rs.empty()) parsy_cuda_destroy(sh->rs[0].h1);
+  delete sh;
+}
+
+extern "C" int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const int* c, const int* r, const size_t* lC,
+                                         const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo,
+                                         const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr,
+                                         const int* parPtr, const int* partition, const parsy_cuda_options* opt,
+                                         const void* nccl_unique_id) {
+  if (!out || !opt) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  *out = nullptr;
+  if (!c || !r) return fail(PARSY_CUDA_ERR_BAD_ARG, "the pattern of A is required");
+  if (!levelPtr || !parPtr || !partition) return fail(PARSY_CUDA_ERR_BAD_ARG, "a sharded factorization needs the LBC schedule");
+  const int world = opt->world;
+  if (world < 2 || opt->rank < 0 || opt->rank >= world) return fail(PARSY_CUDA_ERR_BAD_ARG, "need world >= 2 and 0 <= rank < world");
+  if (parsy_cuda_device_count() <= 0) return fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
+  parsy_cuda_sharded* sh = new parsy_cuda_sharded();
+  sh->world = world; sh->device = opt->device; sh->local = nccl_unique_id == nullptr; sh->use_graph = opt->use_graph != 0;
+#define TRY(x) do { int rc_ = (x); if (rc_) { const std::string keep_ = g_err; parsy_cuda_sharded_destroy(sh); g_err = keep_; return rc_; } } while (0)
+#define TRYCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { parsy_cuda_sharded_destroy(sh); return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  TRYCU(cudaSetDevice(sh->device));
+  for (int k = 0; k < (sh->local ? world : 1); ++k) {
+    ShardRank R;
+    R.rank = sh->local ? k : opt->rank;
+    parsy_cuda_options o = *opt;
+    o.rank = R.rank; o.use_graph = 0;
+    if (sh->local) { o.reserved[0] = 1; o.reserved[6] = 1; }   // one stream, program order
+    o.reserved[2] = 1;
+    parsy_cuda_solver* parent = sh->rs.empty() ? nullptr : sh->rs[0].h1;
+    TRY(create_impl(&R.h1, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition, &o, parent, false));
+    sh->rs.push_back(R);
+    o.reserved[2] = 2;
+    TRY(create_impl(&sh->rs.back().h2, n, nullptr, nullptr, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr,
+                    partition, &o, sh->rs.back().h1, true));
+  }
+  sh->stream = sh->rs[0].h1->stream;
+  for (auto& e : sh->ev) TRYCU(cudaEventCreate(&e));
+  if (sh->local) TRYCU(cudaMalloc((void**)&sh->d_srcs, sizeof(double*) * (size_t)world));
+  // columns a rank zeroes before the final sum of x: everything but its subtrees (rank 0: and the top)
+  for (ShardRank& R : sh->rs) {
+    const Plan& P = R.h1->plan;
+    std::vector<char> keep((size_t)n, 0);
+    for (size_t k = 0; k + 1 < P.col_runs.size(); k += 2) for (int j = P.col_runs[k]; j < P.col_runs[k + 1]; ++j) keep[j] = 1;
+    if (R.rank == 0) { const Plan& T = R.h2->plan; for (size_t k = 0; k + 1 < T.col_runs.size(); k += 2) for (int j = T.col_runs[k]; j < T.col_runs[k + 1]; ++j) keep[j] = 1; }
+    int b = -1;
+    for (int j = 0; j <= n; ++j) {
+      const bool z = j < n && !keep[j];
+      if (z && b < 0) b = j;
+      if (!z && b >= 0) { R.gather_zero.push_back(b); R.gather_zero.push_back(j); b = -1; }
+    }
+  }
+  if (!sh->local) {
+    NcclApi* N = nccl_api();
+    if (!N) { parsy_cuda_sharded_destroy(sh); return fail(PARSY_CUDA_ERR_CUDA, "libnccl.so.2 could not be loaded"); }
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, sizeof(id));
+    ncclResult_t nr = N->CommInitRank(&sh->comm, world, id, opt->rank);
+    if (nr != ncclSuccess) { sh->comm = nullptr; parsy_cuda_sharded_destroy(sh); return fail(PARSY_CUDA_ERR_CUDA, std::string("ncclCommInitRank: ") + N->GetErrorString(nr)); }
+    // every collective of a factorization and of the sweeps once outside capture: NCCL sets up its channels and
+    // buffers on first use, which must not happen while a stream is being captured
+    sh_enqueue_sum(sh);
+    const int nst = (int)sh->rs[0].h2->plan.steps.size();
+    if (sh->rs[0].h2->dist_top) for (int i = sh->rs[0].h2->plan.first_top_step; i < nst; ++i) sh_step_bcasts(sh, i, sh->stream);
+    sh_allreduce(sh, 1, 0, n, sh->stream);
+    TRYCU(cudaStreamSynchronize(sh->stream));
+    if (sh->rc_enqueue) { const int rc2 = sh->rc_enqueue; parsy_cuda_sharded_destroy(sh); return rc2; }
+  }
+  if (sh->use_graph && !sh->local) {
+    int64_t l1 = 0, l2 = 0, l3 = 0;
+    TRY(sh_capture(sh, &sh->g_p1, &l1, [&] { return sh_enqueue_phase1(sh); }));
+    TRY(sh_capture(sh, &sh->g_sum, &l2, [&] { return sh_enqueue_sum(sh); }));
+    TRY(sh_capture(sh, &sh->g_top, &l3, [&] { return sh_enqueue_top(sh); }));
+    sh->launches_factor = l1 + l2 + l3;
+    TRY(sh_capture(sh, &sh->g_fwd, &sh->launches_fwd, [&] { return sh_enqueue_fwd(sh); }));
+    TRY(sh_capture(sh, &sh->g_bwd, &sh->launches_bwd, [&] { return sh_enqueue_bwd(sh); }));
+  }
+  // communication per factorization, counted once
+  sh->n_bcast = sh->n_allreduce = sh->bytes_bcast = sh->bytes_sum = 0;
+  {
+    const Plan& P1 = sh->rs[0].h1->plan; const Plan& P2 = sh->rs[0].h2->plan;
+    for (size_t k = 0; k + 1 < P1.top_runs.size(); k += 2) { sh->n_allreduce++; sh->bytes_sum += 8 * (P1.top_runs[k + 1] - P1.top_runs[k]); }
+    for (size_t i = 0; i < P2.bcast.size() / 3; ++i) { sh->n_bcast++; sh->bytes_bcast += 8 * (P2.bcast[3 * i + 2] - P2.bcast[3 * i + 1]); }
+  }
+  TRYCU(cudaStreamSynchronize(sh->stream));
+  *out = sh;
   return PARSY_CUDA_OK;
+#undef TRY
+#undef TRYCU
+}
+
+extern "C" int parsy_cuda_sharded_set_values(parsy_cuda_sharded* sh, const double* values) {
+  if (!sh || !values) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  for (ShardRank& R : sh->rs) { int rc = parsy_cuda_set_values(R.h1, values); if (rc) return rc; }
+  sh->has_values = true;
+  return PARSY_CUDA_OK;
+}
+
+// Asynchronous on the handle's stream: phase 1 -> sum of the top panels over the ranks -> distributed top.
+extern "C" int parsy_cuda_sharded_factor(parsy_cuda_sharded* sh) {
+  if (!sh) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  if (!sh->has_values) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede factor");
+  CU(cudaSetDevice(sh->device));
+  cudaStream_t st = sh->stream;
+  sh->rc_enqueue = 0;
+  CU(cudaEventRecord(sh->ev[0], st));
+  if (sh->g_p1) CU(cudaGraphLaunch(sh->g_p1, st)); else sh->launches_factor = sh_enqueue_phase1(sh);
+  CU(cudaEventRecord(sh->ev[1], st));
+  if (sh->g_sum) CU(cudaGraphLaunch(sh->g_sum, st)); else sh_enqueue_sum(sh);
+  CU(cudaEventRecord(sh->ev[2], st));
+  if (sh->g_top) CU(cudaGraphLaunch(sh->g_top, st)); else sh->launches_factor += sh_enqueue_top(sh);
+  CU(cudaEventRecord(sh->ev[3], st));
+  CU(cudaGetLastError());
+  if (sh->rc_enqueue) return sh->rc_enqueue;
+  sh->factored = sh->timed = true;
+  for (ShardRank& R : sh->rs) R.h1->factored = R.h2->factored = true;
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_sharded_sync(parsy_cuda_sharded* sh) {
+  if (!sh) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  for (ShardRank& R : sh->rs) { int rc = parsy_cuda_sync(R.h1); if (rc) return rc; }
+  return PARSY_CUDA_OK;
+}
+
+// seconds of the last factorization on this rank: [0] phase 1 (owned subtrees + their updates), [1] sum of the top
+// panels over the ranks, [2] distributed top
+extern "C" int parsy_cuda_sharded_phase_times(parsy_cuda_sharded* sh, double* out3) {
+  if (!sh || !out3) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  if (!sh->timed) return fail(PARSY_CUDA_ERR_STATE, "no factorization has run");
+  CU(cudaSetDevice(sh->device));
+  CU(cudaEventSynchronize(sh->ev[3]));
+  for (int k = 0; k < 3; ++k) { float ms = 0; CU(cudaEventElapsedTime(&ms, sh->ev[k], sh->ev[k + 1])); out3[k] = ms * 1e-3; }
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_sharded_set_rhs(parsy_cuda_sharded* sh, const double* b) {
+  if (!sh || !b) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  for (ShardRank& R : sh->rs) { int rc = parsy_cuda_set_rhs(R.h1, b); if (rc) return rc; }
+  return PARSY_CUDA_OK;
+}
+extern "C" int parsy_cuda_sharded_get_rhs(parsy_cuda_sharded* sh, double* x) {
+  if (!sh || !x) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  return parsy_cuda_get_rhs(sh->rs[0].h1, x);
+}
+// L y = b and/or L' x = y over the sharded factor; afterwards every rank holds the full vector.  A backward sweep on
+// its own expects the full y on every rank (what the forward sweep leaves only for this rank's subtrees and the top),
+// so FWD alone returns y for this rank's columns and the top — use FWD|BWD for a complete solve.
+extern "C" int parsy_cuda_sharded_solve(parsy_cuda_sharded* sh, int which) {
+  if (!sh) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL handle");
+  if (!sh->factored) return fail(PARSY_CUDA_ERR_STATE, "solve before factor");
+  if (!(which & (PARSY_CUDA_SOLVE_FWD | PARSY_CUDA_SOLVE_BWD))) return fail(PARSY_CUDA_ERR_BAD_ARG, "which must be FWD, BWD or both");
+  CU(cudaSetDevice(sh->device));
+  sh->rc_enqueue = 0;
+  if (which & PARSY_CUDA_SOLVE_FWD) { if (sh->g_fwd) CU(cudaGraphLaunch(sh->g_fwd, sh->stream)); else sh->launches_fwd = sh_enqueue_fwd(sh); }
+  if (which & PARSY_CUDA_SOLVE_BWD) { if (sh->g_bwd) CU(cudaGraphLaunch(sh->g_bwd, sh->stream)); else sh->launches_bwd = sh_enqueue_bwd(sh); }
+  CU(cudaGetLastError());
+  return sh->rc_enqueue;
+}
+
+// Host lValues (xsize doubles, reference layout): this process writes what it holds complete — the panels of its own
+// subtrees and of the top separators — and leaves the other ranks' subtrees untouched (emulated ranks: everything).
+extern "C" int parsy_cuda_sharded_get_factor(parsy_cuda_sharded* sh, double* lValues) {
+  if (!sh || !lValues) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(sh->device));
+  CU(cudaStreamSynchronize(sh->stream));
+  for (ShardRank& R : sh->rs) {
+    const Plan& P = R.h1->plan;
+    std::vector<int64_t> runs((size_t)2 * (P.nsuper + 1));
+    const int cnt = owned_ranges_of(P, R.rank, runs.data(), P.nsuper + 1);
+    for (int k = 0; k < cnt; ++k)
+      CU(cudaMemcpy(lValues + runs[2 * k], R.h1->d_lv + runs[2 * k], sizeof(double) * (size_t)(runs[2 * k + 1] - runs[2 * k]), cudaMemcpyDeviceToHost));
+    if (&R == &sh->rs[0])
+      for (size_t k = 0; k + 1 < P.top_runs.size(); k += 2)
+        CU(cudaMemcpy(lValues + P.top_runs[k], R.h1->d_lv + P.top_runs[k], sizeof(double) * (size_t)(P.top_runs[k + 1] - P.top_runs[k]), cudaMemcpyDeviceToHost));
+  }
+  return PARSY_CUDA_OK;
+}
+
+// out[0] kernel launches per factorization on this rank, [1] / [2] NCCL broadcasts / all-reduces per factorization,
+// [3] / [4] their bytes, [5] HBM held on this device, [6] dependency steps of the top chain, [7] NCCL version (0: none),
+// [8] / [9] kernel launches per forward / backward sweep, [10] supernodes owned by this rank, [11] shared top supernodes
+extern "C" int parsy_cuda_sharded_stats(parsy_cuda_sharded* sh, int64_t* out12) {
+  if (!sh || !out12) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  const Plan& P2 = sh->rs[0].h2->plan;
+  int ver = 0;
+  if (!sh->local && nccl_api() && nccl_api()->GetVersion) nccl_api()->GetVersion(&ver);
+  int64_t dev = 0, mine = 0, top = 0;
+  for (ShardRank& R : sh->rs) dev += R.h1->device_bytes + R.h2->device_bytes;
+  for (int s = 0; s < P2.nsuper; ++s) { if (P2.owner[s] == sh->rs[0].rank) ++mine; if (P2.owner[s] < 0) ++top; }
+  const int64_t v[12] = {sh->launches_factor, sh->n_bcast, sh->n_allreduce, sh->bytes_bcast, sh->bytes_sum, dev,
+                         (int64_t)P2.steps.size() - P2.first_top_step, ver, sh->launches_fwd, sh->launches_bwd, mine, top};
+  memcpy(out12, v, sizeof(v));
+  return PARSY_CUDA_OK;
+}
+extern "C" double* parsy_cuda_sharded_device_factor(parsy_cuda_sharded* sh) { return sh ? sh->rs[0].h1->d_lv : nullptr; }
+extern "C" double* parsy_cuda_sharded_device_rhs(parsy_cuda_sharded* sh) { return sh ? sh->rs[0].h1->d_rhs : nullptr; }
+extern "C" void* parsy_cuda_sharded_stream(parsy_cuda_sharded* sh) { return sh ? (void*)sh->stream : nullptr; }
+// the two plans of this process' rank (introspection: parsy_cuda_get_stats, parsy_cuda_owned_ranges)
+extern "C" parsy_cuda_solver* parsy_cuda_sharded_plan(parsy_cuda_sharded* sh, int emulated_rank, int phase) {
+  if (!sh || phase < 1 || phase > 2) return nullptr;
+  const size_t k = sh->local ? (size_t)emulated_rank : 0;
+  if (k >= sh->rs.size()) return nullptr;
+  return phase == 1 ? sh->rs[k].h1 : sh->rs[k].h2;
 }

@@ -248,16 +248,14 @@ class Solver:
 
     def __init__(self, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
                  device=0, block_cols=0, use_graph=True, ignore_hlevels=False, lookahead=True, dataflow_sweeps=True,
-                 rank=0, world=1, phase=0, top_levels=1, top_distributed=True, narrow_sweeps=True, fan_out=True):
+                 narrow_sweeps=True, fan_out=True):
         L = lib()
         self._L = L
         self._h = c_void_p()
         opt = Options()
         opt.device, opt.block_cols, opt.use_graph, opt.ignore_hlevels = int(device), int(block_cols), int(use_graph), \
             int(ignore_hlevels)
-        opt.rank, opt.world = int(rank), int(world)
         opt.reserved[0], opt.reserved[1] = int(not lookahead), int(not dataflow_sweeps)
-        opt.reserved[2], opt.reserved[3], opt.reserved[4] = int(phase), int(top_levels), int(not top_distributed)
         opt.reserved[5], opt.reserved[6] = int(not narrow_sweeps), int(not fan_out)
         f = L.parsy_cuda_create
         f.restype = c_int
@@ -414,66 +412,6 @@ class Solver:
         f(self._h, int(rank), out.ctypes.data_as(c_void_p), cnt)
         return out[:2 * cnt].reshape(-1, 2)
 
-    def adopt_factor(self, other):
-        """Work on `other`'s factor buffer (phase-2 handle adopting the phase-1 handle's)."""
-        f = self._L.parsy_cuda_adopt_factor
-        f.restype = c_int
-        f.argtypes = [c_void_p, c_void_p]
-        rc = f(self._h, other._h)
-        if rc != OK:
-            raise ParsyCudaError(rc, "parsy_cuda_adopt_factor")
-        self._keep = other
-
-    def num_steps(self):
-        f = self._L.parsy_cuda_num_steps
-        f.restype = c_int
-        f.argtypes = [c_void_p]
-        return int(f(self._h))
-
-    def first_top_step(self):
-        f = self._L.parsy_cuda_first_top_step
-        f.restype = c_int
-        f.argtypes = [c_void_p]
-        return int(f(self._h))
-
-    def step_bcasts(self, step):
-        """(owner, begin, end) of the panels to broadcast before `step` (distributed top)."""
-        f = self._L.parsy_cuda_step_bcasts
-        f.restype = c_int
-        f.argtypes = [c_void_p, c_int, c_void_p, c_int]
-        cnt = f(self._h, int(step), None, 0)
-        if cnt <= 0:
-            return np.zeros((0, 3), np.int64)
-        out = np.zeros(3 * cnt, np.int64)
-        f(self._h, int(step), out.ctypes.data_as(c_void_p), cnt)
-        return out.reshape(-1, 3)
-
-    def factor_steps(self, begin, end):
-        self._call("parsy_cuda_factor_steps", int(begin), int(end))
-
-    def step_begin(self, step, first):
-        self._call("parsy_cuda_step_begin", int(step), int(bool(first)))
-
-    def step_run(self, step):
-        self._call("parsy_cuda_step_run", int(step))
-
-    def steps_end(self):
-        self._call("parsy_cuda_steps_end")
-
-    def stream2(self):
-        f = self._L.parsy_cuda_stream2
-        f.restype = c_void_p
-        f.argtypes = [c_void_p]
-        return f(self._h)
-
-    def copy_range_from(self, other, begin, end):
-        f = self._L.parsy_cuda_copy_range
-        f.restype = c_int
-        f.argtypes = [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64]
-        rc = f(self._h, other._h, int(begin), int(end))
-        if rc != OK:
-            raise ParsyCudaError(rc, "parsy_cuda_copy_range")
-
     def device_pointers(self):
         L = self._L
         out = {}
@@ -491,6 +429,150 @@ class Solver:
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             f = self._L.parsy_cuda_destroy
+            f.restype = None
+            f.argtypes = [c_void_p]
+            f(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Borrowed(Solver):
+    """A plan owned by a Sharded handle (introspection only: stats, owned_ranges)."""
+
+    def __init__(self, L, h, owner):   # noqa: super().__init__ not called on purpose
+        self._L, self._h, self._owner = L, c_void_p(h), owner
+        st = self.stats()
+        self.n, self.xsize, self.nnzA = st["n"], st["xsize"], st["nnzA"]
+
+    def close(self):
+        self._h = c_void_p()
+
+
+def nccl_unique_id() -> bytes:
+    """128 bytes from ncclGetUniqueId (rank 0 calls it and hands the bytes to every rank)."""
+    buf = ctypes.create_string_buffer(128)
+    f = lib().parsy_cuda_nccl_unique_id
+    f.restype = c_int
+    f.argtypes = [c_void_p]
+    rc = f(buf)
+    if rc != OK:
+        raise ParsyCudaError(rc, "parsy_cuda_nccl_unique_id")
+    return buf.raw
+
+
+class Sharded:
+    """ONE factorization + solve sharded over the GPUs of a node, one process per GPU (include/parsy_cuda.h section 3,
+    DESIGN.md section 8).  ``unique_id``: the bytes of :func:`nccl_unique_id` from rank 0; ``None`` emulates all ``world``
+    ranks in this process on ``device`` (tests)."""
+
+    def __init__(self, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
+                 rank, world, unique_id, device=0, block_cols=0, top_levels=1, top_distributed=True, use_graph=True,
+                 lookahead=True):
+        L = lib()
+        self._L = L
+        self._h = c_void_p()
+        opt = Options()
+        opt.device, opt.block_cols, opt.use_graph = int(device), int(block_cols), int(use_graph)
+        opt.rank, opt.world = int(rank), int(world)
+        opt.reserved[0], opt.reserved[3], opt.reserved[4] = int(not lookahead), int(top_levels), int(not top_distributed)
+        f = L.parsy_cuda_sharded_create
+        f.restype = c_int
+        f.argtypes = [POINTER(c_void_p), c_int] + [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + \
+            [c_void_p] * 3 + [POINTER(Options), c_void_p]
+        keep = [_i32(c, "c"), _i32(r, "r"), _u64(lC, "lC"), _i32(lR, "lR"), _u64(Li_ptr, "Li_ptr"),
+                _i32(blockSet, "blockSet"), _i32(aTree, "aTree", True), _i32(col2Sup, "col2Sup"),
+                _i32(levelPtr, "levelPtr"), _i32(parPtr, "parPtr"), _i32(partition, "partition")]
+        p = [k[1] for k in keep]
+        uid = None
+        if unique_id is not None:
+            if len(unique_id) != 128:
+                raise ValueError("unique_id must be the 128 bytes of nccl_unique_id()")
+            uid = ctypes.create_string_buffer(bytes(unique_id), 128)
+        rc = f(byref(self._h), int(n), p[0], p[1], p[2], p[3], p[4], p[5], int(supNo), p[6], p[7], int(nLevels), p[8],
+               p[9], p[10], byref(opt), uid)
+        if rc != OK:
+            self._h = c_void_p()
+            raise ParsyCudaError(rc, "parsy_cuda_sharded_create")
+        self.n, self.rank, self.world, self.local = int(n), int(rank), int(world), unique_id is None
+        self.xsize = int(np.asarray(lC)[n])
+        self.nnzA = int(np.asarray(c)[n])
+
+    _call = Solver._call
+
+    def set_values(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if v.size != self.nnzA:
+            raise ValueError("values has the wrong length")
+        self._call("parsy_cuda_sharded_set_values", v.ctypes.data_as(c_void_p))
+        self._call("parsy_cuda_sharded_sync", ok=(OK, ERR_NOT_SPD))
+
+    def factor(self):
+        self._call("parsy_cuda_sharded_factor")
+
+    def sync(self) -> bool:
+        return self._call("parsy_cuda_sharded_sync", ok=(OK, ERR_NOT_SPD)) == OK
+
+    def set_rhs(self, b, sync=True):
+        v = np.ascontiguousarray(b, dtype=np.float64)
+        if v.size != self.n:
+            raise ValueError("b has the wrong length")
+        self._call("parsy_cuda_sharded_set_rhs", v.ctypes.data_as(c_void_p))
+        if sync:
+            self._call("parsy_cuda_sharded_sync", ok=(OK, ERR_NOT_SPD))
+
+    def solve(self, which=SOLVE_FWD | SOLVE_BWD):
+        self._call("parsy_cuda_sharded_solve", int(which))
+
+    def get_rhs(self, out=None):
+        x = np.empty(self.n) if out is None else out
+        self._call("parsy_cuda_sharded_get_rhs", _f64_inplace(x, "x"))
+        return x
+
+    def get_factor(self, out=None):
+        """The panels this process holds complete (own subtrees + top; emulation: all) written into ``out`` (reference
+        layout); other entries keep their previous content (zeros for a fresh array)."""
+        lv = np.zeros(self.xsize) if out is None else out
+        self._call("parsy_cuda_sharded_get_factor", _f64_inplace(lv, "lValues"))
+        return lv
+
+    def phase_times(self):
+        t = np.zeros(3)
+        self._call("parsy_cuda_sharded_phase_times", t.ctypes.data_as(c_void_p))
+        return {"phase1": t[0], "sum_top": t[1], "top": t[2]}
+
+    def stats(self):
+        v = np.zeros(12, np.int64)
+        self._call("parsy_cuda_sharded_stats", v.ctypes.data_as(c_void_p))
+        keys = ("launches_factor", "nccl_broadcasts", "nccl_allreduces", "bytes_broadcast", "bytes_summed", "device_bytes",
+                "top_chain_steps", "nccl_version", "launches_fwd", "launches_bwd", "owned_supernodes", "top_supernodes")
+        return {k: int(x) for k, x in zip(keys, v)}
+
+    def plan(self, phase, emulated_rank=0):
+        f = self._L.parsy_cuda_sharded_plan
+        f.restype = c_void_p
+        f.argtypes = [c_void_p, c_int, c_int]
+        h = f(self._h, int(emulated_rank), int(phase))
+        if not h:
+            raise ParsyCudaError(ERR_BAD_ARG, "parsy_cuda_sharded_plan")
+        return _Borrowed(self._L, h, self)
+
+    def device_pointers(self):
+        out = {}
+        for k in ("device_factor", "device_rhs", "stream"):
+            f = getattr(self._L, f"parsy_cuda_sharded_{k}")
+            f.restype = c_void_p
+            f.argtypes = [c_void_p]
+            out[k.replace("device_", "")] = f(self._h)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            f = self._L.parsy_cuda_sharded_destroy
             f.restype = None
             f.argtypes = [c_void_p]
             f(self._h)

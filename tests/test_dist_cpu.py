@@ -1,5 +1,6 @@
-"""CPU, world_size 2 over gloo: host logic of the sharded factorization (ownership split + panel exchange
-bookkeeping).  The numeric kernels need a GPU; here the exchanged "panels" are stand-in values."""
+"""CPU, world_size 2 over gloo: host logic of the sharded factorization (ownership split, fan-in sum of the top panels,
+every supernode factored once, every update applied once).  The numeric kernels need a GPU; here the summed "panels"
+are stand-in values."""
 import os
 import socket
 
@@ -28,42 +29,39 @@ def _worker(rank, world, port, q):
         S = inspector.analyze(n, Ap, Ai, Ax, 64, 1, 2)
         args = (n, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.col2Sup, S.nLevels, S.levelPtr, S.parPtr, S.partition)
         ranges = [ex.plan_owned_ranges(*args, world, r, top_levels=2) for r in range(world)]
-        # stand-in factor: every rank only knows the panels it owns
-        lv = torch.full((S.xsize,), float("nan"), dtype=torch.float64)
-        for b, e in ranges[rank]:
-            lv[b:e] = torch.arange(b, e, dtype=torch.float64) * (rank + 1)
-        for owner, runs in enumerate(ranges):
-            for b, e in runs:
-                dist.broadcast(lv[int(b):int(e)], src=owner)
-        # after the exchange every rank holds every owner's values
-        for owner, runs in enumerate(ranges):
-            for b, e in runs:
-                assert torch.equal(lv[int(b):int(e)], torch.arange(int(b), int(e), dtype=torch.float64) * (owner + 1))
+        top = ex.plan_owned_ranges(*args, world, -1, top_levels=2)
+        # ownership: the ranks' subtrees and the shared top partition the panels
         owned = torch.zeros(S.xsize, dtype=torch.int32)
-        for runs in ranges:
+        for runs in ranges + [top]:
             for b, e in runs:
                 owned[int(b):int(e)] += 1
-        assert int(owned.max()) == 1                       # disjoint
-        # what nobody owns is exactly the shared top (still NaN), and its supernode count matches the planner
+        assert int(owned.min()) == 1 and int(owned.max()) == 1
+        # fan-in over gloo with stand-in numbers: every rank adds "its subtrees' contribution" into its own copy of the
+        # top panels, rank 0 alone carries A's entries; the all-reduce must deliver A_top - sum of all contributions
+        lv = torch.zeros(S.xsize, dtype=torch.float64)
+        for b, e in top:
+            if rank == 0:
+                lv[int(b):int(e)] = 1000.0
+            lv[int(b):int(e)] -= float(rank + 1)
+        for b, e in top:
+            dist.all_reduce(lv[int(b):int(e)])
+        want = 1000.0 - sum(range(1, world + 1))
+        for b, e in top:
+            assert bool((lv[int(b):int(e)] == want).all())
+        # plans: phase 1 of rank r factors exactly the supernodes r owns; phase 2 lists every top supernode on every
+        # rank (the sweeps need them all) and, between the ranks, every update runs exactly once: the flops add up
         rc, st = ex.plan_check(*args, rank=rank, world=world, phase=2, top_levels=2)
         assert rc == ex.OK
         top_sup = st["reserved"][3]
-        assert st["reserved"][0] == top_sup                # every rank factors every top supernode (POTRF/TRSM replicated)
+        assert st["reserved"][0] == top_sup
         rc1, st1 = ex.plan_check(*args, rank=rank, world=world, phase=1, top_levels=2)
+        assert rc1 == ex.OK and st1["reserved"][0] == st1["reserved"][2]
         mine = torch.tensor([st1["reserved"][0], st1["reserved"][4] + st["reserved"][4]], dtype=torch.int64)
         tot = mine.clone()
         dist.all_reduce(tot)
         full = ex.plan_check(*args)[1]
         assert int(tot[0]) + top_sup == S.nsuper           # every bottom supernode is factored exactly once
-        # every update (descendant pair or trailing block update) runs on exactly one rank: the flops add up
         assert abs(int(tot[1]) - full["reserved"][4]) <= 4 * world
-        assert bool(torch.isnan(lv[owned == 0]).all()) and not bool(torch.isnan(lv[owned == 1]).any())
-        # checksum agreement across ranks
-        chk = torch.nan_to_num(lv).sum().reshape(1)
-        lo, hi = chk.clone(), chk.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        assert float(lo) == float(hi)
         q.put((rank, "ok", int(mine[0])))
     except Exception as exc:  # noqa: BLE001
         q.put((rank, repr(exc), 0))

@@ -409,55 +409,47 @@ def test_ill_conditioned_factor_and_solve(case):
     H.close()
 
 
-@pytest.mark.parametrize("world,top,dist_top", [(2, 1, True), (3, 2, True), (2, 2, False)])
-def test_sharded_factorization_emulated_on_one_gpu(world, top, dist_top):
-    """phase 1 per rank (owned bottom subtrees) -> panel exchange -> phase 2 (top separators, block-cyclic
-    with a panel broadcast before every step, or replicated).  All ranks are emulated on this one device; the NCCL
-    broadcasts become device-to-device copies between the ranks' buffers."""
-    S = analyze("3d27", 14, 64, 1, 2)
+@pytest.mark.parametrize("world,top,dist_top,case", [(2, 1, True, ("3d27", 14, 64, 1, 2)), (3, 2, True, ("3d27", 14, 64, 1, 2)),
+                                                     (2, 2, False, ("3d27", 14, 64, 1, 2)), (4, 1, True, ("2d5", 120, 148, 1, 4)),
+                                                     (8, 1, True, ("3d7", 22, 592, 1, 4))])
+def test_sharded_factorization_and_solve_emulated_on_one_gpu(world, top, dist_top, case):
+    """DESIGN.md §8 through parsy_cuda_sharded with every rank emulated on this one device (the NCCL collectives become
+    device copies / a summing kernel, the plans, kernels and ownership rules are the ones the multi-GPU runs use):
+    phase 1 (owned subtrees + fan-in of their updates into the top) -> sum of the top panels -> distributed top
+    (owner factors, panel broadcast, owners update) or replicated top; then the sharded forward / backward sweeps.
+    Factor against the oracle at 1e-9, solution against the oracle's restated sweeps."""
+    S = analyze(*case)
     ref = orc.cholesky_left_par_05(S)
-    args = (S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels, S.levelPtr,
-            S.parPtr, S.partition)
-    h1 = [ex.Solver(*args, rank=r, world=world, phase=1, top_levels=top) for r in range(world)]
-    for h in h1:
-        h.set_values(S.A2_x)
-        h.factor()
-    for h in h1:
-        assert h.sync()
-    owned = np.zeros(S.xsize, bool)
-    for o in range(world):
-        for b, e in h1[o].owned_ranges(o):
-            assert not owned[b:e].any()
-            owned[b:e] = True
-            for r in range(world):
-                if r != o:
-                    h1[r].copy_range_from(h1[o], b, e)       # the "broadcast" from owner o
-    h2 = [ex.Solver(*args, rank=r, world=world, phase=2, top_levels=top, top_distributed=dist_top) for r in range(world)]
+    sh = ex.Sharded(S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                    S.levelPtr, S.parPtr, S.partition, 0, world, None, top_levels=top, top_distributed=dist_top)
+    sh.set_values(S.A2_x)
+    for _ in range(2):                       # a second factorization on the same handle re-zeroes what it must
+        sh.factor()
+        assert sh.sync()
+    lv = sh.get_factor(np.full(S.xsize, np.nan))
+    assert not np.isnan(lv).any()            # the ranks' subtrees and the top cover the whole factor
+    assert rel_err(lv, ref) < TOL
+    assert np.array_equal(lv == 0.0, ref == 0.0)
+    owned = np.zeros(S.xsize, np.int32)
     for r in range(world):
-        h2[r].adopt_factor(h1[r])
-    if dist_top:
-        ft, ns = h2[0].first_top_step(), h2[0].num_steps()
-        assert 0 < ft < ns
-        for h in h2:
-            h.factor_steps(0, ft)
-        nb = 0
-        for st in range(ft, ns):
-            for o, b, e in h2[0].step_bcasts(st):
-                nb += 1
-                for r in range(world):
-                    if r != o:
-                        h2[r].copy_range_from(h2[o], b, e)
-            for h in h2:
-                h.factor_steps(st, st + 1)
-        assert nb > 0
-    else:
-        for h in h2:
-            h.factor()
-    for h in h2:
-        assert h.sync()
-        assert rel_err(h.get_factor(), ref) < TOL
-    for h in h2 + h1:
-        h.close()
+        for b0, e0 in sh.plan(1, r).owned_ranges(r):
+            owned[b0:e0] += 1
+    for b0, e0 in sh.plan(1, 0).owned_ranges(-1):
+        owned[b0:e0] += 1
+    assert owned.min() == 1 and owned.max() == 1          # ownership is a partition of the panels
+    st = sh.stats()
+    assert st["top_supernodes"] > 0 and st["nccl_allreduces"] > 0 and (st["nccl_broadcasts"] > 0) == dist_top
+    # sharded solve: L L' x = b in the factor's ordering
+    rng = np.random.default_rng(11)
+    bvec = rng.standard_normal(S.n)
+    sh.set_rhs(bvec)
+    sh.solve(ex.SOLVE_FWD | ex.SOLVE_BWD)
+    x = sh.get_rhs()
+    xr = orc.blockedLtsolve(S, ref, orc.blockedLsolve(S, ref, bvec))
+    assert rel_err(x, xr) < 1e-8
+    A = full_matrix(S)
+    assert np.linalg.norm(A @ x - bvec) / np.linalg.norm(bvec) < 1e-10
+    sh.close()
 
 
 # ---- full system A x = b (SURVEY.md §8(f) row 2) and Matrix-Market input (row 3) ---------------------------------
