@@ -293,7 +293,7 @@ def sharded_arm(args, name, rank, world, local, sampler):
     t_insp = time.time() - t0
     t0 = time.time()
     SH = make_sharded(S, rank, world, local, dist, top_levels=args.top_levels, block_cols=args.block_cols,
-                      top_distributed=not args.replicate_top, lookahead=not args.no_lookahead)
+                      top_distributed=not args.replicate_top, lookahead=not args.no_lookahead, top_chunk=args.top_chunk)
     t_create = time.time() - t0
     F = S.flops
     ptr = SH.device_pointers()
@@ -599,6 +599,7 @@ def main():
     ap.add_argument("--no-fan-out", action="store_true", help="kernel classes of a step on one stream (A/B)")
     ap.add_argument("--general-sweeps", action="store_true", help="leaf region of the sweeps on the general dataflow kernel (A/B)")
     ap.add_argument("--replicate-top", action="store_true", help="N>1: every rank computes the top separators")
+    ap.add_argument("--top-chunk", type=int, default=0, help="N>1: consecutive top block columns per owner (0 = library default)")
     ap.add_argument("--top-levels", type=int, default=1, help="N>1: LBC H-levels whose supernodes are shared (distributed by block column)")
     args = ap.parse_args()
     quiet_stdout()

@@ -122,7 +122,9 @@ typedef struct parsy_cuda_options {
   int reserved[10];    /* [0]=1 no look-ahead stream, [1]=1 per-step sweeps, [2] internal (phase), [3] top H-levels kept
                           shared, [4]=1 replicate the top instead of distributing it,
                           [5]=1 run the leaf region of the sweeps on the general dataflow kernel too,
-                          [6]=1 keep the kernel classes of a step on one stream (no fan-out over auxiliary streams) */
+                          [6]=1 keep the kernel classes of a step on one stream (no fan-out over auxiliary streams),
+                          [7] sharded: consecutive top block columns per owner (0 = default 4),
+                          [8] sharded: broadcast lanes (communicator + stream each; 0 = default 4) */
 } parsy_cuda_options;
 void parsy_cuda_options_default(parsy_cuda_options* opt);
 
@@ -273,6 +275,11 @@ int parsy_cuda_sharded_phase_times(parsy_cuda_sharded* s, double* out3);
  * [5] HBM held on this device, [6] dependency steps of the top chain, [7] NCCL version, [8]/[9] launches per forward /
  * backward sweep, [10] supernodes owned by this rank, [11] shared top supernodes */
 int parsy_cuda_sharded_stats(parsy_cuda_sharded* s, int64_t* out12);
+/* Diagnostics: one factorization without graphs, timing events around every part of every step of the distributed top.
+ * out[7*k + j] = milliseconds since the top phase started on this rank, step k: j = 0 F begin, 1 F end, 2 A end (chain
+ * stream), 3 / 4 broadcast begin / end (communication stream), 5 / 6 R begin / end (bulk stream); owner_of_step[k] = rank
+ * that factors the step's first block column.  Returns the number of steps, -1 on error. */
+int parsy_cuda_sharded_trace_top(parsy_cuda_sharded* s, int max_steps, float* out, int* owner_of_step);
 double* parsy_cuda_sharded_device_factor(parsy_cuda_sharded* s);
 double* parsy_cuda_sharded_device_rhs(parsy_cuda_sharded* s);
 void* parsy_cuda_sharded_stream(parsy_cuda_sharded* s);

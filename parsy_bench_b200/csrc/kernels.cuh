@@ -741,6 +741,12 @@ __global__ void k_sum_buffers(int64_t count, double* __restrict__ dst, const dou
     dst[i] = a;
   }
 }
+// timeline probes (parsy_cuda_sharded_trace_top): a one-thread kernel node that stores the GPU's nanosecond timer
+__global__ void k_stamp(unsigned long long* out) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  *out = t;
+}
 __global__ void k_zero_range(double* __restrict__ x, int b, int e) {
   for (int i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) x[i] = 0.0;
 }

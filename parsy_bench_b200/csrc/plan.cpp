@@ -173,7 +173,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     for (int s = 0; s < supNo; ++s) {
       if (P.owner[s] >= 0) continue;
       P.first_top_step = std::min(P.first_top_step, (int)step0[s]);
-      for (int b2 = 0; b2 < nblk[s]; ++b2) P.node_owner[node_first[s] + b2] = rr++ % opt.world;
+      for (int b2 = 0; b2 < nblk[s]; ++b2) P.node_owner[node_first[s] + b2] = (rr++ / std::max(1, opt.top_chunk)) % opt.world;
     }
   }
   auto sup_active = [&](int s) {
@@ -228,10 +228,14 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   // group (0 = "A": the target is factored in the very next step, 1 = "R": the rest; the executor overlaps R with
   // the next step's POTRF/TRSM on a second stream)
   struct Gen { GemmTask t; int32_t step; int8_t cls, grp; };
+  // distributed top: does an update task of (step, group) read a panel that another rank factors (= must it wait for
+  // that step's broadcasts)?  Set by the emitters below through `src_remote`.
+  bool src_remote = false;
   std::vector<Gen> gen;
   gen.reserve(P.pairs.size() + 3 * (size_t)o_blk[nsteps]);
   auto emit_update = [&](const GemmTask& t, int st, int grp, bool real_pair) {
     Gen g; g.t = t; g.step = st; g.grp = (int8_t)grp;
+    if (src_remote) P.steps[st].upd_remote[grp] = 1;
     const double fl = upd_flops(t);
     if (real_pair && is_small_pair(t.K, t.N)) { g.cls = 3; P.class_flops[5] += fl; P.n_pairs_small++; }
     else if (use128(t.M, t.N)) { g.cls = 1; P.class_flops[3] += fl; if (real_pair) P.n_pairs_tiled++; }
@@ -291,6 +295,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         // one task per later block column, kept only if this rank owns that block column
         for (int b3 = b2 + 1; b3 < nblk[s]; ++b3) {
           if (P.node_owner[node_first[s] + b3] != opt.rank) continue;
+          src_remote = P.node_owner[node_first[s] + b2] != opt.rank;
           const int c0 = (b3 - b2 - 1) * NB, c1 = std::min(Nt, c0 + NB);
           GemmTask t; memset(&t, 0, sizeof(t));
           t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb + c0; t.b_off = t.a_off;
@@ -330,21 +335,35 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     P.rel_prefix[pi] = rel; P.rel_pair_src[pi] = q.src; P.rel_pair_tgt[pi] = q.tgt; P.rel_pair_lb[pi] = q.lb;
     rel += q.m;
     if (!pair_active(q.src, q.tgt)) continue;
+    src_remote = false;
     if (!dist_top) { emit_update(t, st, step0[q.tgt] == st + 1 ? 0 : 1, true); continue; }
-    // split the pair's columns by the target block column they fall into; keep what this rank owns
+    // Distributed top.  (i) The pair's columns are split by the target block column they fall into; a rank keeps what
+    // it owns.  (ii) A wide source is applied in K-chunks of PAIR_KBLK block columns as they are finished instead of
+    // in one K = width task after its last block column: the ancestors' updates then overlap the source's own chain
+    // instead of arriving in one burst right before the next separator starts (sums via red.add, so K can be cut).
+    constexpr int PAIR_KBLK = 4;
+    const int nkb = D.flags ? 1 : nblk[q.src];
     for (int n0 = 0; n0 < q.nd1;) {
       auto blk_of = [&](int j) { return T.flags ? 0 : (lR[D.rowptr + q.lb + j] - T.col0) / NB; };
       const int tb = blk_of(n0);
       int n1 = n0 + 1;
       while (n1 < q.nd1 && blk_of(n1) == tb) ++n1;
       if (P.node_owner[node_first[q.tgt] + tb] == opt.rank) {
-        GemmTask u = t;
-        u.a_off += n0; u.b_off += n0; u.rel_off += n0; u.M = q.m - n0; u.N = n1 - n0;
-        emit_update(u, st, step0[q.tgt] + tb == st + 1 ? 0 : 1, true);
+        for (int kb0 = 0; kb0 < nkb; kb0 += PAIR_KBLK) {
+          const int kb1 = std::min(nkb, kb0 + PAIR_KBLK);
+          const int k0 = kb0 * NB, k1 = D.flags ? D.w : std::min(D.w, kb1 * NB);
+          const int stq = step0[q.src] + kb1 - 1;
+          GemmTask u = t;
+          u.a_off += n0 + (int64_t)k0 * D.r; u.b_off = u.a_off; u.rel_off += n0; u.M = q.m - n0; u.N = n1 - n0; u.K = k1 - k0;
+          src_remote = false;
+          for (int kb = kb0; kb < kb1; ++kb) if (P.node_owner[node_first[q.src] + kb] != opt.rank) src_remote = true;
+          emit_update(u, stq, step0[q.tgt] + tb == stq + 1 ? 0 : 1, true);
+        }
       }
       n0 = n1;
     }
   }
+  src_remote = false;
   P.rel_prefix[P.pairs.size()] = rel;
   P.rel_entries = rel;
 

@@ -137,6 +137,7 @@ struct Step {
   int32_t trsm_tiles = 0;
   int32_t trsm_tm = 64;      // row-tile height of this step's TRSM launch (64, 32 or 16)
   UpdGroup upd[2];   // [0] targets factored in the next step ("A"), [1] everything else ("R")
+  int8_t upd_remote[2] = {0, 0};   // distributed top: the group reads a panel another rank factors (wait for the broadcast)
   int32_t solve_tiles = 0;   // row tiles of the block tasks (forward / backward sweeps)
   int32_t max_nb = 0;        // widest block column in this step
 };
@@ -156,6 +157,10 @@ struct PlanOptions {
   // applies every update into it, factors it (POTRF + TRSM) and broadcasts the finished panel), 0 = the top is
   // computed redundantly by every rank
   int top_distributed = 1;
+  // consecutive block columns of the top given to one rank before moving on to the next (block-cyclic with this block
+  // size): inside such a run the chain POTRF -> TRSM -> next-column update stays on one GPU and the panel broadcast
+  // leaves the critical path
+  int top_chunk = 4;
 };
 
 struct Plan {

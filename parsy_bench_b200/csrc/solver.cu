@@ -480,6 +480,7 @@ static int create_impl(parsy_cuda_solver** out, int n, const int* c, const int* 
   }
   s->phase = po.world > 1 ? po.phase : 0;
   po.top_distributed = o.reserved[4] == 0;   // reserved[4] = 1: replicate the top instead of distributing it
+  if (o.reserved[7] > 0) po.top_chunk = o.reserved[7];
   s->dist_top = po.world > 1 && po.phase == 2 && po.top_distributed;
   // a missing schedule means "supernode order": one H-level with a single w-partition 0..supNo-1
   std::vector<int> tl, tp, tq;
@@ -949,6 +950,8 @@ extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, con
   if (opt) {
     po.nb = opt->block_cols; po.ignore_hlevels = opt->ignore_hlevels != 0;
     po.rank = opt->rank; po.world = std::max(1, opt->world); po.phase = opt->reserved[2]; po.top_levels = std::max(1, opt->reserved[3]);
+    po.top_distributed = opt->reserved[4] == 0;
+    if (opt->reserved[7] > 0) po.top_chunk = opt->reserved[7];
   }
   std::vector<int> tl, tp, tq;
   if (!levelPtr || !parPtr || !partition) {
@@ -1358,6 +1361,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -1372,7 +1376,7 @@ NcclApi* nccl_api() {
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!h) return;
 #define SYM(name) *(void**)(&api.name) = dlsym(h, "nccl" #name)
-    SYM(GetVersion); SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Broadcast);
+    SYM(GetVersion); SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(CommSplit); SYM(AllReduce); SYM(Broadcast);
     SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
     if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Broadcast && api.GroupStart &&
@@ -1401,6 +1405,15 @@ struct parsy_cuda_sharded {
   std::vector<ShardRank> rs;          // NCCL mode: this process' rank only
   ncclComm_t comm = nullptr;
   cudaStream_t stream = nullptr;
+  // panel broadcasts of the distributed top run off the factorization chain, round-robin over a few lanes (stream +
+  // communicator each) so that broadcasts rooted at different owners overlap on the NVLink fabric
+  static constexpr int MAX_LANES = 4;
+  int lanes = 1;
+  ncclComm_t lane_comm[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};   // [0] = comm
+  cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_B[2][MAX_LANES] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+  cudaEvent_t ev_cjoin[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t bcast_seq = 0;
   cudaGraphExec_t g_p1 = nullptr, g_sum = nullptr, g_top = nullptr, g_fwd = nullptr, g_bwd = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   const double** d_srcs = nullptr;    // local mode: the ranks' factor / rhs buffers (k_sum_buffers)
@@ -1442,11 +1455,11 @@ static void sh_allreduce(parsy_cuda_sharded* sh, int which, int64_t begin, int64
   }
   sh->n_allreduce++; sh->bytes_sum += 8 * (end - begin);
 }
-static void sh_bcast(parsy_cuda_sharded* sh, int root, int64_t begin, int64_t end, cudaStream_t st) {
+static void sh_bcast(parsy_cuda_sharded* sh, int root, int64_t begin, int64_t end, cudaStream_t st, int lane = 0) {
   if (end <= begin) return;
   if (!sh->local) {
     double* p = sh->rs[0].h1->d_lv + begin;
-    const ncclResult_t r = nccl_api()->Broadcast(p, p, (size_t)(end - begin), ncclDouble, root, sh->comm, st);
+    const ncclResult_t r = nccl_api()->Broadcast(p, p, (size_t)(end - begin), ncclDouble, root, sh->lane_comm[lane], st);
     if (r != ncclSuccess && !sh->rc_enqueue) sh->rc_enqueue = fail(PARSY_CUDA_ERR_CUDA, std::string("ncclBroadcast: ") + nccl_api()->GetErrorString(r));
   } else {
     for (const ShardRank& R : sh->rs)
@@ -1477,7 +1490,14 @@ static void sh_step_bcasts(parsy_cuda_sharded* sh, int step, cudaStream_t st) {
   for (int i = P.bcast_ptr[step]; i < P.bcast_ptr[step + 1]; ++i)
     sh_bcast(sh, (int)P.bcast[3 * i], P.bcast[3 * i + 1], P.bcast[3 * i + 2], st);
 }
-static int64_t sh_enqueue_top(parsy_cuda_sharded* sh) {
+// optional timeline of the distributed top (parsy_cuda_sharded_trace_top): one-thread kernels that store the GPU timer,
+// captured into the graph like everything else, so the timeline is the production schedule's
+struct TopTrace {
+  unsigned long long* d = nullptr;   // 8 slots per step + 1
+  void rec(int step_idx, int which, cudaStream_t st) { k_stamp<<<1, 1, 0, st>>>(d + 1 + (size_t)step_idx * 8 + which); }
+};
+
+static int64_t sh_enqueue_top(parsy_cuda_sharded* sh, TopTrace* tr = nullptr) {
   int64_t l = 0;
   parsy_cuda_solver* h0 = sh->rs[0].h2;
   const int nst = (int)h0->plan.steps.size(), first = h0->plan.first_top_step;
@@ -1498,26 +1518,49 @@ static int64_t sh_enqueue_top(parsy_cuda_sharded* sh) {
       }
     }
   } else {
-    // side (high priority): [F_i on the owner] -> broadcast_i -> A_i     main: R_i after broadcast_i
-    // F_i needs A_{i-1} (stream order) and R_{i-2} (event) — all updates into a block column run on its owner
+    // Streams.  side (high priority): F_i = POTRF + TRSM of the block columns this rank owns, then A_i = updates into
+    // the block columns of step i+1; main: R_i = the other updates of step i; lanes: the broadcasts of step i's panels,
+    // rooted at their owners, round-robin over the lanes.  A_i / R_i wait for the broadcasts only if one of their
+    // tasks reads a panel factored elsewhere (Step::upd_remote): inside an owner's run of consecutive block columns
+    // the chain F_i -> A_i -> F_{i+1} never waits for the network.  Receivers post their broadcasts as early as stream
+    // order allows (nothing local touches a panel owned elsewhere), so a busy rank does not hold up the ring.
+    // F_i needs A_{i-1} (stream order) and R_{i-2} (event) — all updates into a block column run on its owner.
     parsy_cuda_solver* s = h0;
     const Plan& P = s->plan;
+    const int me = sh->rs[0].rank, NL = sh->lanes;
     cudaStream_t mainst = s->stream, side = s->stream2;
     cudaEventRecord(s->ev_fork, mainst);
     cudaStreamWaitEvent(side, s->ev_fork, 0);
+    for (int k = 0; k < NL; ++k) cudaStreamWaitEvent(sh->lane_stream[k], s->ev_fork, 0);
+    if (tr) k_stamp<<<1, 1, 0, mainst>>>(tr->d);
     for (int i = first; i < nst; ++i) {
       const Step& S = P.steps[i];
       if (i - 2 >= first) cudaStreamWaitEvent(side, s->ev_R[(i - 1) & 1], 0);
+      if (tr) tr->rec(i - first, 0, side);
       l += launch_factor_phase(s, S, side, nullptr);
-      sh_step_bcasts(sh, i, side);
       cudaEventRecord(s->ev_F[i & 1], side);
+      if (tr) tr->rec(i - first, 1, side);
+      for (int q = P.bcast_ptr[i]; q < P.bcast_ptr[i + 1]; ++q) {
+        const int lane = q % NL;
+        if ((int)P.bcast[3 * q] == me) cudaStreamWaitEvent(sh->lane_stream[lane], s->ev_F[i & 1], 0);
+        if (tr && q == P.bcast_ptr[i]) tr->rec(i - first, 3, sh->lane_stream[lane]);
+        sh_bcast(sh, (int)P.bcast[3 * q], P.bcast[3 * q + 1], P.bcast[3 * q + 2], sh->lane_stream[lane], lane);
+        if (tr && q + 1 == P.bcast_ptr[i + 1]) tr->rec(i - first, 4, sh->lane_stream[lane]);
+      }
+      for (int k = 0; k < NL; ++k) cudaEventRecord(sh->ev_B[i & 1][k], sh->lane_stream[k]);
+      if (S.upd_remote[0]) for (int k = 0; k < NL; ++k) cudaStreamWaitEvent(side, sh->ev_B[i & 1][k], 0);
       l += launch_update_group(s, S.upd[0], side, nullptr);
+      if (tr) tr->rec(i - first, 2, side);
       cudaStreamWaitEvent(mainst, s->ev_F[i & 1], 0);
+      if (S.upd_remote[1]) for (int k = 0; k < NL; ++k) cudaStreamWaitEvent(mainst, sh->ev_B[i & 1][k], 0);
+      if (tr) tr->rec(i - first, 5, mainst);
       l += launch_update_group(s, S.upd[1], mainst, nullptr);
       cudaEventRecord(s->ev_R[(i + 1) & 1], mainst);
+      if (tr) tr->rec(i - first, 6, mainst);
     }
     cudaEventRecord(s->ev_join, side);
     cudaStreamWaitEvent(mainst, s->ev_join, 0);
+    for (int k = 0; k < NL; ++k) { cudaEventRecord(sh->ev_cjoin[k], sh->lane_stream[k]); cudaStreamWaitEvent(mainst, sh->ev_cjoin[k], 0); }
   }
   // inverse diagonal blocks of the block columns other ranks factored (the sweeps solve with them)
   for (ShardRank& R : sh->rs)
@@ -1574,6 +1617,11 @@ extern "C" void parsy_cuda_sharded_destroy(parsy_cuda_sharded* sh) {
   for (cudaGraphExec_t g : {sh->g_p1, sh->g_sum, sh->g_top, sh->g_fwd, sh->g_bwd}) if (g) cudaGraphExecDestroy(g);
   if (sh->comm) nccl_api()->CommDestroy(sh->comm);
   for (auto& e : sh->ev) if (e) cudaEventDestroy(e);
+  for (int k = 0; k < parsy_cuda_sharded::MAX_LANES; ++k) {
+    for (cudaEvent_t e : {sh->ev_B[0][k], sh->ev_B[1][k], sh->ev_cjoin[k]}) if (e) cudaEventDestroy(e);
+    if (sh->lane_stream[k]) cudaStreamDestroy(sh->lane_stream[k]);
+    if (k && sh->lane_comm[k]) nccl_api()->CommDestroy(sh->lane_comm[k]);
+  }
   if (sh->d_srcs) cudaFree(sh->d_srcs);
   // phase-2 handles and the other emulated ranks borrow streams from the first phase-1 handle: destroy it last
   for (size_t k = sh->rs.size(); k-- > 0;) { parsy_cuda_destroy(sh->rs[k].h2); if (k) parsy_cuda_destroy(sh->rs[k].h1); }
@@ -1614,6 +1662,15 @@ extern "C" int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const 
   }
   sh->stream = sh->rs[0].h1->stream;
   for (auto& e : sh->ev) TRYCU(cudaEventCreate(&e));
+  {
+    int lo = 0, hi = 0;
+    TRYCU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    sh->lanes = opt->reserved[8] > 0 ? std::min((int)parsy_cuda_sharded::MAX_LANES, opt->reserved[8]) : parsy_cuda_sharded::MAX_LANES;
+    for (int k = 0; k < sh->lanes; ++k) {
+      TRYCU(cudaStreamCreateWithPriority(&sh->lane_stream[k], cudaStreamNonBlocking, hi));
+      for (cudaEvent_t* e : {&sh->ev_B[0][k], &sh->ev_B[1][k], &sh->ev_cjoin[k]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+  }
   if (sh->local) TRYCU(cudaMalloc((void**)&sh->d_srcs, sizeof(double*) * (size_t)world));
   // columns a rank zeroes before the final sum of x: everything but its subtrees (rank 0: and the top)
   for (ShardRank& R : sh->rs) {
@@ -1635,12 +1692,24 @@ extern "C" int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const 
     memcpy(&id, nccl_unique_id, sizeof(id));
     ncclResult_t nr = N->CommInitRank(&sh->comm, world, id, opt->rank);
     if (nr != ncclSuccess) { sh->comm = nullptr; parsy_cuda_sharded_destroy(sh); return fail(PARSY_CUDA_ERR_CUDA, std::string("ncclCommInitRank: ") + N->GetErrorString(nr)); }
+    sh->lane_comm[0] = sh->comm;
+    if (!N->CommSplit) sh->lanes = 1;
+    for (int k = 1; k < sh->lanes; ++k) {
+      nr = N->CommSplit(sh->comm, 0, opt->rank, &sh->lane_comm[k], nullptr);
+      if (nr != ncclSuccess) { sh->lane_comm[k] = nullptr; parsy_cuda_sharded_destroy(sh); return fail(PARSY_CUDA_ERR_CUDA, std::string("ncclCommSplit: ") + N->GetErrorString(nr)); }
+    }
     // every collective of a factorization and of the sweeps once outside capture: NCCL sets up its channels and
     // buffers on first use, which must not happen while a stream is being captured
     sh_enqueue_sum(sh);
     const int nst = (int)sh->rs[0].h2->plan.steps.size();
-    if (sh->rs[0].h2->dist_top) for (int i = sh->rs[0].h2->plan.first_top_step; i < nst; ++i) sh_step_bcasts(sh, i, sh->stream);
+    if (sh->rs[0].h2->dist_top) {
+      const Plan& P2 = sh->rs[0].h2->plan;
+      for (int i = P2.first_top_step; i < nst; ++i)
+        for (int q = P2.bcast_ptr[i]; q < P2.bcast_ptr[i + 1]; ++q)
+          sh_bcast(sh, (int)P2.bcast[3 * q], P2.bcast[3 * q + 1], P2.bcast[3 * q + 2], sh->lane_stream[q % sh->lanes], q % sh->lanes);
+    }
     sh_allreduce(sh, 1, 0, n, sh->stream);
+    for (int k = 0; k < sh->lanes; ++k) TRYCU(cudaStreamSynchronize(sh->lane_stream[k]));
     TRYCU(cudaStreamSynchronize(sh->stream));
     if (sh->rc_enqueue) { const int rc2 = sh->rc_enqueue; parsy_cuda_sharded_destroy(sh); return rc2; }
   }
@@ -1693,6 +1762,45 @@ extern "C" int parsy_cuda_sharded_factor(parsy_cuda_sharded* sh) {
   sh->factored = sh->timed = true;
   for (ShardRank& R : sh->rs) R.h1->factored = R.h2->factored = true;
   return PARSY_CUDA_OK;
+}
+
+// Diagnostics: one factorization whose distributed top carries timer probes (captured into a graph exactly like the
+// production schedule).  out[7*k + j], milliseconds since the top phase started on this rank, for step k:
+// j = 0 F begin, 1 F end, 2 A end (chain stream) | 3 first broadcast begin, 4 last broadcast end (lanes) |
+// 5 R begin, 6 R end (bulk stream).  owner_of_step[k] = owner of the step's first block column.  Returns the number of steps.
+extern "C" int parsy_cuda_sharded_trace_top(parsy_cuda_sharded* sh, int max_steps, float* out, int* owner_of_step) {
+  if (!sh || sh->local || !sh->has_values || !sh->rs[0].h2->dist_top || !sh->rs[0].h2->lookahead) { fail(PARSY_CUDA_ERR_STATE, "needs a multi-process handle with a distributed top, look-ahead on, values set"); return -1; }
+  if (cudaSetDevice(sh->device) != cudaSuccess) return -1;
+  cudaStream_t st = sh->stream;
+  const Plan& P = sh->rs[0].h2->plan;
+  const int first = P.first_top_step, nst = (int)P.steps.size() - first;
+  TopTrace tr;
+  const size_t slots = 1 + (size_t)nst * 8;
+  if (cudaMalloc((void**)&tr.d, slots * 8) != cudaSuccess) { fail(PARSY_CUDA_ERR_CUDA, "cudaMalloc"); return -1; }
+  cudaMemsetAsync(tr.d, 0, slots * 8, st);
+  cudaGraphExec_t g = nullptr;
+  int64_t l = 0;
+  int rc = sh_capture(sh, &g, &l, [&] { return sh_enqueue_top(sh, &tr); });
+  if (!rc) {
+    if (sh->g_p1) cudaGraphLaunch(sh->g_p1, st); else sh_enqueue_phase1(sh);
+    if (sh->g_sum) cudaGraphLaunch(sh->g_sum, st); else sh_enqueue_sum(sh);
+    cudaGraphLaunch(g, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = fail(PARSY_CUDA_ERR_CUDA, "trace run failed");
+  }
+  std::vector<unsigned long long> h(slots);
+  if (!rc) cudaMemcpy(h.data(), tr.d, slots * 8, cudaMemcpyDeviceToHost);
+  cudaFree(tr.d);
+  if (g) cudaGraphExecDestroy(g);
+  if (rc) return -1;
+  for (int k = 0; k < nst && k < max_steps; ++k) {
+    for (int j = 0; j < 7; ++j) {
+      const unsigned long long v = h[1 + (size_t)k * 8 + j];
+      out[(size_t)k * 7 + j] = v ? (float)((double)(v - h[0]) * 1e-6) : 0.f;
+    }
+    if (owner_of_step) owner_of_step[k] = P.bcast_ptr[first + k] < P.bcast_ptr[first + k + 1] ? (int)P.bcast[3 * (size_t)P.bcast_ptr[first + k]] : -1;
+  }
+  sh->factored = true;
+  return nst;
 }
 
 extern "C" int parsy_cuda_sharded_sync(parsy_cuda_sharded* sh) {

@@ -472,7 +472,7 @@ class Sharded:
 
     def __init__(self, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition,
                  rank, world, unique_id, device=0, block_cols=0, top_levels=1, top_distributed=True, use_graph=True,
-                 lookahead=True):
+                 lookahead=True, top_chunk=0, lanes=0):
         L = lib()
         self._L = L
         self._h = c_void_p()
@@ -480,6 +480,7 @@ class Sharded:
         opt.device, opt.block_cols, opt.use_graph = int(device), int(block_cols), int(use_graph)
         opt.rank, opt.world = int(rank), int(world)
         opt.reserved[0], opt.reserved[3], opt.reserved[4] = int(not lookahead), int(top_levels), int(not top_distributed)
+        opt.reserved[7], opt.reserved[8] = int(top_chunk), int(lanes)      # 0 = library defaults
         f = L.parsy_cuda_sharded_create
         f.restype = c_int
         f.argtypes = [POINTER(c_void_p), c_int] + [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + \
@@ -551,6 +552,18 @@ class Sharded:
         keys = ("launches_factor", "nccl_broadcasts", "nccl_allreduces", "bytes_broadcast", "bytes_summed", "device_bytes",
                 "top_chain_steps", "nccl_version", "launches_fwd", "launches_bwd", "owned_supernodes", "top_supernodes")
         return {k: int(x) for k, x in zip(keys, v)}
+
+    def trace_top(self, max_steps=4096):
+        """(times[steps, 7] in ms, owner[steps]) of one un-graphed factorization: see parsy_cuda_sharded_trace_top."""
+        out = np.zeros((max_steps, 7), np.float32)
+        own = np.zeros(max_steps, np.int32)
+        f = self._L.parsy_cuda_sharded_trace_top
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+        cnt = f(self._h, int(max_steps), out.ctypes.data_as(c_void_p), own.ctypes.data_as(c_void_p))
+        if cnt < 0:
+            raise ParsyCudaError(ERR_STATE, "parsy_cuda_sharded_trace_top")
+        return out[:min(cnt, max_steps)], own[:min(cnt, max_steps)]
 
     def plan(self, phase, emulated_rank=0):
         f = self._L.parsy_cuda_sharded_plan
