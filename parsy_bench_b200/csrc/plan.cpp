@@ -233,7 +233,11 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   bool src_remote = false;
   std::vector<Gen> gen;
   gen.reserve(P.pairs.size() + 3 * (size_t)o_blk[nsteps]);
-  auto emit_update = [&](const GemmTask& t, int st, int grp, bool real_pair) {
+  // group of an update by the step its target is factored at: 0 = the very next step ("A", on the chain), 1 = soon
+  // ("R"), 2 = at least FAR_STEPS later ("far": distributed top only — runs on its own low-priority stream and is
+  // awaited FAR_STEPS steps later, so bursts of separator-to-separator updates do not stall the chain)
+  auto emit_update = [&](const GemmTask& t, int st, int tstep, bool real_pair) {
+    const int grp = tstep <= st + 1 ? 0 : ((dist_top && tstep >= st + FAR_STEPS) ? 2 : 1);
     Gen g; g.t = t; g.step = st; g.grp = (int8_t)grp;
     if (src_remote) P.steps[st].upd_remote[grp] = 1;
     const double fl = upd_flops(t);
@@ -301,7 +305,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
           t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb + c0; t.b_off = t.a_off;
           t.c_off = I.valptr + (int64_t)(j0 + nb + c0) * I.r + j0 + nb + c0;
           t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = Mb - c0; t.N = c1 - c0; t.K = nb; t.flags = GF_LOWER;
-          emit_update(t, st, b3 == b2 + 1 ? 0 : 1, false);
+          emit_update(t, st, st + (b3 - b2), false);
         }
       } else if (Nt > 0) {
         // columns of the next block column first ("A"), the remainder of the trapezoid separately ("R")
@@ -310,11 +314,11 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = t.a_off;
         t.c_off = I.valptr + (int64_t)(j0 + nb) * I.r + j0 + nb;
         t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = Mb; t.N = n1; t.K = nb; t.flags = GF_LOWER;
-        emit_update(t, st, 0, false);
+        emit_update(t, st, st + 1, false);
         if (Nt > n1) {
           GemmTask u = t;
           u.a_off += n1; u.b_off += n1; u.c_off += (int64_t)n1 * I.r + n1; u.M = Mb - n1; u.N = Nt - n1;
-          emit_update(u, st, 1, false);
+          emit_update(u, st, st + 2, false);
         }
       }
     }
@@ -336,7 +340,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     rel += q.m;
     if (!pair_active(q.src, q.tgt)) continue;
     src_remote = false;
-    if (!dist_top) { emit_update(t, st, step0[q.tgt] == st + 1 ? 0 : 1, true); continue; }
+    if (!dist_top) { emit_update(t, st, step0[q.tgt], true); continue; }
     // Distributed top.  (i) The pair's columns are split by the target block column they fall into; a rank keeps what
     // it owns.  (ii) A wide source is applied in K-chunks of PAIR_KBLK block columns as they are finished instead of
     // in one K = width task after its last block column: the ancestors' updates then overlap the source's own chain
@@ -357,7 +361,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
           u.a_off += n0 + (int64_t)k0 * D.r; u.b_off = u.a_off; u.rel_off += n0; u.M = q.m - n0; u.N = n1 - n0; u.K = k1 - k0;
           src_remote = false;
           for (int kb = kb0; kb < kb1; ++kb) if (P.node_owner[node_first[q.src] + kb] != opt.rank) src_remote = true;
-          emit_update(u, stq, step0[q.tgt] + tb == stq + 1 ? 0 : 1, true);
+          emit_update(u, stq, step0[q.tgt] + tb, true);
         }
       }
       n0 = n1;
@@ -372,15 +376,15 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   // critical path of a separator are the typical case)
   {
     constexpr int SMS = 148;
-    std::vector<int32_t> tdef(2 * (size_t)nsteps, 0), t64(2 * (size_t)nsteps, 0);
+    std::vector<int32_t> tdef(3 * (size_t)nsteps, 0), t64(3 * (size_t)nsteps, 0);
     for (const Gen& g : gen) {
       if (g.cls != 1 && g.cls != 2) continue;
-      tdef[2 * g.step + g.grp] += g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : lower_tiles(g.t.M, g.t.N, 64, 64);
-      t64[2 * g.step + g.grp] += lower_tiles(g.t.M, g.t.N, 64, 64);
+      tdef[3 * g.step + g.grp] += g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : lower_tiles(g.t.M, g.t.N, 64, 64);
+      t64[3 * g.step + g.grp] += lower_tiles(g.t.M, g.t.N, 64, 64);
     }
     for (Gen& g : gen) {
       if (g.cls != 1 && g.cls != 2) continue;
-      const int k = 2 * g.step + g.grp;
+      const int k = 3 * g.step + g.grp;
       if (tdef[k] >= SMS) continue;
       const double fl = upd_flops(g.t);
       const int ncls = t64[k] >= SMS ? 2 : 4;
@@ -393,15 +397,15 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   // K (wide descendants) set the duration; the epilogue is an atomic add, so K can be cut into independent pieces
   {
     constexpr int FILL = 2 * 148;
-    std::vector<int32_t> tl(2 * (size_t)nsteps, 0);
+    std::vector<int32_t> tl(3 * (size_t)nsteps, 0);
     auto ntiles = [&](const Gen& g) {
       return g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : g.cls == 2 ? lower_tiles(g.t.M, g.t.N, 64, 64) : lower_tiles(g.t.M, g.t.N, 32, 32);
     };
-    for (const Gen& g : gen) if (g.cls == 1 || g.cls == 2 || g.cls == 4) tl[2 * g.step + g.grp] += ntiles(g);
+    for (const Gen& g : gen) if (g.cls == 1 || g.cls == 2 || g.cls == 4) tl[3 * g.step + g.grp] += ntiles(g);
     const size_t n0 = gen.size();
     for (size_t i = 0; i < n0; ++i) {
       if ((gen[i].cls != 1 && gen[i].cls != 2 && gen[i].cls != 4) || gen[i].t.K < 128) continue;
-      const int total = tl[2 * gen[i].step + gen[i].grp];
+      const int total = tl[3 * gen[i].step + gen[i].grp];
       if (total >= FILL) continue;
       const int K = gen[i].t.K;
       const int f = std::min(std::min(cdiv(K, 64), cdiv(FILL, std::max(total, 1))), 8);
@@ -434,16 +438,16 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         return Range{b0, (int32_t)i};
       };
       S.trsm = take(0, 0);
-      for (int g = 0; g < 2; ++g) S.upd[g].u128 = take(1, g);
-      for (int g = 0; g < 2; ++g) S.upd[g].u64 = take(2, g);
-      for (int g = 0; g < 2; ++g) S.upd[g].small_pairs = take(3, g);
-      for (int g = 0; g < 2; ++g) S.upd[g].u32 = take(4, g);
+      for (int g = 0; g < 3; ++g) S.upd[g].u128 = take(1, g);
+      for (int g = 0; g < 3; ++g) S.upd[g].u64 = take(2, g);
+      for (int g = 0; g < 3; ++g) S.upd[g].small_pairs = take(3, g);
+      for (int g = 0; g < 3; ++g) S.upd[g].u32 = take(4, g);
     }
   }
   std::vector<Gen>().swap(gen);
   // row chunks of the small pairs, narrow (K <= 4) first inside every (step, group)
   for (int st = 0; st < nsteps; ++st)
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < 3; ++g) {
       UpdGroup& U = P.steps[st].upd[g];
       U.small.begin = (int32_t)P.small_tasks.size();
       for (int pass = 0; pass < 2; ++pass) {
@@ -483,7 +487,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     acc = 0;
     for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, S.trsm_tm); }
     S.trsm_tiles = acc;
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < 3; ++g) {
       UpdGroup& U = S.upd[g];
       acc = 0;
       for (int i = U.u128.begin; i < U.u128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128, 64); }
@@ -504,6 +508,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   P.bcast_ptr.assign(nsteps + 1, 0);
   if (dist_top) {
     std::vector<std::vector<int64_t>> per(nsteps);
+    std::vector<std::vector<int32_t>> shp(nsteps);
     for (int s = 0; s < supNo; ++s) {
       if (P.owner[s] >= 0) continue;
       const SupInfo& I = P.sup[s];
@@ -513,10 +518,13 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         v.push_back(P.node_owner[node_first[s] + b2]);
         v.push_back(I.valptr + (int64_t)j0 * I.r);
         v.push_back(I.valptr + (int64_t)(j0 + nb) * I.r);
+        auto& h = shp[step0[s] + b2];
+        h.push_back(j0); h.push_back(I.r); h.push_back(nb);
       }
     }
     for (int st = 0; st < nsteps; ++st) {
       P.bcast.insert(P.bcast.end(), per[st].begin(), per[st].end());
+      P.bcast_shape.insert(P.bcast_shape.end(), shp[st].begin(), shp[st].end());
       P.bcast_ptr[st + 1] = (int32_t)(P.bcast.size() / 3);
     }
   }

@@ -21,6 +21,7 @@ constexpr int SMALL_W = 32;       // widest supernode handled by the warp-cooper
 constexpr int SMALL_R = 1024;     // ... and its largest row count
 constexpr int64_t SMALL_WORK = 100000;   // ... and the bound on (rows below) * width^2 one warp is asked to do
 constexpr int SMALL_W_NARROW = 8;        // supernodes / pairs at most this wide run in the low-register kernels
+constexpr int FAR_STEPS = 8;      // see Step::upd
 constexpr int NB_MAX = 128;       // largest block-column width (POTRF tile held in shared memory)
 
 enum GemmFlags : int32_t {
@@ -136,8 +137,9 @@ struct Step {
   Range trsm;        // into gemm_tasks (T128, GF_OVERWRITE|GF_B_LINV)
   int32_t trsm_tiles = 0;
   int32_t trsm_tm = 64;      // row-tile height of this step's TRSM launch (64, 32 or 16)
-  UpdGroup upd[2];   // [0] targets factored in the next step ("A"), [1] everything else ("R")
-  int8_t upd_remote[2] = {0, 0};   // distributed top: the group reads a panel another rank factors (wait for the broadcast)
+  UpdGroup upd[3];   // [0] targets factored in the next step ("A"), [1] the others ("R"); distributed top only:
+                     // [2] targets at least FAR_STEPS steps away ("far", own stream)
+  int8_t upd_remote[3] = {0, 0, 0};   // distributed top: the group reads a panel another rank factors (wait for the broadcast)
   int32_t solve_tiles = 0;   // row tiles of the block tasks (forward / backward sweeps)
   int32_t max_nb = 0;        // widest block column in this step
 };
@@ -187,6 +189,8 @@ struct Plan {
   std::vector<int32_t> bcast_ptr;           // per step: range in bcast (phase 2, distributed top)
   std::vector<int64_t> bcast;               // triples (owner, begin, end) in doubles: panels the owner broadcasts once the
                                             // step's block columns are factored
+  std::vector<int32_t> bcast_shape;         // per broadcast: (j0, rows of the supernode, block-column width) — rows above
+                                            // j0 of a block column are structural zeros and need not travel
   std::vector<BlockTask> invert_tasks;      // phase 2, distributed top: block columns factored by OTHER ranks; their inverse
                                             // diagonal blocks (diagonal solves of the sweeps) are rebuilt locally
   std::vector<int64_t> zero_runs;           // pairs (begin, end) in doubles: what a factorization zeroes first

@@ -138,7 +138,8 @@ struct Fan {
   cudaStream_t st;
   int set, used = 0, count = 0;
   bool on;
-  Fan(parsy_cuda_solver* s_, cudaStream_t st_, bool on_) : s(s_), st(st_), set(st_ == s_->stream2 ? 0 : 1), on(on_ && s_->fan_out) {
+  Fan(parsy_cuda_solver* s_, cudaStream_t st_, bool on_) : s(s_), st(st_), set(st_ == s_->stream2 ? 0 : 1),
+      on(on_ && s_->fan_out && (st_ == s_->stream || st_ == s_->stream2)) {   // other streams (far updates) keep to themselves
     if (on) cudaEventRecord(s->ev_fan_fork[set], st);
   }
   cudaStream_t pick() {
@@ -260,7 +261,7 @@ static int64_t launch_update_group(parsy_cuda_solver* s, const UpdGroup& U, cuda
 //   overlaps the latency-bound POTRF/TRSM of the next block column (look-ahead of depth one).
 static bool step_has_work(const Step& S) {
   if (S.blocks_owned || S.small_sup.size() || S.trsm_tiles) return true;
-  for (int g = 0; g < 2; ++g)
+  for (int g = 0; g < 3; ++g)
     if (S.upd[g].tiles128 || S.upd[g].tiles64 || S.upd[g].tiles32 || S.upd[g].small.size()) return true;
   return false;
 }
@@ -1413,7 +1414,10 @@ struct parsy_cuda_sharded {
   cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_B[2][MAX_LANES] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
   cudaEvent_t ev_cjoin[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
-  int64_t bcast_seq = 0;
+  double* lane_stage[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};   // packed panels (rows from the diagonal block down)
+  int64_t stage_doubles = 0;
+  cudaStream_t far_stream = nullptr;          // "far" updates (Step::upd[2]) of the distributed top, low priority
+  cudaEvent_t ev_far[FAR_STEPS] = {}, ev_farjoin = nullptr;
   cudaGraphExec_t g_p1 = nullptr, g_sum = nullptr, g_top = nullptr, g_fwd = nullptr, g_bwd = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   const double** d_srcs = nullptr;    // local mode: the ranks' factor / rhs buffers (k_sum_buffers)
@@ -1485,10 +1489,42 @@ static int64_t sh_enqueue_sum(parsy_cuda_sharded* sh) {
   if (!sh->local) nccl_api()->GroupEnd();
   return 0;
 }
+// Broadcast q of the plan (one block column of a top separator).  The rows above the block column's diagonal block are
+// structural zeros: when they are a sizeable part of the panel, only rows j0.. travel — packed into the lane's staging
+// buffer by a strided device copy on the root, unpacked the same way on the receivers.
+static void sh_bcast_panel(parsy_cuda_sharded* sh, int q, cudaStream_t st, int lane) {
+  const Plan& P = sh->rs[0].h2->plan;
+  const int root = (int)P.bcast[3 * (size_t)q];
+  const int64_t begin = P.bcast[3 * (size_t)q + 1], end = P.bcast[3 * (size_t)q + 2];
+  const int64_t j0 = P.bcast_shape[3 * (size_t)q], r = P.bcast_shape[3 * (size_t)q + 1], nb = P.bcast_shape[3 * (size_t)q + 2];
+  const bool pack = !sh->local && sh->lane_stage[lane] && j0 * 8 >= r && (r - j0) * nb <= sh->stage_doubles;
+  if (!pack) {
+    if (sh->local && j0 > 0) {
+      // emulated ranks: the same rows, as strided copies between the ranks' buffers
+      for (const ShardRank& R : sh->rs)
+        if (R.rank != root)
+          cudaMemcpy2DAsync(R.h1->d_lv + begin + j0, (size_t)r * 8, sh->rs[root].h1->d_lv + begin + j0, (size_t)r * 8,
+                            (size_t)(r - j0) * 8, (size_t)nb, cudaMemcpyDeviceToDevice, st);
+      sh->n_bcast++; sh->bytes_bcast += 8 * (r - j0) * nb;
+      return;
+    }
+    sh_bcast(sh, root, begin, end, st, lane);
+    return;
+  }
+  double* lv = sh->rs[0].h1->d_lv;
+  double* stage = sh->lane_stage[lane];
+  const size_t rows = (size_t)(r - j0);
+  if (sh->rs[0].rank == root)
+    cudaMemcpy2DAsync(stage, rows * 8, lv + begin + j0, (size_t)r * 8, rows * 8, (size_t)nb, cudaMemcpyDeviceToDevice, st);
+  const ncclResult_t rc = nccl_api()->Broadcast(stage, stage, rows * (size_t)nb, ncclDouble, root, sh->lane_comm[lane], st);
+  if (rc != ncclSuccess && !sh->rc_enqueue) sh->rc_enqueue = fail(PARSY_CUDA_ERR_CUDA, std::string("ncclBroadcast: ") + nccl_api()->GetErrorString(rc));
+  if (sh->rs[0].rank != root)
+    cudaMemcpy2DAsync(lv + begin + j0, (size_t)r * 8, stage, rows * 8, rows * 8, (size_t)nb, cudaMemcpyDeviceToDevice, st);
+  sh->n_bcast++; sh->bytes_bcast += 8 * (int64_t)rows * nb;
+}
 static void sh_step_bcasts(parsy_cuda_sharded* sh, int step, cudaStream_t st) {
   const Plan& P = sh->rs[0].h2->plan;
-  for (int i = P.bcast_ptr[step]; i < P.bcast_ptr[step + 1]; ++i)
-    sh_bcast(sh, (int)P.bcast[3 * i], P.bcast[3 * i + 1], P.bcast[3 * i + 2], st);
+  for (int i = P.bcast_ptr[step]; i < P.bcast_ptr[step + 1]; ++i) sh_bcast_panel(sh, i, st, 0);
 }
 // optional timeline of the distributed top (parsy_cuda_sharded_trace_top): one-thread kernels that store the GPU timer,
 // captured into the graph like everything else, so the timeline is the production schedule's
@@ -1513,8 +1549,7 @@ static int64_t sh_enqueue_top(parsy_cuda_sharded* sh, TopTrace* tr = nullptr) {
       for (ShardRank& R : sh->rs) l += launch_factor_phase(R.h2, R.h2->plan.steps[i], st, nullptr);
       sh_step_bcasts(sh, i, st);
       for (ShardRank& R : sh->rs) {
-        l += launch_update_group(R.h2, R.h2->plan.steps[i].upd[0], st, nullptr);
-        l += launch_update_group(R.h2, R.h2->plan.steps[i].upd[1], st, nullptr);
+        for (int g = 0; g < 3; ++g) l += launch_update_group(R.h2, R.h2->plan.steps[i].upd[g], st, nullptr);
       }
     }
   } else {
@@ -1532,10 +1567,14 @@ static int64_t sh_enqueue_top(parsy_cuda_sharded* sh, TopTrace* tr = nullptr) {
     cudaEventRecord(s->ev_fork, mainst);
     cudaStreamWaitEvent(side, s->ev_fork, 0);
     for (int k = 0; k < NL; ++k) cudaStreamWaitEvent(sh->lane_stream[k], s->ev_fork, 0);
+    cudaStream_t far = sh->far_stream;
+    cudaStreamWaitEvent(far, s->ev_fork, 0);
     if (tr) k_stamp<<<1, 1, 0, mainst>>>(tr->d);
     for (int i = first; i < nst; ++i) {
       const Step& S = P.steps[i];
       if (i - 2 >= first) cudaStreamWaitEvent(side, s->ev_R[(i - 1) & 1], 0);
+      // far updates issued FAR_STEPS steps ago (and, the stream being in order, all earlier ones) target this step at the earliest
+      if (i - FAR_STEPS >= first) cudaStreamWaitEvent(side, sh->ev_far[i % FAR_STEPS], 0);
       if (tr) tr->rec(i - first, 0, side);
       l += launch_factor_phase(s, S, side, nullptr);
       cudaEventRecord(s->ev_F[i & 1], side);
@@ -1544,7 +1583,7 @@ static int64_t sh_enqueue_top(parsy_cuda_sharded* sh, TopTrace* tr = nullptr) {
         const int lane = q % NL;
         if ((int)P.bcast[3 * q] == me) cudaStreamWaitEvent(sh->lane_stream[lane], s->ev_F[i & 1], 0);
         if (tr && q == P.bcast_ptr[i]) tr->rec(i - first, 3, sh->lane_stream[lane]);
-        sh_bcast(sh, (int)P.bcast[3 * q], P.bcast[3 * q + 1], P.bcast[3 * q + 2], sh->lane_stream[lane], lane);
+        sh_bcast_panel(sh, q, sh->lane_stream[lane], lane);
         if (tr && q + 1 == P.bcast_ptr[i + 1]) tr->rec(i - first, 4, sh->lane_stream[lane]);
       }
       for (int k = 0; k < NL; ++k) cudaEventRecord(sh->ev_B[i & 1][k], sh->lane_stream[k]);
@@ -1557,7 +1596,18 @@ static int64_t sh_enqueue_top(parsy_cuda_sharded* sh, TopTrace* tr = nullptr) {
       l += launch_update_group(s, S.upd[1], mainst, nullptr);
       cudaEventRecord(s->ev_R[(i + 1) & 1], mainst);
       if (tr) tr->rec(i - first, 6, mainst);
+      {
+        const UpdGroup& Fg = S.upd[2];
+        if (Fg.tiles128 || Fg.tiles64 || Fg.tiles32 || Fg.small.size()) {
+          cudaStreamWaitEvent(far, s->ev_F[i & 1], 0);
+          if (S.upd_remote[2]) for (int k = 0; k < NL; ++k) cudaStreamWaitEvent(far, sh->ev_B[i & 1][k], 0);
+          l += launch_update_group(s, Fg, far, nullptr);
+        }
+        cudaEventRecord(sh->ev_far[i % FAR_STEPS], far);
+      }
     }
+    cudaEventRecord(sh->ev_farjoin, far);
+    cudaStreamWaitEvent(mainst, sh->ev_farjoin, 0);
     cudaEventRecord(s->ev_join, side);
     cudaStreamWaitEvent(mainst, s->ev_join, 0);
     for (int k = 0; k < NL; ++k) { cudaEventRecord(sh->ev_cjoin[k], sh->lane_stream[k]); cudaStreamWaitEvent(mainst, sh->ev_cjoin[k], 0); }
@@ -1617,6 +1667,10 @@ extern "C" void parsy_cuda_sharded_destroy(parsy_cuda_sharded* sh) {
   for (cudaGraphExec_t g : {sh->g_p1, sh->g_sum, sh->g_top, sh->g_fwd, sh->g_bwd}) if (g) cudaGraphExecDestroy(g);
   if (sh->comm) nccl_api()->CommDestroy(sh->comm);
   for (auto& e : sh->ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : sh->ev_far) if (e) cudaEventDestroy(e);
+  if (sh->ev_farjoin) cudaEventDestroy(sh->ev_farjoin);
+  if (sh->far_stream) cudaStreamDestroy(sh->far_stream);
+  for (double* p : sh->lane_stage) if (p) cudaFree(p);
   for (int k = 0; k < parsy_cuda_sharded::MAX_LANES; ++k) {
     for (cudaEvent_t e : {sh->ev_B[0][k], sh->ev_B[1][k], sh->ev_cjoin[k]}) if (e) cudaEventDestroy(e);
     if (sh->lane_stream[k]) cudaStreamDestroy(sh->lane_stream[k]);
@@ -1665,6 +1719,9 @@ extern "C" int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const 
   {
     int lo = 0, hi = 0;
     TRYCU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TRYCU(cudaStreamCreateWithPriority(&sh->far_stream, cudaStreamNonBlocking, lo));
+    for (auto& e : sh->ev_far) TRYCU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TRYCU(cudaEventCreateWithFlags(&sh->ev_farjoin, cudaEventDisableTiming));
     sh->lanes = opt->reserved[8] > 0 ? std::min((int)parsy_cuda_sharded::MAX_LANES, opt->reserved[8]) : parsy_cuda_sharded::MAX_LANES;
     for (int k = 0; k < sh->lanes; ++k) {
       TRYCU(cudaStreamCreateWithPriority(&sh->lane_stream[k], cudaStreamNonBlocking, hi));
@@ -1684,6 +1741,16 @@ extern "C" int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const 
       if (z && b < 0) b = j;
       if (!z && b >= 0) { R.gather_zero.push_back(b); R.gather_zero.push_back(j); b = -1; }
     }
+  }
+  if (!sh->local && sh->rs[0].h2->dist_top && opt->reserved[9] == 0) {   // reserved[9] = 1: broadcast whole block columns
+    const Plan& P2 = sh->rs[0].h2->plan;
+    int64_t mx = 0;
+    for (size_t q = 0; q < P2.bcast_shape.size() / 3; ++q) {
+      const int64_t j0 = P2.bcast_shape[3 * q], r = P2.bcast_shape[3 * q + 1], nb = P2.bcast_shape[3 * q + 2];
+      if (j0 * 8 >= r) mx = std::max(mx, (r - j0) * nb);
+    }
+    sh->stage_doubles = mx;
+    for (int k = 0; k < sh->lanes && mx > 0; ++k) TRYCU(cudaMalloc((void**)&sh->lane_stage[k], (size_t)mx * 8));
   }
   if (!sh->local) {
     NcclApi* N = nccl_api();
@@ -1706,7 +1773,7 @@ extern "C" int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const 
       const Plan& P2 = sh->rs[0].h2->plan;
       for (int i = P2.first_top_step; i < nst; ++i)
         for (int q = P2.bcast_ptr[i]; q < P2.bcast_ptr[i + 1]; ++q)
-          sh_bcast(sh, (int)P2.bcast[3 * q], P2.bcast[3 * q + 1], P2.bcast[3 * q + 2], sh->lane_stream[q % sh->lanes], q % sh->lanes);
+          sh_bcast_panel(sh, q, sh->lane_stream[q % sh->lanes], q % sh->lanes);
     }
     sh_allreduce(sh, 1, 0, n, sh->stream);
     for (int k = 0; k < sh->lanes; ++k) TRYCU(cudaStreamSynchronize(sh->lane_stream[k]));
@@ -1727,7 +1794,11 @@ extern "C" int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const 
   {
     const Plan& P1 = sh->rs[0].h1->plan; const Plan& P2 = sh->rs[0].h2->plan;
     for (size_t k = 0; k + 1 < P1.top_runs.size(); k += 2) { sh->n_allreduce++; sh->bytes_sum += 8 * (P1.top_runs[k + 1] - P1.top_runs[k]); }
-    for (size_t i = 0; i < P2.bcast.size() / 3; ++i) { sh->n_bcast++; sh->bytes_bcast += 8 * (P2.bcast[3 * i + 2] - P2.bcast[3 * i + 1]); }
+    for (size_t i = 0; i < P2.bcast.size() / 3; ++i) {
+      const int64_t j0 = P2.bcast_shape[3 * i], r = P2.bcast_shape[3 * i + 1], nb = P2.bcast_shape[3 * i + 2];
+      const bool pack = sh->lane_stage[0] && j0 * 8 >= r && (r - j0) * nb <= sh->stage_doubles;
+      sh->n_bcast++; sh->bytes_bcast += pack ? 8 * (r - j0) * nb : 8 * (P2.bcast[3 * i + 2] - P2.bcast[3 * i + 1]);
+    }
   }
   TRYCU(cudaStreamSynchronize(sh->stream));
   *out = sh;
