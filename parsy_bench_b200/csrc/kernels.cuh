@@ -23,6 +23,10 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool pre
   const int sz = pred ? 8 : 0;   // src-size 0 => zero-fill, nothing is read
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
 }
+// same with a 32-bit shared-window address computed by the caller (hoisted out of the K loop)
+__device__ __forceinline__ void cp_async8_s(unsigned saddr, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(saddr), "l"(gmem), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
@@ -103,24 +107,44 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) k_gemm_tiles(const Ge
     srel[i] = v;
   }
 
-  auto load_chunk = [&](int kc, int stage) {
-    double* As = smem + stage * C::STAGE_DOUBLES;
-    double* Bs = As + C::KC * C::LDA;
-    const int k0 = kc * C::KC;
+  // Operand staging.  Every thread copies the same tile row (ia / jb) of RA / RB consecutive k-columns per pass, so the
+  // row predicate, the shared-memory address and the global pointer are set up once per tile; a K-chunk is then
+  // KC/RA + KC/RB copies at fixed strides (the per-element index arithmetic of a generic loop cost ~20 instructions
+  // per 8-byte copy — more issue slots than the DMMAs themselves).  Only a partial last chunk tests k < K per copy.
+  constexpr int RA = C::THREADS / C::TM, NA = C::KC / RA, RB = C::THREADS / C::TN, NBP = C::KC / RB;
+  static_assert(C::THREADS % C::TM == 0 && C::THREADS % C::TN == 0 && C::KC % RA == 0 && C::KC % RB == 0 && NA >= 1 && NBP >= 1,
+                "tile shape must give every thread a fixed operand row");
+  const int ia = tid % C::TM, ka = tid / C::TM, jb = tid % C::TN, kb = tid / C::TN;
+  const int szA = ia < mrows ? 8 : 0, szB = jb < nrows ? 8 : 0;     // src-size 0: zero-fill, nothing is read
+  const double* pA = A + (int64_t)ka * lda + (szA ? ia : 0);
+  const double* pB = B + (int64_t)kb * ldb + (szB ? jb : 0);
+  const int64_t passA = (int64_t)RA * lda, passB = (int64_t)RB * ldb;
+  const unsigned s0 = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned sA = s0 + (unsigned)(ka * C::LDA + ia) * 8u;
+  const unsigned sB = s0 + (unsigned)(C::KC * C::LDA + kb * C::LDB + jb) * 8u;
+  int k_next = 0;                                                    // chunks are loaded in increasing order
+  auto load_chunk = [&](int /*kc*/, int stage) {
+    const unsigned so = (unsigned)stage * (unsigned)(C::STAGE_DOUBLES * 8);
+    if (k_next + C::KC <= K) {
 #pragma unroll
-    for (int e = tid; e < C::KC * C::TM; e += C::THREADS) {
-      const int kk = e / C::TM, i = e % C::TM;
-      const bool p = (i < mrows) && (k0 + kk < K);
-      const double* src = p ? (A + (int64_t)(k0 + kk) * lda + i) : lv;
-      cp_async8(&As[kk * C::LDA + i], src, p);
-    }
+      for (int u = 0; u < NA; ++u) cp_async8_s(sA + so + (unsigned)(u * RA * C::LDA * 8), pA + u * passA, szA);
 #pragma unroll
-    for (int e = tid; e < C::KC * C::TN; e += C::THREADS) {
-      const int kk = e / C::TN, j = e % C::TN;
-      const bool p = (j < nrows) && (k0 + kk < K);
-      const double* src = p ? (B + (int64_t)(k0 + kk) * ldb + j) : lv;
-      cp_async8(&Bs[kk * C::LDB + j], src, p);
+      for (int u = 0; u < NBP; ++u) cp_async8_s(sB + so + (unsigned)(u * RB * C::LDB * 8), pB + u * passB, szB);
+    } else {
+#pragma unroll
+      for (int u = 0; u < NA; ++u) {
+        const bool in = k_next + ka + u * RA < K;
+        cp_async8_s(sA + so + (unsigned)(u * RA * C::LDA * 8), in ? (const void*)(pA + u * passA) : (const void*)lv, in ? szA : 0);
+      }
+#pragma unroll
+      for (int u = 0; u < NBP; ++u) {
+        const bool in = k_next + kb + u * RB < K;
+        cp_async8_s(sB + so + (unsigned)(u * RB * C::LDB * 8), in ? (const void*)(pB + u * passB) : (const void*)lv, in ? szB : 0);
+      }
     }
+    k_next += C::KC;
+    pA += (int64_t)C::KC * lda;
+    pB += (int64_t)C::KC * ldb;
   };
 
   const int nchunks = (K + C::KC - 1) / C::KC;

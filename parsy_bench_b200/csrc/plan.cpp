@@ -287,39 +287,49 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       }
     }
   }
-  // trailing updates inside a supernode: block column b2's panel into the later block columns
+  // Trailing updates inside a wide supernode.  Block columns are grouped in runs of TRAIL_KBLK.  The panel of block
+  // column b is applied right away (K = one block column) only to the targets that are factored soon — b+1 ("A", on
+  // the chain) and the rest of b's run plus the first block column of the next run; everything further right receives
+  // the whole run at once when its last block column is finished (K = TRAIL_KBLK block columns): four times fewer
+  // scatter epilogues and operand re-reads per flop than rank-128 updates, with the same dependencies.
+  constexpr int TRAIL_KBLK = 4;
+  auto emit_trailing = [&](int s, int kb0, int kb1, int tb0, int tb1, int st, int tstep) {
+    const SupInfo& I = P.sup[s];
+    const int k0 = kb0 * NB, k1 = std::min(I.w, kb1 * NB), c0 = tb0 * NB, c1 = std::min(I.w, tb1 * NB);
+    if (k1 <= k0 || c1 <= c0) return;
+    GemmTask t; memset(&t, 0, sizeof(t));
+    t.a_off = I.valptr + (int64_t)k0 * I.r + c0; t.b_off = t.a_off;
+    t.c_off = I.valptr + (int64_t)c0 * I.r + c0;
+    t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = I.r - c0; t.N = c1 - c0; t.K = k1 - k0; t.flags = GF_LOWER;
+    emit_update(t, st, tstep, false);
+  };
   for (int s = 0; s < supNo; ++s) {
     const SupInfo& I = P.sup[s];
     if (!sup_active(s) || I.flags) continue;
-    for (int b2 = 0; b2 < nblk[s]; ++b2) {
-      const int st = step0[s] + b2, j0 = b2 * NB, nb = std::min(NB, I.w - j0);
-      const int Mb = I.r - j0 - nb;
-      const int Nt = I.w - j0 - nb;   // trailing columns of the same supernode
-      if (Nt > 0 && dist_top) {
-        // one task per later block column, kept only if this rank owns that block column
-        for (int b3 = b2 + 1; b3 < nblk[s]; ++b3) {
+    const int nbk = nblk[s];
+    for (int b2 = 0; b2 < nbk; ++b2) {
+      const int st = step0[s] + b2;
+      const int g0 = (b2 / TRAIL_KBLK) * TRAIL_KBLK, g1 = std::min(nbk, g0 + TRAIL_KBLK);
+      const int near_end = std::min(nbk, g1 + 1);          // targets b2+1 .. near_end-1 get this panel alone
+      const bool run_done = b2 == g1 - 1 && g1 + 1 < nbk;  // targets g1+1 .. get the whole run now
+      if (dist_top) {
+        // one task per target block column, kept only if this rank owns that block column
+        auto remote = [&](int kb0, int kb1) { for (int kb = kb0; kb < kb1; ++kb) if (P.node_owner[node_first[s] + kb] != opt.rank) return true; return false; };
+        for (int b3 = b2 + 1; b3 < near_end; ++b3) {
           if (P.node_owner[node_first[s] + b3] != opt.rank) continue;
-          src_remote = P.node_owner[node_first[s] + b2] != opt.rank;
-          const int c0 = (b3 - b2 - 1) * NB, c1 = std::min(Nt, c0 + NB);
-          GemmTask t; memset(&t, 0, sizeof(t));
-          t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb + c0; t.b_off = t.a_off;
-          t.c_off = I.valptr + (int64_t)(j0 + nb + c0) * I.r + j0 + nb + c0;
-          t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = Mb - c0; t.N = c1 - c0; t.K = nb; t.flags = GF_LOWER;
-          emit_update(t, st, st + (b3 - b2), false);
+          src_remote = remote(b2, b2 + 1);
+          emit_trailing(s, b2, b2 + 1, b3, b3 + 1, st, step0[s] + b3);
         }
-      } else if (Nt > 0) {
-        // columns of the next block column first ("A"), the remainder of the trapezoid separately ("R")
-        const int n1 = std::min(Nt, NB);
-        GemmTask t; memset(&t, 0, sizeof(t));
-        t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = t.a_off;
-        t.c_off = I.valptr + (int64_t)(j0 + nb) * I.r + j0 + nb;
-        t.rel_off = -1; t.lda = t.ldb = t.ldc = I.r; t.M = Mb; t.N = n1; t.K = nb; t.flags = GF_LOWER;
-        emit_update(t, st, st + 1, false);
-        if (Nt > n1) {
-          GemmTask u = t;
-          u.a_off += n1; u.b_off += n1; u.c_off += (int64_t)n1 * I.r + n1; u.M = Mb - n1; u.N = Nt - n1;
-          emit_update(u, st, st + 2, false);
+        for (int b3 = g1 + 1; run_done && b3 < nbk; ++b3) {
+          if (P.node_owner[node_first[s] + b3] != opt.rank) continue;
+          src_remote = remote(g0, g1);
+          emit_trailing(s, g0, g1, b3, b3 + 1, st, step0[s] + b3);
         }
+        src_remote = false;
+      } else {
+        if (b2 + 1 < nbk) emit_trailing(s, b2, b2 + 1, b2 + 1, b2 + 2, st, st + 1);
+        if (b2 + 2 < near_end) emit_trailing(s, b2, b2 + 1, b2 + 2, near_end, st, st + 2);
+        if (run_done) emit_trailing(s, g0, g1, g1 + 1, nbk, st, st + 2);
       }
     }
   }
