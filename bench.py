@@ -526,6 +526,28 @@ def run_single(args, name, local, steps, warmup, sampler, with_dropin=True):
                           "warm = structure cached by content hash"}
         del lv
 
+    # column (CSC) forward solve on the same factor (Triangular_CSC.h:76, lsolveParH2): the LBC schedule expanded to
+    # columns, one dataflow launch; algorithmic traffic 12 B per stored entry + 16 B per column
+    csc = None
+    if S.xsize < 3e8:
+        Cp, Ci, Cx = S.bcsc2csc(H.get_factor())
+        order = np.concatenate([np.arange(S.super[sn], S.super[sn + 1], dtype=np.int32) for sn in S.partition])
+        C = ex.CscSolver(n, Cp, Ci, order=order, device=local)
+        C.set_values(Cx)
+        ms = []
+        for _ in range(5):
+            xs = b_host.copy()
+            ms.append(C.solve(xs))
+        C.close()
+        cbytes = 12.0 * len(Ci) + 16.0 * n
+        peaks0, _ = measured_peaks()
+        hbm0 = float(peaks0.get("hbm_gbs", HBM_FALLBACK_GBS))
+        csc = {"lsolveParH2_ms": float(np.median(ms)), "nnz": int(len(Ci)), "algorithmic_bytes": cbytes,
+               "achieved_gbs": cbytes / (float(np.median(ms)) * 1e-3) / 1e9,
+               "hbm_frac": cbytes / (float(np.median(ms)) * 1e-3) / 1e9 / hbm0,
+               "max_abs_diff_vs_supernodal_forward": None}
+        del Cp, Ci, Cx
+
     prof = H.factor_profiled()
     H.sync()
     tot_prof = sum(v["ms"] for v in prof.values())
@@ -565,7 +587,7 @@ def run_single(args, name, local, steps, warmup, sampler, with_dropin=True):
         "breakdown_ms": {"factor": fac_ms, "fwd_solve": fwd_ms, "bwd_solve": bwd_ms,
                          "factor_levels": times["levels"] * 1e3, "factor_last_level": times["last_level"] * 1e3,
                          "assemble": times["assemble"] * 1e3},
-        "sptrsv_ms": {"forward": fwd_ms, "backward": bwd_ms},
+        "sptrsv_ms": {"forward": fwd_ms, "backward": bwd_ms}, "sptrsv_csc": csc,
         "e2e": {"value": F / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(8 * S.nnzA + 8 * n), "d2h_bytes_per_step": int(8 * n),
                 "api": "Solver.set_values + set_rhs + factor + solve(FWD|BWD) + get_rhs, pinned host buffers",
@@ -643,7 +665,7 @@ def main():
         "metric": "cholesky_factor_gflops", "value": rec["value"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": rec["config"], "details": rec["details"],
-        "breakdown_ms": rec["breakdown_ms"], "sptrsv_ms": rec["sptrsv_ms"], "e2e": rec["e2e"],
+        "breakdown_ms": rec["breakdown_ms"], "sptrsv_ms": rec["sptrsv_ms"], "sptrsv_csc": rec["sptrsv_csc"], "e2e": rec["e2e"],
         "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"], "roofline_solve": rec["roofline_solve"],
         "kernel_classes": rec["kernel_classes"], "cpu_baseline": cb, "clocks": clocks, "residual": rec["residual"],
         "setup_s": rec["setup_s"], "device_bytes": rec["device_bytes"],

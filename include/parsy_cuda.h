@@ -105,6 +105,17 @@ int parsy_cuda_lsolvePar(int n, int* Lp, int* Li, double* Lx, double* x, int lev
 int parsy_cuda_lsolveParH2(int n, int* Lp, int* Li, double* Lx, double* x, int levels, int* levelPtr,
                            int* levelSet, int parts, int* parPtr, int* partition, int chunk);
 
+/* Resident form of the column solves: structure (and the column order of the schedule) once, values and right-hand sides
+ * per call.  `order` = the schedule flattened to a column order (levelSet of lsolvePar, partition of lsolveParH2, NULL for
+ * 0..n-1); it must be a topological order of the column DAG (checked: PARSY_CUDA_ERR_BAD_SCHEDULE otherwise).  One kernel
+ * launch per solve: warps take the columns in that order and wait on per-column dependency counters. */
+typedef struct parsy_cuda_csc parsy_cuda_csc;
+int parsy_cuda_csc_create(parsy_cuda_csc** out, int n, const int* Lp, const int* Li, const int* order, int device);
+void parsy_cuda_csc_destroy(parsy_cuda_csc* h);
+int parsy_cuda_csc_set_values(parsy_cuda_csc* h, const double* Lx);            /* nnz doubles, host */
+/* x: host, n doubles, solved in place; device_ms (may be NULL): kernel time of the sweep from CUDA events */
+int parsy_cuda_csc_solve(parsy_cuda_csc* h, double* x, double* device_ms);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* 2. resident handle API                                                                            */
 /* ------------------------------------------------------------------------------------------------ */

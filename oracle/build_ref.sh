@@ -27,6 +27,17 @@ g++ -O2 -DNDEBUG -std=c++11 -fpermissive -w -fopenmp -DMKL -DMETIS \
     -I"$HERE/shim" -I"$TMP/cholesky" -I"$TMP/common" -I"$TMP/triangularSolve" \
     "$HERE/ref_driver.cpp" "$METIS" "$BLAS" -Wl,--disable-new-dtags,-rpath,"$(dirname "$BLAS")" -o "$OUT/parsy_ref"
 echo "built $OUT/parsy_ref"
+# The same driver with the call sites forwarded to the CUDA executor through include/parsy_cuda_dropin.h (tests only:
+# the reference's own inspector and harness drive libparsy_cuda); needs the library built first.
+LIBDIR="$HERE/../parsy_bench_b200"
+if [ -f "$LIBDIR/libparsy_cuda.so" ]; then
+  g++ -O2 -DNDEBUG -std=c++11 -fpermissive -w -fopenmp -DMKL -DMETIS -DPARSY_GPU_FORWARD \
+      -I"$HERE/shim" -I"$TMP/cholesky" -I"$TMP/common" -I"$TMP/triangularSolve" -I"$HERE/../include" \
+      "$HERE/ref_driver.cpp" "$METIS" "$BLAS" -L"$LIBDIR" -l:libparsy_cuda.so -L/usr/local/cuda/lib64 -lcudart \
+      -Wl,--disable-new-dtags,-rpath,"$(dirname "$BLAS")",-rpath,'$ORIGIN/../../parsy_bench_b200',-rpath,/usr/local/cuda/lib64 \
+      -o "$OUT/parsy_ref_gpu"
+  echo "built $OUT/parsy_ref_gpu"
+fi
 # examples/MakingLowerHalf.cpp is a self-contained program (std headers only): compiled where it lies, used by
 # tests/test_mmio.py to pin parsy_make_lower_half byte for byte.
 g++ -O2 -w "$REF/examples/MakingLowerHalf.cpp" -o "$OUT/making_lower_half"

@@ -34,6 +34,11 @@
 #include "Triangular_BCSC.h"
 #include "Triangular_CSC.h"
 #include "Inspection_Level.h"
+#ifdef PARSY_GPU_FORWARD
+// The same driver with the reference's call sites forwarded to libparsy_cuda (include/parsy_cuda_dropin.h, the header
+// INTEGRATION.md gives to a maintainer): the reference's inspector and harness drive the CUDA executor — parsy_ref_gpu.
+#include "parsy_cuda_dropin.h"
+#endif
 
 static double now() {
   return std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();

@@ -134,12 +134,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) k_gemm_tiles(const Ge
 #pragma unroll
       for (int u = 0; u < NA; ++u) {
         const bool in = k_next + ka + u * RA < K;
-        cp_async8_s(sA + so + (unsigned)(u * RA * C::LDA * 8), in ? (const void*)(pA + u * passA) : (const void*)lv, in ? szA : 0);
+        cp_async8_s(sA + so + (unsigned)(u * RA * C::LDA * 8), in ? (const void*)(pA + u * passA) : (const void*)tasks, in ? szA : 0);
       }
 #pragma unroll
       for (int u = 0; u < NBP; ++u) {
         const bool in = k_next + kb + u * RB < K;
-        cp_async8_s(sB + so + (unsigned)(u * RB * C::LDB * 8), in ? (const void*)(pB + u * passB) : (const void*)lv, in ? szB : 0);
+        cp_async8_s(sB + so + (unsigned)(u * RB * C::LDB * 8), in ? (const void*)(pB + u * passB) : (const void*)tasks, in ? szB : 0);
       }
     }
     k_next += C::KC;
@@ -1547,18 +1547,55 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MIN_CTAS) k_bwd_narrow(
 }
 
 // ------------------------------------------------------------------------------------------------
-// column (CSC) forward solve, one level per launch: warp per column            (Triangular_CSC.h:50-71)
+// column (CSC) forward solve (triangularSolve/Triangular_CSC.h:14,50,76), one launch per solve.
+//
+// One warp per column, diagonal first in every column.  Warps draw tickets and take the columns in the order of the
+// caller's schedule (level sets, Triangular_CSC.h:58-70; H-levels x w-partitions, :84-98; or 0..n-1 for the serial
+// lsolve) — any topological order of the column DAG.  Column j is ready when indeg[j] updates have arrived
+// (indeg = number of off-diagonal entries of row j, counted once per structure); a finished column adds
+// -L(i,j) x_j into x_i with red.add, fences, and bumps done[i].  Producers hold smaller tickets than their consumers,
+// so spinning cannot deadlock.  Algorithmic traffic: 12 B per stored entry (value + row index) + 16 B per column.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_csc_level(const int* __restrict__ cols, int count, const int* __restrict__ Lp,
-                            const int* __restrict__ Li, const double* __restrict__ Lx, double* __restrict__ x) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= count) return;
-  const int j = cols[warp];
+__global__ void k_csc_indeg(int n, const int* __restrict__ Lp, const int* __restrict__ Li, int* __restrict__ indeg) {
+  const int64_t nnz = Lp[n];
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+    // entry p is the diagonal iff it is the first of its column: binary search for the column
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (Lp[mid] <= p) lo = mid; else hi = mid - 1; }
+    if (p != Lp[lo]) atomicAdd(&indeg[Li[p]], 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_csc_dataflow(int n, const int* __restrict__ order, const int* __restrict__ Lp,
+                                                       const int* __restrict__ Li, const double* __restrict__ Lx,
+                                                       const int* __restrict__ indeg, int* done, int* ticket, double* x) {
+  const int lane = threadIdx.x & 31;
+  int t = 0;
+  if (lane == 0) t = atomicAdd(ticket, 1);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t >= n) return;
+  const int j = order[t];
   const int p0 = Lp[j], p1 = Lp[j + 1];
-  const double xj = x[j] / Lx[p0];
-  for (int p = p0 + 1 + lane; p < p1; p += 32) atomicAdd(&x[Li[p]], -Lx[p] * xj);
+  // first entries of the column ahead of the wait: the chain then carries one L2 round trip less
+  const int pf = p0 + 1 + lane;
+  const int i_first = pf < p1 ? Li[pf] : -1;
+  const double l_first = pf < p1 ? Lx[pf] : 0.0;
+  // lane 0 alone waits, reads x_j and writes the solved value back; the other lanes get x_j by shuffle (they must not
+  // read x[j] themselves: lane 0 may already have overwritten it with the solved value)
+  double xj = 0.0;
+  if (lane == 0) {
+    const double dinv = 1.0 / Lx[p0];
+    spin_until_ge_busy(&done[j], indeg[j]);
+    xj = __ldcg(&x[j]) * dinv;
+    x[j] = xj;
+  }
+  xj = __shfl_sync(0xffffffffu, xj, 0);
+  if (i_first >= 0) atomicAdd(&x[i_first], -l_first * xj);
+  for (int p = pf + 32; p < p1; p += 32) atomicAdd(&x[Li[p]], -Lx[p] * xj);
+  __threadfence();
   __syncwarp();
-  if (lane == 0) x[j] = xj;
+  if (i_first >= 0) atomicAdd(&done[i_first], 1);
+  for (int p = pf + 32; p < p1; p += 32) atomicAdd(&done[Li[p]], 1);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -23,8 +23,95 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
       return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
+// ---- factor buffer of a sharded plan: virtual range of the full factor, physical memory only where this rank works ----
+// A sharded rank touches the panels of its own subtrees and of the shared top separators, nothing else.  The factor
+// keeps the reference's global offsets (lC), so the buffer is a reserved virtual address range of xsize doubles with
+// physical memory (cuMemCreate / cuMemMap, 2 MiB granules) mapped only under Plan::zero_runs.  Driver entry points are
+// fetched through the runtime (cudaGetDriverEntryPoint): no link-time dependency on libcuda.
+#include <cuda.h>
+namespace {
+struct VmmApi {
+  CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+VmmApi* vmm_api() {
+  static VmmApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    api.ok = get("cuMemAddressReserve", (void**)&api.AddressReserve) && get("cuMemAddressFree", (void**)&api.AddressFree) &&
+             get("cuMemCreate", (void**)&api.Create) && get("cuMemRelease", (void**)&api.Release) &&
+             get("cuMemMap", (void**)&api.Map) && get("cuMemUnmap", (void**)&api.Unmap) &&
+             get("cuMemSetAccess", (void**)&api.SetAccess) && get("cuMemGetAllocationGranularity", (void**)&api.GetGranularity);
+    cudaGetLastError();
+  });
+  return api.ok ? &api : nullptr;
+}
+struct SparseBuffer {
+  CUdeviceptr base = 0;
+  size_t reserved = 0;
+  struct Seg { size_t off, len; CUmemGenericAllocationHandle h; };
+  std::vector<Seg> segs;
+  size_t mapped_bytes = 0;
+  void release() {
+    VmmApi* V = vmm_api();
+    if (!V || !base) return;
+    for (Seg& g : segs) { V->Unmap(base + g.off, g.len); V->Release(g.h); }
+    segs.clear();
+    V->AddressFree(base, reserved);
+    base = 0;
+  }
+  // runs: pairs (begin, end) in doubles.  Returns false (nothing left allocated) if the driver refuses.
+  bool create(int device, size_t total_doubles, const std::vector<int64_t>& runs) {
+    VmmApi* V = vmm_api();
+    if (!V) return false;
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    size_t gran = 0;
+    if (V->GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return false;
+    reserved = ((total_doubles * 8 + gran - 1) / gran) * gran;
+    if (V->AddressReserve(&base, reserved, gran, 0, 0) != CUDA_SUCCESS) { base = 0; return false; }
+    // granule ranges covering the runs, merged
+    std::vector<std::pair<size_t, size_t>> g;
+    for (size_t k = 0; k + 1 < runs.size(); k += 2) {
+      if (runs[k + 1] <= runs[k]) continue;
+      const size_t b = ((size_t)runs[k] * 8) / gran, e = ((size_t)runs[k + 1] * 8 + gran - 1) / gran;
+      if (!g.empty() && b <= g.back().second) g.back().second = std::max(g.back().second, e);
+      else g.push_back({b, e});
+    }
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    for (auto& r : g) {
+      Seg sgm{r.first * gran, (r.second - r.first) * gran, 0};
+      if (V->Create(&sgm.h, sgm.len, &prop, 0) != CUDA_SUCCESS) { release(); return false; }
+      if (V->Map(base + sgm.off, sgm.len, 0, sgm.h, 0) != CUDA_SUCCESS) { V->Release(sgm.h); release(); return false; }
+      segs.push_back(sgm);
+      if (V->SetAccess(base + sgm.off, sgm.len, &acc, 1) != CUDA_SUCCESS) { release(); return false; }
+      mapped_bytes += sgm.len;
+    }
+    return true;
+  }
+};
+}  // namespace
+
 struct parsy_cuda_solver {
   Plan plan;
+  SparseBuffer lv_sparse;     // sharded plans: d_lv is a sparsely mapped virtual range (see above)
   int device = 0;
   bool use_graph = true;
   bool has_A = false, factored = false, has_values = false;
@@ -426,6 +513,7 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
   if (s->g_fwd) cudaGraphExecDestroy(s->g_fwd);
   if (s->g_bwd) cudaGraphExecDestroy(s->g_bwd);
   if (s->borrowed_buffers) { s->d_lv = nullptr; s->d_rhs = nullptr; s->d_xs = nullptr; s->d_info = nullptr; }
+  if (s->lv_sparse.base) { s->lv_sparse.release(); s->d_lv = nullptr; }
   void* ptrs[] = {s->d_sup, s->d_lR, s->d_small_list, s->d_blocks, s->d_gemm, s->d_small_tasks, s->d_rel, s->d_apos,
                   s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info, s->d_stasks, s->d_sctas, s->d_stargets,
                   s->d_need, s->d_ntiles, s->d_sync, s->d_Ac, s->d_Ar, s->d_perm, s->d_sys, s->d_norms, s->d_invert, s->d_sync_init};
@@ -539,7 +627,12 @@ static int create_impl(parsy_cuda_solver** out, int n, const int* c, const int* 
     s->borrowed_buffers = true;
     s->d_lv = parent->d_lv; s->d_rhs = parent->d_rhs; s->d_xs = parent->d_xs; s->d_info = parent->d_info;
   } else {
-    TRY(dev_alloc(s, &s->d_lv, (size_t)P.xsize));
+    if (s->phase == 1 && o.reserved[9] != 2 && s->lv_sparse.create(o.device, (size_t)P.xsize, P.zero_runs)) {
+      s->d_lv = (double*)s->lv_sparse.base;
+      s->device_bytes += (int64_t)s->lv_sparse.mapped_bytes;
+    } else {
+      TRY(dev_alloc(s, &s->d_lv, (size_t)P.xsize));
+    }
     TRY(dev_alloc(s, &s->d_rhs, (size_t)n));
     TRY(dev_alloc(s, &s->d_xs, (size_t)n));
     TRY(dev_alloc(s, &s->d_info, 1));
@@ -1229,70 +1322,172 @@ extern "C" int parsy_cuda_H2LeveledBlockedLsolve_Peeled(int n, size_t* Lp, int* 
 }
 
 // ---- CSC column solves ----------------------------------------------------------------------------------
-static int csc_solve(int n, int* Lp, int* Li, double* Lx, double* x, const std::vector<int>& lptr,
-                     const std::vector<int>& lset) {
-  if (parsy_cuda_device_count() <= 0) { fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)"); return 0; }
-  const size_t nnz = (size_t)Lp[n];
-  int *dp = nullptr, *di = nullptr, *dset = nullptr; double *dx = nullptr, *dv = nullptr;
-  auto cleanup = [&] { cudaFree(dp); cudaFree(di); cudaFree(dset); cudaFree(dx); cudaFree(dv); };
-#define C2(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return 0; } } while (0)
-  C2(cudaMalloc(&dp, (size_t)(n + 1) * 4)); C2(cudaMalloc(&di, std::max<size_t>(nnz, 1) * 4));
-  C2(cudaMalloc(&dset, std::max<size_t>(n, 1) * 4)); C2(cudaMalloc(&dx, std::max<size_t>(n, 1) * 8));
-  C2(cudaMalloc(&dv, std::max<size_t>(nnz, 1) * 8));
-  C2(cudaMemcpy(dp, Lp, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
-  C2(cudaMemcpy(di, Li, nnz * 4, cudaMemcpyHostToDevice));
-  C2(cudaMemcpy(dv, Lx, nnz * 8, cudaMemcpyHostToDevice));
-  C2(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
-  C2(cudaMemcpy(dset, lset.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
-  for (size_t l = 0; l + 1 < lptr.size(); ++l) {
-    const int cnt = lptr[l + 1] - lptr[l];
-    if (cnt > 0) k_csc_level<<<cdivi((int64_t)cnt * 32, 256), 256>>>(dset + lptr[l], cnt, dp, di, dv, dx);
-  }
-  C2(cudaGetLastError());
-  C2(cudaMemcpy(x, dx, (size_t)n * 8, cudaMemcpyDeviceToHost));
-  cleanup();
-#undef C2
-  return 1;
+// Resident state of one lower-triangular CSC structure + one column order (k_csc_dataflow): built once per structure,
+// re-used by the drop-in entry points through the same content-hash cache as the supernodal handles.
+struct parsy_cuda_csc {
+  int n = 0, device = 0;
+  int64_t nnz = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int *d_p = nullptr, *d_i = nullptr, *d_order = nullptr, *d_indeg = nullptr, *d_sync = nullptr;   // d_sync: [ticket | done(n)]
+  double *d_v = nullptr, *d_x = nullptr;
+  bool has_values = false;
+};
+
+extern "C" void parsy_cuda_csc_destroy(parsy_cuda_csc* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : {(void*)h->d_p, (void*)h->d_i, (void*)h->d_order, (void*)h->d_indeg, (void*)h->d_sync, (void*)h->d_v, (void*)h->d_x}) if (p) cudaFree(p);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
 }
 
-// dependency levels of the columns of a lower-triangular CSC matrix (what the reference's level-set
-// inspector would produce); used when the caller passes no schedule (lsolve, Triangular_CSC.h:14)
-static void csc_levels(int n, const int* Lp, const int* Li, std::vector<int>& lptr, std::vector<int>& lset) {
-  std::vector<int> lev((size_t)n, 0);
-  int nl = 0;
-  for (int j = 0; j < n; ++j) {
-    for (int p = Lp[j] + 1; p < Lp[j + 1]; ++p) lev[Li[p]] = std::max(lev[Li[p]], lev[j] + 1);
-    nl = std::max(nl, lev[j] + 1);
+// order: any topological order of the columns (n entries), NULL = 0..n-1.  Checked on the host: a column must come
+// after every column that updates it, otherwise the spinning kernel would never finish.
+extern "C" int parsy_cuda_csc_create(parsy_cuda_csc** out, int n, const int* Lp, const int* Li, const int* order, int device) {
+  if (!out || !Lp || !Li || n < 0) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  *out = nullptr;
+  if (parsy_cuda_device_count() <= 0) return fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
+  if (device < 0 || device >= parsy_cuda_device_count()) return fail(PARSY_CUDA_ERR_BAD_ARG, "bad device ordinal");
+  const int64_t nnz = Lp[n];
+  std::vector<int> ord((size_t)n), pos((size_t)n, -1);
+  for (int t = 0; t < n; ++t) {
+    const int j = order ? order[t] : t;
+    if (j < 0 || j >= n || pos[j] >= 0) return fail(PARSY_CUDA_ERR_BAD_SCHEDULE, "column order is not a permutation of 0..n-1");
+    ord[t] = j; pos[j] = t;
   }
-  lptr.assign((size_t)nl + 1, 0);
-  for (int j = 0; j < n; ++j) lptr[lev[j] + 1]++;
-  for (int l = 0; l < nl; ++l) lptr[l + 1] += lptr[l];
-  lset.resize((size_t)n);
-  std::vector<int> fill(lptr.begin(), lptr.end() - 1);
-  for (int j = 0; j < n; ++j) lset[fill[lev[j]]++] = j;
+  for (int j = 0; j < n; ++j) {
+    if (Lp[j + 1] <= Lp[j] || Li[Lp[j]] != j) return fail(PARSY_CUDA_ERR_BAD_ARG, "every column must start with its diagonal entry");
+    for (int p = Lp[j] + 1; p < Lp[j + 1]; ++p) {
+      const int i = Li[p];
+      if (i <= j || i >= n) return fail(PARSY_CUDA_ERR_BAD_ARG, "matrix is not lower triangular");
+      if (pos[i] < pos[j]) return fail(PARSY_CUDA_ERR_BAD_SCHEDULE, "schedule runs a column before one that updates it");
+    }
+  }
+  CU(cudaSetDevice(device));
+  parsy_cuda_csc* h = new parsy_cuda_csc();
+  h->n = n; h->nnz = nnz; h->device = device;
+#define TRYCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { parsy_cuda_csc_destroy(h); return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  TRYCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) TRYCU(cudaEventCreate(&e));
+  TRYCU(cudaMalloc(&h->d_p, (size_t)(n + 1) * 4)); TRYCU(cudaMalloc(&h->d_i, std::max<size_t>(nnz, 1) * 4));
+  TRYCU(cudaMalloc(&h->d_order, std::max<size_t>(n, 1) * 4)); TRYCU(cudaMalloc(&h->d_indeg, std::max<size_t>(n, 1) * 4));
+  TRYCU(cudaMalloc(&h->d_sync, ((size_t)n + 1) * 4)); TRYCU(cudaMalloc(&h->d_v, std::max<size_t>(nnz, 1) * 8));
+  TRYCU(cudaMalloc(&h->d_x, std::max<size_t>(n, 1) * 8));
+  TRYCU(cudaMemcpyAsync(h->d_p, Lp, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  TRYCU(cudaMemcpyAsync(h->d_i, Li, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+  TRYCU(cudaMemcpyAsync(h->d_order, ord.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  TRYCU(cudaMemsetAsync(h->d_indeg, 0, std::max<size_t>(n, 1) * 4, h->stream));
+  if (nnz > 0) k_csc_indeg<<<(int)std::min<int64_t>((nnz + 255) / 256, 148 * 16), 256, 0, h->stream>>>(n, h->d_p, h->d_i, h->d_indeg);
+  TRYCU(cudaStreamSynchronize(h->stream));
+  TRYCU(cudaGetLastError());
+#undef TRYCU
+  *out = h;
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_csc_set_values(parsy_cuda_csc* h, const double* Lx) {
+  if (!h || !Lx) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->d_v, Lx, (size_t)h->nnz * 8, cudaMemcpyHostToDevice, h->stream));
+  h->has_values = true;
+  return PARSY_CUDA_OK;
+}
+
+// x (host, n doubles) is solved in place; device_ms, if not NULL, receives the kernel time of the sweep (CUDA events).
+extern "C" int parsy_cuda_csc_solve(parsy_cuda_csc* h, double* x, double* device_ms) {
+  if (!h || !x) return fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument");
+  if (!h->has_values) return fail(PARSY_CUDA_ERR_STATE, "set_values must precede solve");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int n = h->n;
+  if (n == 0) return PARSY_CUDA_OK;
+  CU(cudaMemcpyAsync(h->d_x, x, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(h->d_sync, 0, ((size_t)n + 1) * 4, st));
+  CU(cudaEventRecord(h->ev[0], st));
+  k_csc_dataflow<<<(n + 7) / 8, 256, 0, st>>>(n, h->d_order, h->d_p, h->d_i, h->d_v, h->d_indeg, h->d_sync + 1, h->d_sync, h->d_x);
+  CU(cudaEventRecord(h->ev[1], st));
+  CU(cudaMemcpyAsync(x, h->d_x, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  if (device_ms) { float ms = 0; CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); *device_ms = ms; }
+  return PARSY_CUDA_OK;
+}
+
+namespace {
+struct CscEntry { uint64_t key = 0; parsy_cuda_csc* h = nullptr; uint64_t stamp = 0; };
+CscEntry g_csc_cache[2];
+parsy_cuda_csc* csc_cache_take(uint64_t key) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (CscEntry& e : g_csc_cache) if (e.h && e.key == key) { parsy_cuda_csc* h = e.h; e.h = nullptr; return h; }
+  return nullptr;
+}
+void csc_cache_put(uint64_t key, parsy_cuda_csc* h) {
+  parsy_cuda_csc* evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CscEntry* slot = &g_csc_cache[0];
+    for (CscEntry& e : g_csc_cache) { if (!e.h) { slot = &e; break; } if (e.stamp < slot->stamp) slot = &e; }
+    evict = slot->h;
+    slot->h = h; slot->key = key; slot->stamp = ++g_cache_clock;
+  }
+  if (evict) parsy_cuda_csc_destroy(evict);
+}
+}  // namespace
+
+// drop-in body shared by lsolve / lsolvePar / lsolveParH2: `order` is the schedule flattened to a column order
+static int csc_dropin(int n, int* Lp, int* Li, double* Lx, double* x, const int* order) {
+  if (parsy_cuda_device_count() <= 0) { fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)"); return 0; }
+  const bool cache = dropin_cache_enabled();
+  uint64_t key = 0;
+  parsy_cuda_csc* h = nullptr;
+  if (cache) {
+    Hasher H;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    H.word(3); H.word((uint64_t)n); H.word((uint64_t)dev);
+    H.arr(Lp, (size_t)n + 1); H.arr(Li, (size_t)Lp[n]); H.arr(order, order ? (size_t)n : 0);
+    key = H.h ? H.h : 1;
+    h = csc_cache_take(key);
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int rc = h ? 0 : parsy_cuda_csc_create(&h, n, Lp, Li, order, dev);
+  if (rc) return 0;
+  rc = parsy_cuda_csc_set_values(h, Lx);
+  if (!rc) rc = parsy_cuda_csc_solve(h, x, nullptr);
+  const std::string keep = g_err;
+  if (cache && rc == PARSY_CUDA_OK) csc_cache_put(key, h);
+  else parsy_cuda_csc_destroy(h);
+  g_err = keep;
+  return rc == PARSY_CUDA_OK ? 1 : 0;
 }
 
 extern "C" int parsy_cuda_lsolve(int n, int* Lp, int* Li, double* Lx, double* x) {
   if (!Lp || !Li || !x) return 0;   // Triangular_CSC.h:16
   if (!Lx) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
-  std::vector<int> lptr, lset;
-  csc_levels(n, Lp, Li, lptr, lset);
-  return csc_solve(n, Lp, Li, Lx, x, lptr, lset);
+  return csc_dropin(n, Lp, Li, Lx, x, nullptr);          // column order 0..n-1, as the reference's serial loop
 }
 extern "C" int parsy_cuda_lsolvePar(int n, int* Lp, int* Li, double* Lx, double* x, int levels, int* levelPtr,
                                     int* levelSet, int chunk) {
   (void)chunk;
   if (!Lp || !Li || !x) return 0;
   if (!Lx || !levelPtr || !levelSet) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
-  std::vector<int> lptr(levelPtr, levelPtr + levels + 1), lset(levelSet, levelSet + n);
-  return csc_solve(n, Lp, Li, Lx, x, lptr, lset);
+  if (levels < 0 || levelPtr[levels] != n) { fail(PARSY_CUDA_ERR_BAD_SCHEDULE, "level set does not cover every column"); return 0; }
+  return csc_dropin(n, Lp, Li, Lx, x, levelSet);         // Triangular_CSC.h:58-70: levels in order, columns of a level in parallel
 }
 extern "C" int parsy_cuda_lsolveParH2(int n, int* Lp, int* Li, double* Lx, double* x, int levels, int* levelPtr,
                                       int* levelSet, int parts, int* parPtr, int* partition, int chunk) {
-  (void)chunk; (void)levelSet; (void)parts; (void)levels; (void)levelPtr; (void)parPtr; (void)partition;
-  // Columns inside one w-partition depend on each other (Triangular_CSC.h:84-96 runs them sequentially),
-  // so the device sweep orders by the column dependency levels, which refine any legal LBC schedule.
-  return parsy_cuda_lsolve(n, Lp, Li, Lx, x);
+  (void)chunk; (void)levelSet; (void)parts;
+  if (!Lp || !Li || !x) return 0;
+  if (!Lx || !levelPtr || !parPtr || !partition) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL schedule"); return 0; }
+  // Triangular_CSC.h:84-98: H-levels in order, w-partitions of a level in parallel, the columns of a w-partition in
+  // list order.  The device walks exactly that order (partition[] flattened); columns that the reference would run
+  // in parallel are handed to different warps, dependencies are enforced by the per-column counters.
+  if (levels < 0 || levelPtr[levels] < 0 || parPtr[levelPtr[levels]] != n) { fail(PARSY_CUDA_ERR_BAD_SCHEDULE, "schedule does not cover every column"); return 0; }
+  return csc_dropin(n, Lp, Li, Lx, x, partition);
 }
 
 static int owned_ranges_of(const Plan& P, int rank, int64_t* begin_end_pairs, int max_pairs) {

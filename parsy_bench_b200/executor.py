@@ -199,6 +199,61 @@ def lsolveParH2(n, Lp, Li, Lx, x, levels, levelPtr, levelSet, parts, parPtr, par
                         _i32(partition, "partition", True), int(chunk)])
 
 
+class CscSolver:
+    """Resident column (CSC) forward solve: structure and column order once, values / right-hand sides per call
+    (parsy_cuda_csc_*).  ``order``: the schedule flattened to a column order, None = 0..n-1."""
+
+    def __init__(self, n, Lp, Li, order=None, device=0):
+        self._L = lib()
+        self._h = c_void_p()
+        keep = [_i32(Lp, "Lp"), _i32(Li, "Li"), _i32(order, "order", True)]
+        f = self._L.parsy_cuda_csc_create
+        f.restype = c_int
+        f.argtypes = [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_int]
+        rc = f(byref(self._h), int(n), keep[0][1], keep[1][1], keep[2][1], int(device))
+        if rc != OK:
+            self._h = c_void_p()
+            raise ParsyCudaError(rc, "parsy_cuda_csc_create")
+        self.n, self.nnz = int(n), int(np.asarray(Lp)[n])
+
+    def set_values(self, Lx):
+        v = np.ascontiguousarray(Lx, dtype=np.float64)
+        if v.size != self.nnz:
+            raise ValueError("Lx has the wrong length")
+        self._v = v          # the copy is asynchronous: keep the buffer alive until the next solve has synchronised
+        f = self._L.parsy_cuda_csc_set_values
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_void_p]
+        rc = f(self._h, v.ctypes.data_as(c_void_p))
+        if rc != OK:
+            raise ParsyCudaError(rc, "parsy_cuda_csc_set_values")
+
+    def solve(self, x) -> float:
+        """Solves L x = b in place on ``x``; returns the device time of the sweep in ms."""
+        ms = c_double(0.0)
+        f = self._L.parsy_cuda_csc_solve
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_void_p, POINTER(c_double)]
+        rc = f(self._h, _f64_inplace(x, "x"), byref(ms))
+        if rc != OK:
+            raise ParsyCudaError(rc, "parsy_cuda_csc_solve")
+        return float(ms.value)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            f = self._L.parsy_cuda_csc_destroy
+            f.restype = None
+            f.argtypes = [c_void_p]
+            f(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def plan_check(n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition, block_cols=0,
                ignore_hlevels=False, rank=0, world=1, phase=0, top_levels=1):
     """Host-only planner run (no device needed): returns (status code, stats dict)."""

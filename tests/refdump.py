@@ -9,6 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "parsy_ref")
+REF_GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "parsy_ref_gpu")   # same driver, call sites forwarded to libparsy_cuda
 _DT = {"i32": np.int32, "u64": np.uint64, "f64": np.float64}
 _CACHE = {}
 
@@ -22,15 +23,15 @@ class RefCase(dict):
 
 
 def ref_case(kind, N, cost=8, level=1, div=2, threads=1, factor=True, solve=True, iters=1, keep_values=True, mtx=None,
-             blas_threads=None, csc=True, cache=True):
+             blas_threads=None, csc=True, cache=True, binary=None):
     """mtx: path of a lower-half Matrix-Market file read by the reference's readMatrix instead of the synthetic grid.
     blas_threads: BLAS threads of the LAST (sequential) H-level only (parallel_PB_Cholesky_05.h:271); the parallel levels
     stay on `threads` OpenMP threads — 1 for goldens, because of the `top` race (:43,69,115)."""
-    key = (kind, N, cost, level, div, threads, factor, solve, mtx, blas_threads, csc)
+    key = (kind, N, cost, level, div, threads, factor, solve, mtx, blas_threads, csc, binary, iters)
     if cache and key in _CACHE:
         return _CACHE[key]
     d = tempfile.mkdtemp(prefix="parsy_ref_")
-    cmd = [REF_BIN, "--kind", kind, "--N", str(N), "--cost", str(cost), "--level", str(level), "--div", str(div),
+    cmd = [binary or REF_BIN, "--kind", kind, "--N", str(N), "--cost", str(cost), "--level", str(level), "--div", str(div),
            "--threads", str(threads), "--iters", str(iters), "--dump", d]
     if mtx is not None:
         cmd += ["--mtx", str(mtx)]

@@ -6,6 +6,7 @@ import subprocess
 import numpy as np
 import pytest
 
+import refdump
 from parsy_bench_b200 import executor as ex, matrices
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -40,3 +41,24 @@ def test_driver_flow_on_the_gpu(tmp_path, spec):
     assert t_all > 0 and t_levels >= 0 and t_last > 0 and t_all >= t_last
     tail = dict(kv.split("=") for kv in fields[12].split())
     assert float(tail["residual"]) < 1e-12 and abs(float(tail["device_residual"]) - float(tail["residual"])) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(refdump.REF_BIN) and os.path.exists(refdump.REF_GPU_BIN)),
+                    reason="compiled reference drivers (oracle/_ref) not present")
+@pytest.mark.parametrize("case", [("2d5", 150, 8, 1, 2), ("3d27", 16, 16, 0, 2), ("3d7", 24, 592, 1, 4)])
+def test_reference_driver_with_call_sites_forwarded_to_the_gpu(case):
+    """oracle/_ref/parsy_ref_gpu is oracle/ref_driver.cpp — the reference's inspector (analyze_p2), its harness
+    (rhsInitBlocked / testTriangular, common/Util.h:277-306) and its call sites — compiled with
+    include/parsy_cuda_dropin.h, the forwarding header of INTEGRATION.md section 1, so that cholesky_left_par_05 and every
+    forward solve run in libparsy_cuda on the arrays the REFERENCE's inspector produced.  Three factorizations per run
+    (the second and third hit the structure cache of the drop-in entry points).  Compared with the unforwarded driver."""
+    kind, N, c, l, d = case
+    R = refdump.ref_case(kind, N, cost=c, level=l, div=d, threads=1)
+    G = refdump.ref_case(kind, N, cost=c, level=l, div=d, threads=1, iters=3, binary=refdump.REF_GPU_BIN)
+    assert G.meta["factor_ok"] == 1 and G.meta["solve_ok"] == 1          # testTriangular: x == 1 for b = L*1
+    assert np.array_equal(G.partition, R.partition) and np.array_equal(G.p, R.p)
+    assert refdump.rel_err(G.valL, R.valL) < 1e-9
+    assert np.array_equal(G.valL == 0.0, R.valL == 0.0)
+    for k in ("x_blocked", "x_h2", "y_ramp", "y_ramp_csc"):
+        assert refdump.rel_err(G[k], R[k]) < 1e-9, k

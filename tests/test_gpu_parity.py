@@ -172,10 +172,32 @@ def test_csc_solves_vs_reference_golden(name):
     x = ramp.copy()
     assert ex.lsolvePar(n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, x, len(lptr) - 1, lptr, order, 1) == 1
     assert rel_err(x, G.y_ramp_csc) < 1e-11
+    # lsolveParH2 (Triangular_CSC.h:76): H-levels x w-partitions over COLUMNS — the LBC schedule of the factorization
+    # with every supernode expanded into its columns (sequential inside a w-partition, as the reference runs them)
+    col_part, col_parptr = [], [0]
+    for j1 in range(len(G.parPtr) - 1):
+        for sn in G.partition[G.parPtr[j1]:G.parPtr[j1 + 1]]:
+            col_part.extend(range(G.super[sn], G.super[sn + 1]))
+        col_parptr.append(len(col_part))
+    col_part, col_parptr = np.array(col_part, np.int32), np.array(col_parptr, np.int32)
     x = ramp.copy()
-    assert ex.lsolveParH2(n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, x, 0, None, None, 0, None, None, 1) == 1
+    assert ex.lsolveParH2(n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, x, len(G.levelPtr) - 1, G.levelPtr, None, 0, col_parptr,
+                          col_part, 1) == 1
     assert rel_err(x, G.y_ramp_csc) < 1e-11
+    # a schedule that runs a column before one that updates it is refused (it would hang a dataflow kernel)
+    x = ramp.copy()
+    assert ex.lsolveParH2(n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, x, len(G.levelPtr) - 1, G.levelPtr, None, 0, col_parptr,
+                          col_part[::-1].copy(), 1) == 0
+    assert ex.lsolveParH2(n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, x, 0, None, None, 0, None, None, 1) == 0
     assert ex.lsolve(n, None, G.Lcsc_i, G.Lcsc_x, x) == 0
+    # resident form: structure once, several right-hand sides
+    H = ex.CscSolver(n, G.Lcsc_p, G.Lcsc_i, order=col_part)
+    H.set_values(G.Lcsc_x)
+    for scale in (1.0, -2.5):
+        x = ramp * scale
+        ms = H.solve(x)
+        assert ms > 0 and rel_err(x, G.y_ramp_csc * scale) < 1e-11
+    H.close()
 
 
 @pytest.mark.parametrize("case", [("2d5", 100, 8, 1, 2), ("3d27", 16, 8, 1, 2), ("3d7", 24, 148, 1, 4)])
