@@ -4,6 +4,10 @@
 #include <algorithm>
 #include <climits>
 #include <cstring>
+#include <chrono>
+#include <thread>
+#include <cstdio>
+#include <cstdlib>
 
 namespace parsy {
 
@@ -40,6 +44,10 @@ static inline int lower_tiles(int M, int N, int TM, int TN) {
 int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo,
                const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
                const int* partition, const PlanOptions& opt) {
+  const bool timing_on = getenv("PARSY_PLAN_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tlast = tnow();
+  auto lap = [&](const char* what) { if (timing_on) { const double t = tnow(); fprintf(stderr, "[plan] %-28s %.1f ms\n", what, (t - tlast) * 1e3); tlast = t; } };
   if (n < 0 || supNo < 0 || !lC || !lR || !Li_ptr || !blockSet || !col2Sup || !levelPtr || !parPtr ||
       !partition || nLevels < 0) {
     P.error = "NULL or negative argument";
@@ -70,6 +78,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   P.xsize = xs; P.ssize = ss;
   P.bytes_solve += 4.0 * (double)ss + 16.0 * (double)n;
 
+  lap("supernode table");
   // ---- schedule: validate, then assign dependency steps --------------------------------------------
   std::vector<int32_t> hl(supNo, -1), part(supNo, -1), pos(supNo, -1);
   std::vector<int32_t> order; order.reserve(supNo);
@@ -120,6 +129,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     P.hlevel_first_step[nLevels] = nsteps;
   }
 
+  lap("pairs + schedule + steps");
   // ---- ownership for the sharded factorization ----------------------------------------------------------
   P.owner.assign(supNo, opt.world > 1 ? -1 : 0);
   if (opt.world > 1) {
@@ -198,6 +208,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   // pairs are emitted grouped by source d ascending; the step of a pair is the last step of its source
   // (the whole width of d is applied in one task, K = width(d)).
 
+  lap("ownership + flops");
   // ---- bucket everything by step ----------------------------------------------------------------------
   P.steps.assign(nsteps, Step());
   for (int H = 0; H < nLevels; ++H)
@@ -335,145 +346,6 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   }
   P.n_slots = slot; P.n_block_cols = slot;
 
-  // real pairs (+ relative-index bookkeeping)
-  P.rel_prefix.assign(P.pairs.size() + 1, 0);
-  P.rel_pair_src.resize(P.pairs.size()); P.rel_pair_tgt.resize(P.pairs.size()); P.rel_pair_lb.resize(P.pairs.size());
-  int64_t rel = 0;
-  for (size_t pi = 0; pi < P.pairs.size(); ++pi) {
-    const PairDesc& q = P.pairs[pi];
-    const SupInfo& D = P.sup[q.src]; const SupInfo& T = P.sup[q.tgt];
-    const int st = step0[q.src] + nblk[q.src] - 1;
-    GemmTask t; memset(&t, 0, sizeof(t));
-    t.a_off = D.valptr + q.lb; t.b_off = t.a_off; t.c_off = T.valptr; t.rel_off = rel;
-    t.lda = t.ldb = D.r; t.ldc = T.r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
-    P.rel_prefix[pi] = rel; P.rel_pair_src[pi] = q.src; P.rel_pair_tgt[pi] = q.tgt; P.rel_pair_lb[pi] = q.lb;
-    rel += q.m;
-    if (!pair_active(q.src, q.tgt)) continue;
-    src_remote = false;
-    if (!dist_top) { emit_update(t, st, step0[q.tgt], true); continue; }
-    // Distributed top.  (i) The pair's columns are split by the target block column they fall into; a rank keeps what
-    // it owns.  (ii) A wide source is applied in K-chunks of PAIR_KBLK block columns as they are finished instead of
-    // in one K = width task after its last block column: the ancestors' updates then overlap the source's own chain
-    // instead of arriving in one burst right before the next separator starts (sums via red.add, so K can be cut).
-    constexpr int PAIR_KBLK = 4;
-    const int nkb = D.flags ? 1 : nblk[q.src];
-    for (int n0 = 0; n0 < q.nd1;) {
-      auto blk_of = [&](int j) { return T.flags ? 0 : (lR[D.rowptr + q.lb + j] - T.col0) / NB; };
-      const int tb = blk_of(n0);
-      int n1 = n0 + 1;
-      while (n1 < q.nd1 && blk_of(n1) == tb) ++n1;
-      if (P.node_owner[node_first[q.tgt] + tb] == opt.rank) {
-        for (int kb0 = 0; kb0 < nkb; kb0 += PAIR_KBLK) {
-          const int kb1 = std::min(nkb, kb0 + PAIR_KBLK);
-          const int k0 = kb0 * NB, k1 = D.flags ? D.w : std::min(D.w, kb1 * NB);
-          const int stq = step0[q.src] + kb1 - 1;
-          GemmTask u = t;
-          u.a_off += n0 + (int64_t)k0 * D.r; u.b_off = u.a_off; u.rel_off += n0; u.M = q.m - n0; u.N = n1 - n0; u.K = k1 - k0;
-          src_remote = false;
-          for (int kb = kb0; kb < kb1; ++kb) if (P.node_owner[node_first[q.src] + kb] != opt.rank) src_remote = true;
-          emit_update(u, stq, step0[q.tgt] + tb, true);
-        }
-      }
-      n0 = n1;
-    }
-  }
-  src_remote = false;
-  P.rel_prefix[P.pairs.size()] = rel;
-  P.rel_entries = rel;
-
-  // tile size per launch: a (step, group) launch whose 128x64 / 64x64 tiles cannot cover the SMs is latency-bound by
-  // the duration of one tile, so it is re-cut into 64x64 or 32x32 tiles (the panel -> next block column updates on the
-  // critical path of a separator are the typical case)
-  {
-    constexpr int SMS = 148;
-    std::vector<int32_t> tdef(3 * (size_t)nsteps, 0), t64(3 * (size_t)nsteps, 0);
-    for (const Gen& g : gen) {
-      if (g.cls != 1 && g.cls != 2) continue;
-      tdef[3 * g.step + g.grp] += g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : lower_tiles(g.t.M, g.t.N, 64, 64);
-      t64[3 * g.step + g.grp] += lower_tiles(g.t.M, g.t.N, 64, 64);
-    }
-    for (Gen& g : gen) {
-      if (g.cls != 1 && g.cls != 2) continue;
-      const int k = 3 * g.step + g.grp;
-      if (tdef[k] >= SMS) continue;
-      const double fl = upd_flops(g.t);
-      const int ncls = t64[k] >= SMS ? 2 : 4;
-      if (ncls == g.cls) continue;
-      if (g.cls == 1) { P.class_flops[3] -= fl; P.class_flops[4] += fl; }
-      g.cls = (int8_t)ncls;
-    }
-  }
-  // split-K: a launch with fewer tiles than the GPU has CTA slots cannot fill the machine, and its tiles with a long
-  // K (wide descendants) set the duration; the epilogue is an atomic add, so K can be cut into independent pieces
-  {
-    constexpr int FILL = 2 * 148;
-    std::vector<int32_t> tl(3 * (size_t)nsteps, 0);
-    auto ntiles = [&](const Gen& g) {
-      return g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : g.cls == 2 ? lower_tiles(g.t.M, g.t.N, 64, 64) : lower_tiles(g.t.M, g.t.N, 32, 32);
-    };
-    for (const Gen& g : gen) if (g.cls == 1 || g.cls == 2 || g.cls == 4) tl[3 * g.step + g.grp] += ntiles(g);
-    const size_t n0 = gen.size();
-    for (size_t i = 0; i < n0; ++i) {
-      if ((gen[i].cls != 1 && gen[i].cls != 2 && gen[i].cls != 4) || gen[i].t.K < 128) continue;
-      const int total = tl[3 * gen[i].step + gen[i].grp];
-      if (total >= FILL) continue;
-      const int K = gen[i].t.K;
-      const int f = std::min(std::min(cdiv(K, 64), cdiv(FILL, std::max(total, 1))), 8);
-      if (f <= 1) continue;
-      const int chunk = cdiv(cdiv(K, f), 16) * 16;
-      for (int k0 = chunk; k0 < K; k0 += chunk) {
-        Gen g = gen[i];
-        g.t.a_off += (int64_t)k0 * g.t.lda; g.t.b_off += (int64_t)k0 * g.t.ldb; g.t.K = std::min(chunk, K - k0);
-        gen.push_back(g);
-      }
-      gen[i].t.K = chunk;
-    }
-  }
-  if (gen.size() > (size_t)INT32_MAX) { P.error = "task list too large"; return PARSY_CUDA_ERR_BAD_ARG; }
-  std::vector<int32_t> ord(gen.size());
-  for (size_t i = 0; i < gen.size(); ++i) ord[i] = (int32_t)i;
-  auto key = [&](int32_t i) { return ((int64_t)gen[i].step << 8) | ((int64_t)gen[i].cls << 4) | gen[i].grp; };
-  std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return key(x) < key(y); });
-  P.gemm_tasks.resize(gen.size());
-  {
-    size_t i = 0;
-    for (int st = 0; st < nsteps; ++st) {
-      Step& S = P.steps[st];
-      auto take = [&](int cls, int grp) {
-        const int32_t b0 = (int32_t)i;
-        while (i < ord.size() && gen[ord[i]].step == st && gen[ord[i]].cls == cls && gen[ord[i]].grp == grp) {
-          P.gemm_tasks[i] = gen[ord[i]].t;
-          ++i;
-        }
-        return Range{b0, (int32_t)i};
-      };
-      S.trsm = take(0, 0);
-      for (int g = 0; g < 3; ++g) S.upd[g].u128 = take(1, g);
-      for (int g = 0; g < 3; ++g) S.upd[g].u64 = take(2, g);
-      for (int g = 0; g < 3; ++g) S.upd[g].small_pairs = take(3, g);
-      for (int g = 0; g < 3; ++g) S.upd[g].u32 = take(4, g);
-    }
-  }
-  std::vector<Gen>().swap(gen);
-  // row chunks of the small pairs, narrow (K <= 4) first inside every (step, group)
-  for (int st = 0; st < nsteps; ++st)
-    for (int g = 0; g < 3; ++g) {
-      UpdGroup& U = P.steps[st].upd[g];
-      U.small.begin = (int32_t)P.small_tasks.size();
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int gi = U.small_pairs.begin; gi < U.small_pairs.end; ++gi) {
-          const GemmTask& t = P.gemm_tasks[gi];
-          if ((t.K <= 4) != (pass == 0)) continue;
-          for (int r0 = 0; r0 < t.M; r0 += 256) {
-            SmallTask stt; stt.pair = gi; stt.row0 = r0; stt.nrows = std::min(256, t.M - r0); stt.pad = 0;
-            P.small_tasks.push_back(stt);
-          }
-        }
-        if (pass == 0) U.small_narrow = (int32_t)P.small_tasks.size() - U.small.begin;
-      }
-      U.small.end = (int32_t)P.small_tasks.size();
-    }
-
   // narrow supernodes first inside every step (the low-register kernel variant takes the leading part of the list)
   for (int st = 0; st < nsteps; ++st) {
     Step& S = P.steps[st];
@@ -482,64 +354,8 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     S.small_narrow = 0;
     for (int i = S.small_sup.begin; i < S.small_sup.end; ++i) if (P.sup[P.small_list[i]].w <= SMALL_W_NARROW) S.small_narrow++;
   }
-  // tile prefixes per launch segment
-  for (int st = 0; st < nsteps; ++st) {
-    Step& S = P.steps[st];
-    int32_t acc = 0;
-    // TRSM row-tile height: the tallest of 64 / 32 / 16 that still gives every SM a tile
-    S.trsm_tm = 64;
-    for (int tm : {64, 32, 16}) {
-      acc = 0;
-      for (int i = S.trsm.begin; i < S.trsm.end; ++i) acc += cdiv(P.gemm_tasks[i].M, tm);
-      S.trsm_tm = tm;
-      if (acc >= 148) break;
-    }
-    acc = 0;
-    for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, S.trsm_tm); }
-    S.trsm_tiles = acc;
-    for (int g = 0; g < 3; ++g) {
-      UpdGroup& U = S.upd[g];
-      acc = 0;
-      for (int i = U.u128.begin; i < U.u128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128, 64); }
-      U.tiles128 = acc; acc = 0;
-      for (int i = U.u64.begin; i < U.u64.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 64, 64); }
-      U.tiles64 = acc; acc = 0;
-      for (int i = U.u32.begin; i < U.u32.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 32, 32); }
-      U.tiles32 = acc;
-    }
-    acc = 0;
-    for (int i = S.blocks.begin; i < S.blocks.end; ++i) {
-      BlockTask& bk = P.block_tasks[i];
-      bk.tile0 = acc; acc += std::max(1, cdiv(P.sup[bk.sup].r - bk.j0 - bk.nb, 64));
-    }
-    S.solve_tiles = acc;
-  }
-  // ---- distributed top: panels to broadcast before each step ----------------------------------------------------
-  P.bcast_ptr.assign(nsteps + 1, 0);
-  if (dist_top) {
-    std::vector<std::vector<int64_t>> per(nsteps);
-    std::vector<std::vector<int32_t>> shp(nsteps);
-    for (int s = 0; s < supNo; ++s) {
-      if (P.owner[s] >= 0) continue;
-      const SupInfo& I = P.sup[s];
-      for (int b2 = 0; b2 < nblk[s]; ++b2) {
-        const int j0 = I.flags ? 0 : b2 * NB, nb = I.flags ? I.w : std::min(NB, I.w - j0);
-        auto& v = per[step0[s] + b2];
-        v.push_back(P.node_owner[node_first[s] + b2]);
-        v.push_back(I.valptr + (int64_t)j0 * I.r);
-        v.push_back(I.valptr + (int64_t)(j0 + nb) * I.r);
-        auto& h = shp[step0[s] + b2];
-        h.push_back(j0); h.push_back(I.r); h.push_back(nb);
-      }
-    }
-    for (int st = 0; st < nsteps; ++st) {
-      P.bcast.insert(P.bcast.end(), per[st].begin(), per[st].end());
-      P.bcast_shape.insert(P.bcast_shape.end(), shp[st].begin(), shp[st].end());
-      P.bcast_ptr[st + 1] = (int32_t)(P.bcast.size() / 3);
-    }
-  }
   // ---- dataflow sweeps: nodes, tasks in dependency order, target lists, counters ------------------------------
-  {
+  auto build_sweeps = [&]() {
     P.n_nodes = node_first[supNo];
     auto node_of_row = [&](int row) {
       const int t = col2Sup[row];
@@ -636,7 +452,217 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         }
       }
     }
+  };
+  // the sweep plan only depends on the factor-side lists above: built on a second thread next to the update lists
+  std::thread sweep_thread(build_sweeps);
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } sweep_joiner{sweep_thread};
+  lap("factor-side lists + trailing");
+  // real pairs (+ relative-index bookkeeping)
+  P.rel_prefix.assign(P.pairs.size() + 1, 0);
+  P.rel_pair_src.resize(P.pairs.size()); P.rel_pair_tgt.resize(P.pairs.size()); P.rel_pair_lb.resize(P.pairs.size());
+  int64_t rel = 0;
+  for (size_t pi = 0; pi < P.pairs.size(); ++pi) {
+    const PairDesc& q = P.pairs[pi];
+    const SupInfo& D = P.sup[q.src]; const SupInfo& T = P.sup[q.tgt];
+    const int st = step0[q.src] + nblk[q.src] - 1;
+    GemmTask t; memset(&t, 0, sizeof(t));
+    t.a_off = D.valptr + q.lb; t.b_off = t.a_off; t.c_off = T.valptr; t.rel_off = rel;
+    t.lda = t.ldb = D.r; t.ldc = T.r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
+    P.rel_prefix[pi] = rel; P.rel_pair_src[pi] = q.src; P.rel_pair_tgt[pi] = q.tgt; P.rel_pair_lb[pi] = q.lb;
+    rel += q.m;
+    if (!pair_active(q.src, q.tgt)) continue;
+    src_remote = false;
+    if (!dist_top) { emit_update(t, st, step0[q.tgt], true); continue; }
+    // Distributed top.  (i) The pair's columns are split by the target block column they fall into; a rank keeps what
+    // it owns.  (ii) A wide source is applied in K-chunks of PAIR_KBLK block columns as they are finished instead of
+    // in one K = width task after its last block column: the ancestors' updates then overlap the source's own chain
+    // instead of arriving in one burst right before the next separator starts (sums via red.add, so K can be cut).
+    constexpr int PAIR_KBLK = 4;
+    const int nkb = D.flags ? 1 : nblk[q.src];
+    for (int n0 = 0; n0 < q.nd1;) {
+      auto blk_of = [&](int j) { return T.flags ? 0 : (lR[D.rowptr + q.lb + j] - T.col0) / NB; };
+      const int tb = blk_of(n0);
+      int n1 = n0 + 1;
+      while (n1 < q.nd1 && blk_of(n1) == tb) ++n1;
+      if (P.node_owner[node_first[q.tgt] + tb] == opt.rank) {
+        for (int kb0 = 0; kb0 < nkb; kb0 += PAIR_KBLK) {
+          const int kb1 = std::min(nkb, kb0 + PAIR_KBLK);
+          const int k0 = kb0 * NB, k1 = D.flags ? D.w : std::min(D.w, kb1 * NB);
+          const int stq = step0[q.src] + kb1 - 1;
+          GemmTask u = t;
+          u.a_off += n0 + (int64_t)k0 * D.r; u.b_off = u.a_off; u.rel_off += n0; u.M = q.m - n0; u.N = n1 - n0; u.K = k1 - k0;
+          src_remote = false;
+          for (int kb = kb0; kb < kb1; ++kb) if (P.node_owner[node_first[q.src] + kb] != opt.rank) src_remote = true;
+          emit_update(u, stq, step0[q.tgt] + tb, true);
+        }
+      }
+      n0 = n1;
+    }
   }
+  src_remote = false;
+  P.rel_prefix[P.pairs.size()] = rel;
+  P.rel_entries = rel;
+
+  lap("pair tasks");
+  // tile size per launch: a (step, group) launch whose 128x64 / 64x64 tiles cannot cover the SMs is latency-bound by
+  // the duration of one tile, so it is re-cut into 64x64 or 32x32 tiles (the panel -> next block column updates on the
+  // critical path of a separator are the typical case)
+  {
+    constexpr int SMS = 148;
+    std::vector<int32_t> tdef(3 * (size_t)nsteps, 0), t64(3 * (size_t)nsteps, 0);
+    for (const Gen& g : gen) {
+      if (g.cls != 1 && g.cls != 2) continue;
+      tdef[3 * g.step + g.grp] += g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : lower_tiles(g.t.M, g.t.N, 64, 64);
+      t64[3 * g.step + g.grp] += lower_tiles(g.t.M, g.t.N, 64, 64);
+    }
+    for (Gen& g : gen) {
+      if (g.cls != 1 && g.cls != 2) continue;
+      const int k = 3 * g.step + g.grp;
+      if (tdef[k] >= SMS) continue;
+      const double fl = upd_flops(g.t);
+      const int ncls = t64[k] >= SMS ? 2 : 4;
+      if (ncls == g.cls) continue;
+      if (g.cls == 1) { P.class_flops[3] -= fl; P.class_flops[4] += fl; }
+      g.cls = (int8_t)ncls;
+    }
+  }
+  // split-K: a launch with fewer tiles than the GPU has CTA slots cannot fill the machine, and its tiles with a long
+  // K (wide descendants) set the duration; the epilogue is an atomic add, so K can be cut into independent pieces
+  {
+    constexpr int FILL = 2 * 148;
+    std::vector<int32_t> tl(3 * (size_t)nsteps, 0);
+    auto ntiles = [&](const Gen& g) {
+      return g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : g.cls == 2 ? lower_tiles(g.t.M, g.t.N, 64, 64) : lower_tiles(g.t.M, g.t.N, 32, 32);
+    };
+    for (const Gen& g : gen) if (g.cls == 1 || g.cls == 2 || g.cls == 4) tl[3 * g.step + g.grp] += ntiles(g);
+    const size_t n0 = gen.size();
+    for (size_t i = 0; i < n0; ++i) {
+      if ((gen[i].cls != 1 && gen[i].cls != 2 && gen[i].cls != 4) || gen[i].t.K < 128) continue;
+      const int total = tl[3 * gen[i].step + gen[i].grp];
+      if (total >= FILL) continue;
+      const int K = gen[i].t.K;
+      const int f = std::min(std::min(cdiv(K, 64), cdiv(FILL, std::max(total, 1))), 8);
+      if (f <= 1) continue;
+      const int chunk = cdiv(cdiv(K, f), 16) * 16;
+      for (int k0 = chunk; k0 < K; k0 += chunk) {
+        Gen g = gen[i];
+        g.t.a_off += (int64_t)k0 * g.t.lda; g.t.b_off += (int64_t)k0 * g.t.ldb; g.t.K = std::min(chunk, K - k0);
+        gen.push_back(g);
+      }
+      gen[i].t.K = chunk;
+    }
+  }
+  lap("tile classes + split-K");
+  if (gen.size() > (size_t)INT32_MAX) { P.error = "task list too large"; return PARSY_CUDA_ERR_BAD_ARG; }
+  // stable counting sort by (step, class, group): the key space is small (15 buckets per step)
+  std::vector<int32_t> ord(gen.size());
+  {
+    auto bucket = [&](const Gen& g) { return (size_t)g.step * 15 + (size_t)g.cls * 3 + (size_t)g.grp; };
+    std::vector<int32_t> start((size_t)nsteps * 15 + 1, 0);
+    for (const Gen& g : gen) start[bucket(g) + 1]++;
+    for (size_t b2 = 0; b2 + 1 < start.size(); ++b2) start[b2 + 1] += start[b2];
+    for (size_t i = 0; i < gen.size(); ++i) ord[start[bucket(gen[i])]++] = (int32_t)i;
+  }
+  P.gemm_tasks.resize(gen.size());
+  {
+    size_t i = 0;
+    for (int st = 0; st < nsteps; ++st) {
+      Step& S = P.steps[st];
+      auto take = [&](int cls, int grp) {
+        const int32_t b0 = (int32_t)i;
+        while (i < ord.size() && gen[ord[i]].step == st && gen[ord[i]].cls == cls && gen[ord[i]].grp == grp) {
+          P.gemm_tasks[i] = gen[ord[i]].t;
+          ++i;
+        }
+        return Range{b0, (int32_t)i};
+      };
+      S.trsm = take(0, 0);
+      for (int g = 0; g < 3; ++g) S.upd[g].u128 = take(1, g);
+      for (int g = 0; g < 3; ++g) S.upd[g].u64 = take(2, g);
+      for (int g = 0; g < 3; ++g) S.upd[g].small_pairs = take(3, g);
+      for (int g = 0; g < 3; ++g) S.upd[g].u32 = take(4, g);
+    }
+  }
+  std::vector<Gen>().swap(gen);
+  lap("sort + take");
+  // row chunks of the small pairs, narrow (K <= 4) first inside every (step, group)
+  for (int st = 0; st < nsteps; ++st)
+    for (int g = 0; g < 3; ++g) {
+      UpdGroup& U = P.steps[st].upd[g];
+      U.small.begin = (int32_t)P.small_tasks.size();
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int gi = U.small_pairs.begin; gi < U.small_pairs.end; ++gi) {
+          const GemmTask& t = P.gemm_tasks[gi];
+          if ((t.K <= 4) != (pass == 0)) continue;
+          for (int r0 = 0; r0 < t.M; r0 += 256) {
+            SmallTask stt; stt.pair = gi; stt.row0 = r0; stt.nrows = std::min(256, t.M - r0); stt.pad = 0;
+            P.small_tasks.push_back(stt);
+          }
+        }
+        if (pass == 0) U.small_narrow = (int32_t)P.small_tasks.size() - U.small.begin;
+      }
+      U.small.end = (int32_t)P.small_tasks.size();
+    }
+
+  // tile prefixes per launch segment
+  for (int st = 0; st < nsteps; ++st) {
+    Step& S = P.steps[st];
+    int32_t acc = 0;
+    // TRSM row-tile height: the tallest of 64 / 32 / 16 that still gives every SM a tile
+    S.trsm_tm = 64;
+    for (int tm : {64, 32, 16}) {
+      acc = 0;
+      for (int i = S.trsm.begin; i < S.trsm.end; ++i) acc += cdiv(P.gemm_tasks[i].M, tm);
+      S.trsm_tm = tm;
+      if (acc >= 148) break;
+    }
+    acc = 0;
+    for (int i = S.trsm.begin; i < S.trsm.end; ++i) { P.gemm_tasks[i].tile0 = acc; acc += cdiv(P.gemm_tasks[i].M, S.trsm_tm); }
+    S.trsm_tiles = acc;
+    for (int g = 0; g < 3; ++g) {
+      UpdGroup& U = S.upd[g];
+      acc = 0;
+      for (int i = U.u128.begin; i < U.u128.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 128, 64); }
+      U.tiles128 = acc; acc = 0;
+      for (int i = U.u64.begin; i < U.u64.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 64, 64); }
+      U.tiles64 = acc; acc = 0;
+      for (int i = U.u32.begin; i < U.u32.end; ++i) { GemmTask& t = P.gemm_tasks[i]; t.tile0 = acc; acc += lower_tiles(t.M, t.N, 32, 32); }
+      U.tiles32 = acc;
+    }
+    acc = 0;
+    for (int i = S.blocks.begin; i < S.blocks.end; ++i) {
+      BlockTask& bk = P.block_tasks[i];
+      bk.tile0 = acc; acc += std::max(1, cdiv(P.sup[bk.sup].r - bk.j0 - bk.nb, 64));
+    }
+    S.solve_tiles = acc;
+  }
+  // ---- distributed top: panels to broadcast before each step ----------------------------------------------------
+  P.bcast_ptr.assign(nsteps + 1, 0);
+  if (dist_top) {
+    std::vector<std::vector<int64_t>> per(nsteps);
+    std::vector<std::vector<int32_t>> shp(nsteps);
+    for (int s = 0; s < supNo; ++s) {
+      if (P.owner[s] >= 0) continue;
+      const SupInfo& I = P.sup[s];
+      for (int b2 = 0; b2 < nblk[s]; ++b2) {
+        const int j0 = I.flags ? 0 : b2 * NB, nb = I.flags ? I.w : std::min(NB, I.w - j0);
+        auto& v = per[step0[s] + b2];
+        v.push_back(P.node_owner[node_first[s] + b2]);
+        v.push_back(I.valptr + (int64_t)j0 * I.r);
+        v.push_back(I.valptr + (int64_t)(j0 + nb) * I.r);
+        auto& h = shp[step0[s] + b2];
+        h.push_back(j0); h.push_back(I.r); h.push_back(nb);
+      }
+    }
+    for (int st = 0; st < nsteps; ++st) {
+      P.bcast.insert(P.bcast.end(), per[st].begin(), per[st].end());
+      P.bcast_shape.insert(P.bcast_shape.end(), shp[st].begin(), shp[st].end());
+      P.bcast_ptr[st + 1] = (int32_t)(P.bcast.size() / 3);
+    }
+  }
+  lap("small tasks + prefixes");
+  sweep_thread.join();
+  lap("sweep plan");
   // ---- what a factorization zeroes / assembles, what the ranks sum, which columns the sweeps solve ---------------
   {
     auto runs_of = [&](auto pred, std::vector<int64_t>& out) {
@@ -671,8 +697,11 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     const SupInfo& I = P.sup[t.sup];
     t.rowptr = I.rowptr; t.valptr = I.valptr; t.col0 = I.col0; t.r = I.r; t.need = P.node_need[t.node]; t.pad2 = 0;
   }
+  lap("runs");
   // the sweep kernels spin on counters: a task list that is not a topological order would hang the device
-  if (sweep_order_violations(P) != 0) { P.error = "internal error: sweep task order is not a topological order"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
+  const int64_t viol = sweep_order_violations(P);
+  lap("sweep order check");
+  if (viol != 0) { P.error = "internal error: sweep task order is not a topological order"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
   return PARSY_CUDA_OK;
 }
 
