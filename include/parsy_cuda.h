@@ -135,7 +135,8 @@ typedef struct parsy_cuda_options {
                           [5]=1 run the leaf region of the sweeps on the general dataflow kernel too,
                           [6]=1 keep the kernel classes of a step on one stream (no fan-out over auxiliary streams),
                           [7] sharded: consecutive top block columns per owner (0 = default 4),
-                          [8] sharded: broadcast lanes (communicator + stream each; 0 = default 4) */
+                          [8] sharded: broadcast lanes (communicator + stream each; 0 = default 2, at most 4),
+                          [9] sharded: 1 = broadcast whole block columns (no packing), 2 = also a dense factor buffer */
 } parsy_cuda_options;
 void parsy_cuda_options_default(parsy_cuda_options* opt);
 

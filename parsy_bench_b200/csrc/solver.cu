@@ -1917,7 +1917,7 @@ extern "C" int parsy_cuda_sharded_create(parsy_cuda_sharded** out, int n, const 
     TRYCU(cudaStreamCreateWithPriority(&sh->far_stream, cudaStreamNonBlocking, lo));
     for (auto& e : sh->ev_far) TRYCU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     TRYCU(cudaEventCreateWithFlags(&sh->ev_farjoin, cudaEventDisableTiming));
-    sh->lanes = opt->reserved[8] > 0 ? std::min((int)parsy_cuda_sharded::MAX_LANES, opt->reserved[8]) : parsy_cuda_sharded::MAX_LANES;
+    sh->lanes = opt->reserved[8] > 0 ? std::min((int)parsy_cuda_sharded::MAX_LANES, opt->reserved[8]) : 2;   // measured best at 8 GPUs: 2 (1: 47.6 ms, 2: 42.9, 3: 45.8, 4: 60.4 for the top of cfg3)
     for (int k = 0; k < sh->lanes; ++k) {
       TRYCU(cudaStreamCreateWithPriority(&sh->lane_stream[k], cudaStreamNonBlocking, hi));
       for (cudaEvent_t* e : {&sh->ev_B[0][k], &sh->ev_B[1][k], &sh->ev_cjoin[k]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
