@@ -68,11 +68,11 @@ using CfgTrsm16 = GemmCfg<16, 128, 16, 32, 16, 3>;
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_CTAS) k_gemm_tiles(const GemmTask* __restrict__ tasks, int ntasks,
                                                             double* __restrict__ lv, const double* __restrict__ linv,
-                                                            const int* __restrict__ rel) {
+                                                            const int* __restrict__ rel, int tile_base) {
   extern __shared__ __align__(16) double smem[];
   int* srel = reinterpret_cast<int*>(smem + C::STAGES * C::STAGE_DOUBLES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int bid = blockIdx.x;
+  const int bid = blockIdx.x + tile_base;   // long tile lists are launched in slices (launch_tiles in solver.cu)
   // locate the task that owns this tile (tile0 is an exclusive prefix over the launch)
   int lo = 0, hi = ntasks - 1;
   while (lo < hi) {

@@ -244,6 +244,21 @@ struct Fan {
   }
 };
 
+// A tile list is launched in slices of a few waves.  The block columns on the critical chain (POTRF: 177 KB of shared
+// memory, a whole SM) run on a high-priority stream next to these bulk launches; a pending CTA that needs a whole SM is
+// never placed while a lower-priority grid keeps refilling the half-SM slots its own CTAs free, i.e. until that grid has
+// drained (measured on cfg3 at 2 GPUs: POTRF launches waiting 1.8 ms behind a 5700-tile update).  Slicing bounds that
+// wait by the duration of one slice.  Only sharded plans slice: on one GPU the factorization is bound by the bulk
+// updates themselves and the extra wave tails cost more than the shorter waits return (cfg3: 211.7 -> 216.3 ms).
+template <class C>
+static int64_t launch_tiles(const GemmTask* tasks, int ntasks, int tiles, parsy_cuda_solver* s, cudaStream_t q) {
+  const int SLICE = s->phase != 0 ? 4 * 2 * 148 : (1 << 30);   // four waves at two CTAs per SM
+  int64_t n = 0;
+  for (int base = 0; base < tiles; base += SLICE, ++n)
+    k_gemm_tiles<C><<<std::min(SLICE, tiles - base), C::THREADS, C::SMEM, q>>>(tasks, ntasks, s->d_lv, s->d_linv, s->d_rel, base);
+  return n;
+}
+
 static int64_t launch_factor_phase(parsy_cuda_solver* s, const Step& S, cudaStream_t st, LaunchProfiler* prof) {
   int64_t launches = 0;
   Fan fan(s, st, prof == nullptr);
@@ -260,11 +275,11 @@ static int64_t launch_factor_phase(parsy_cuda_solver* s, const Step& S, cudaStre
       PROF_BEGIN(2);
       const GemmTask* tk = s->d_gemm + S.trsm.begin;
       if (S.trsm_tm == 64)
-        k_gemm_tiles<CfgTrsm><<<S.trsm_tiles, CfgTrsm::THREADS, CfgTrsm::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+        k_gemm_tiles<CfgTrsm><<<S.trsm_tiles, CfgTrsm::THREADS, CfgTrsm::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel, 0);
       else if (S.trsm_tm == 32)
-        k_gemm_tiles<CfgTrsm32><<<S.trsm_tiles, CfgTrsm32::THREADS, CfgTrsm32::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+        k_gemm_tiles<CfgTrsm32><<<S.trsm_tiles, CfgTrsm32::THREADS, CfgTrsm32::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel, 0);
       else
-        k_gemm_tiles<CfgTrsm16><<<S.trsm_tiles, CfgTrsm16::THREADS, CfgTrsm16::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel);
+        k_gemm_tiles<CfgTrsm16><<<S.trsm_tiles, CfgTrsm16::THREADS, CfgTrsm16::SMEM, q>>>(tk, S.trsm.size(), s->d_lv, s->d_linv, s->d_rel, 0);
       PROF_END();
       ++launches;
     }
@@ -296,26 +311,20 @@ static int64_t launch_update_group(parsy_cuda_solver* s, const UpdGroup& U, cuda
   if (U.tiles128) {
     cudaStream_t q = fan.pick();
     PROF_BEGIN(3);
-    k_gemm_tiles<Cfg128><<<U.tiles128, Cfg128::THREADS, Cfg128::SMEM, q>>>(s->d_gemm + U.u128.begin, U.u128.size(),
-                                                                           s->d_lv, s->d_linv, s->d_rel);
+    launches += launch_tiles<Cfg128>(s->d_gemm + U.u128.begin, U.u128.size(), U.tiles128, s, q);
     PROF_END();
-    ++launches;
   }
   if (U.tiles64) {
     cudaStream_t q = fan.pick();
     PROF_BEGIN(4);
-    k_gemm_tiles<Cfg64><<<U.tiles64, Cfg64::THREADS, Cfg64::SMEM, q>>>(s->d_gemm + U.u64.begin, U.u64.size(), s->d_lv,
-                                                                       s->d_linv, s->d_rel);
+    launches += launch_tiles<Cfg64>(s->d_gemm + U.u64.begin, U.u64.size(), U.tiles64, s, q);
     PROF_END();
-    ++launches;
   }
   if (U.tiles32) {
     cudaStream_t q = fan.pick();
     PROF_BEGIN(4);
-    k_gemm_tiles<Cfg32><<<U.tiles32, Cfg32::THREADS, Cfg32::SMEM, q>>>(s->d_gemm + U.u32.begin, U.u32.size(), s->d_lv,
-                                                                       s->d_linv, s->d_rel);
+    launches += launch_tiles<Cfg32>(s->d_gemm + U.u32.begin, U.u32.size(), U.tiles32, s, q);
     PROF_END();
-    ++launches;
   }
   if (U.small.size() - U.small_narrow > 0) {
     cudaStream_t q = fan.pick();
