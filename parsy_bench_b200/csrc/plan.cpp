@@ -161,13 +161,21 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     }
     double total = 0;
     for (int s = 0; s < supNo; ++s) if (root[s] == s) { roots.push_back(s); total += rcost[s]; }
+    // longest-processing-time first: subtrees by decreasing cost, each to the least loaded rank (ties: lowest rank).
+    // A contiguous deal keeps a rank's panels in fewer runs but balances badly when the subtrees are few and unequal
+    // (3D 27-pt 160^3, 9 subtrees, 8 ranks: max/mean 1.96 contiguous, 1.44 LPT; 3D 7-pt 100^3, 82 subtrees: 1.16 both).
     std::vector<int32_t> rown(supNo, -1);
-    double acc = 0;
-    for (int s : roots) {
-      // subtree goes to the rank whose cost interval contains its midpoint
-      const double mid = acc + 0.5 * rcost[s];
-      rown[s] = std::min(opt.world - 1, (int)(mid / (total > 0 ? total : 1.0) * opt.world));
-      acc += rcost[s];
+    (void)total;
+    {
+      std::vector<int32_t> byc(roots);
+      std::stable_sort(byc.begin(), byc.end(), [&](int32_t a, int32_t b2) { return rcost[a] > rcost[b2]; });
+      std::vector<double> load(opt.world, 0.0);
+      for (int s : byc) {
+        int best = 0;
+        for (int q = 1; q < opt.world; ++q) if (load[q] < load[best]) best = q;
+        rown[s] = best;
+        load[best] += rcost[s];
+      }
     }
     for (int s = 0; s < supNo; ++s) if (root[s] >= 0) P.owner[s] = rown[root[s]];
     for (const PairDesc& q : P.pairs)
