@@ -271,7 +271,11 @@ def traffic_for(name):
             with open(os.path.join(ROOT, "profiles", f)) as fh:
                 t = json.load(fh).get(name)
             if t:
-                return t.get("dram_bytes_per_launch"), t.get("source", f)
+                src = t.get("source", f)
+                if t.get("launch_flops"):
+                    src += (f" [captured launch: {t['launch_flops'] / 1e9:.1f} GFLOP in {t.get('launch_ms')} ms, "
+                            f"{t['dram_bytes_per_launch'] / t['launch_flops'] * 1e3:.2f} DRAM bytes per kFLOP]")
+                return t.get("dram_bytes_per_launch"), src
         except Exception:
             pass
     return None, None

@@ -121,3 +121,46 @@ def test_sweep_task_lists_on_a_larger_grid():
     rc, st = ex.plan_check(n, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.col2Sup, S.nLevels, S.levelPtr, S.parPtr, S.partition)
     assert rc == ex.OK and st["reserved"][7] == 0
     assert st["n_block_cols"] > 0 and 0 < st["reserved"][6] < st["reserved"][5]   # block columns exist: two launches per sweep
+
+
+def _trailing_flops(S, nb=128):
+    """Flops of the updates INSIDE wide supernodes, computed independently of the planner: block column b of width K
+    applies (2 M N - N^2) K flops to the N columns right of it over the M rows below it (the count k_gemm_tiles is
+    charged with, additive over any split of the target columns)."""
+    total = 0.0
+    sup, iptr = np.asarray(S.super, np.int64), np.asarray(S.i_ptr, np.int64)
+    for s in range(S.nsuper):
+        w = int(sup[s + 1] - sup[s])
+        r = int(iptr[sup[s + 1]] - iptr[sup[s]])
+        if w <= 32 and r <= 1024 and (r - w) * w * w <= 100000:
+            continue                      # narrow supernode: factored by one warp, no block columns (plan.h SMALL_*)
+        for j0 in range(0, w, nb):
+            k = min(nb, w - j0)
+            N, M = w - j0 - k, r - j0 - k
+            total += (2.0 * M * N - float(N) * N) * k
+    return total
+
+
+@pytest.mark.parametrize("case", [("2d5", 150, 64, 1, 2), ("3d27", 18, 16, 0, 2), ("3d7", 26, 592, 1, 4)])
+def test_planner_update_flops_are_conserved(case):
+    """Every (supernode, descendant) pair and every panel -> trailing-columns product is planned exactly once, however
+    the planner groups them (next-column updates, runs of four block columns applied late, K-splits, sharding by rank
+    and phase): the flops of the planned GEMM-shaped tasks equal the pair flops plus the trailing flops recomputed here."""
+    from parsy_bench_b200 import matrices
+    kind, N, c, l, d = case
+    n, Ap, Ai, Ax = matrices.laplacian(kind, N)
+    S = inspector.analyze(n, Ap, Ai, Ax, c, l, d)
+    args = (n, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.col2Sup, S.nLevels, S.levelPtr, S.parPtr, S.partition)
+    rc, st = ex.plan_check(*args)
+    assert rc == ex.OK
+    want = st["flops_update"] + _trailing_flops(S)
+    assert max(np.diff(S.super)) > 128                                   # block columns and runs exist
+    assert abs(st["reserved"][4] - want) <= 1e-9 * want + 8
+    for world in (2, 3, 8):
+        tot = 0
+        for rank in range(world):
+            for phase in (1, 2):
+                rc, sp = ex.plan_check(*args, rank=rank, world=world, phase=phase)
+                assert rc == ex.OK
+                tot += sp["reserved"][4]
+        assert abs(tot - want) <= 1e-9 * want + 8 * world * 2
