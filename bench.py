@@ -229,7 +229,7 @@ def reference_arm(args, name):
     # size the first run from a quick probe of the factorization time: one warm + what fits a third of the budget
     probe = {"cfg1": 0.1, "cfg2": 1.0, "cfg4": 5.0, "cfg3": 55.0, "cfg5": 1500.0}[name]
     first = int(max(2, min(iters, 1 + (budget / 3.0) // probe)))
-    later = int(max(1, min(args.steps, (budget / 8.0) // probe)))
+    later = int(max(1, min(args.steps, 3, (budget / 8.0) // probe)))     # the other triples: a few factorizations each
     best, tried = reference_sweep(kind, N, later, budget, first_iters=first)
     if best is None:
         base = cpu_baseline(kind, N, budget)
