@@ -129,6 +129,8 @@ struct parsy_cuda_solver {
   int* d_sync_init = nullptr; // sharded plans, backward sweep: initial counters with solved = 1 for the nodes of other plans
   bool dist_top = false;      // phase 2 with block-cyclic top: driven by parsy_cuda_sharded (broadcast after every step)
   BlockTask* d_invert = nullptr;   // phase 2, distributed top: block columns factored by other ranks
+  double* h_stage[2] = {nullptr, nullptr};       // pinned staging of the drop-in download (allocated on first use)
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // device arrays
   SupInfo* d_sup = nullptr;
@@ -527,6 +529,7 @@ extern "C" void parsy_cuda_destroy(parsy_cuda_solver* s) {
                   s->d_vals, s->d_lv, s->d_linv, s->d_rhs, s->d_xs, s->d_info, s->d_stasks, s->d_sctas, s->d_stargets,
                   s->d_need, s->d_ntiles, s->d_sync, s->d_Ac, s->d_Ar, s->d_perm, s->d_sys, s->d_norms, s->d_invert, s->d_sync_init};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (int k = 0; k < 2; ++k) { if (s->h_stage[k]) cudaFreeHost(s->h_stage[k]); if (s->ev_stage[k]) cudaEventDestroy(s->ev_stage[k]); }
   if (s->borrowed) { delete s; return; }
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {s->ev_fork, s->ev_join, s->ev_F[0], s->ev_F[1], s->ev_R[0], s->ev_R[1]}) if (e) cudaEventDestroy(e);
@@ -1173,13 +1176,14 @@ int download_chunked(parsy_cuda_solver* s, double* dst, const double* d_src, siz
     CU(cudaStreamSynchronize(s->stream));
     return 0;
   }
-  double* stage[2] = {nullptr, nullptr};
-  cudaEvent_t done[2] = {nullptr, nullptr};
+  // the staging buffers stay with the handle: pinning 64 MiB costs as much as moving a few hundred MB
   int rc = 0;
   for (int k = 0; k < 2 && !rc; ++k) {
-    if (cudaMallocHost((void**)&stage[k], CH * 8) != cudaSuccess || cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming) != cudaSuccess)
-      rc = fail(PARSY_CUDA_ERR_CUDA, "pinned staging buffer");
+    if (!s->h_stage[k] && cudaMallocHost((void**)&s->h_stage[k], CH * 8) != cudaSuccess) { s->h_stage[k] = nullptr; rc = fail(PARSY_CUDA_ERR_CUDA, "pinned staging buffer"); }
+    if (!rc && !s->ev_stage[k] && cudaEventCreateWithFlags(&s->ev_stage[k], cudaEventDisableTiming) != cudaSuccess) { s->ev_stage[k] = nullptr; rc = fail(PARSY_CUDA_ERR_CUDA, "event"); }
   }
+  double** stage = s->h_stage;
+  cudaEvent_t* done = s->ev_stage;
   const size_t nch = (count + CH - 1) / CH;
   for (size_t k = 0; k <= nch && !rc; ++k) {
     if (k < nch) {
@@ -1193,7 +1197,6 @@ int download_chunked(parsy_cuda_solver* s, double* dst, const double* d_src, siz
       else memcpy(dst + off, stage[(k - 1) & 1], len * 8);
     }
   }
-  for (int k = 0; k < 2; ++k) { if (stage[k]) cudaFreeHost(stage[k]); if (done[k]) cudaEventDestroy(done[k]); }
   return rc;
 }
 }  // namespace
@@ -1222,6 +1225,8 @@ extern "C" int parsy_cuda_cholesky_left_par_05(int n, int* c, int* r, double* va
   if (cache) {
     key = structure_key(1, n, c, r, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition);
     s = cache_take(key);
+    // a 64-bit content hash decides; the sizes must agree as well
+    if (s && (s->plan.n != n || s->plan.nsuper != supNo || s->plan.nnzA != (int64_t)c[n] || s->plan.xsize != (int64_t)lC[n])) { parsy_cuda_destroy(s); s = nullptr; }
   }
   int rc = 0;
   if (!s) rc = parsy_cuda_create(&s, n, c, r, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr,
@@ -1275,6 +1280,7 @@ static int dropin_solve(int n, size_t* Lp, int* Li, double* Lx, size_t* Li_ptr, 
   if (cache) {
     key = structure_key(2, n, nullptr, nullptr, Lp, Li, Li_ptr, sup2col, supNo, col2sup, nLevels, levelPtr, parPtr, partition);
     s = cache_take(key);
+    if (s && (s->plan.n != n || s->plan.nsuper != supNo || s->plan.xsize != (int64_t)Lp[n])) { parsy_cuda_destroy(s); s = nullptr; }
   }
   int rc = 0;
   if (!s) rc = parsy_cuda_create(&s, n, nullptr, nullptr, Lp, Li, Li_ptr, sup2col, supNo, nullptr, col2sup, nLevels,
