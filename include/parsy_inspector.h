@@ -72,6 +72,16 @@ int parsy_etree_level_set(int nsuper, const int* sParent, int* levelPtr /*nsuper
  * or -1 (missing diagonal, entry above the diagonal). */
 int parsy_build_level_set_csc(int n, const int* Lp, const int* Li, int* levelPtr, int* levelSet);
 
+/* Load-balanced level coarsening on the DAG of a general lower-triangular CSC matrix (diagonal first in each column) —
+ * replaces getCoarseLevelSet_DAG_CSC03 (cholesky/InspectionDAG_03.h:14; call site
+ * examples/triangularTest_DAG_nonChordal.cpp:343-360), the inspector of lsolveParH2 (Triangular_CSC.h:76) for inputs that
+ * are not Cholesky factors.  innerParts / minLevelDist / divRate as in the reference (its drivers pass costParam /
+ * levelParam / divRate); nodeCost: n doubles or NULL for unit costs (what the reference driver uses).  Outputs, bit for bit
+ * the reference's: *nLevels H-levels, levelPtr (caller: n+1 ints; nLevels+1 used) into parPtr (caller: n+1 ints) into
+ * partition (n columns).  Returns 0, 2 for bad arguments, 3 where the reference itself would index out of range. */
+int parsy_dag_lbc_csc(int n, const int* Lp, const int* Li, int innerParts, int minLevelDist, int divRate,
+                      const double* nodeCost, int* nLevels, int* levelPtr, int* parPtr, int* partition);
+
 /* BCSC -> CSC conversion of a supernodal factor (common/Util.h:311 bcsc2csc); Cp has n+1 entries; returns nnz.
  * Pass Ci = Cx = NULL to only count. */
 int64_t parsy_bcsc2csc(const parsy_symbolic* sym, const double* Lx, int* Cp, int* Ci, double* Cx);

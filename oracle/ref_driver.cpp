@@ -34,6 +34,8 @@
 #include "Triangular_BCSC.h"
 #include "Triangular_CSC.h"
 #include "Inspection_Level.h"
+#include "DFS.h"
+#include "InspectionDAG_03.h"
 #ifdef PARSY_GPU_FORWARD
 // The same driver with the reference's call sites forwarded to libparsy_cuda (include/parsy_cuda_dropin.h, the header
 // INTEGRATION.md gives to a maintainer): the reference's inspector and harness drive the CUDA executor — parsy_ref_gpu.
@@ -134,7 +136,21 @@ int main(int argc, char** argv) {
     for (size_t i2 = 0; i2 < n; ++i2) x[i2] = 1.0 + (double)i2 / (double)n;
     lsolvePar((int)n, Ap.data(), Ai.data(), Ax.data(), x.data(), levels, lp, ls, chunk);
     dump(dir, "tri_x_par.f64", x.data(), n);
-    printf("{\"n\": %zu, \"nnz\": %zu, \"levels\": %d}\n", n, nnzA, levels);
+    // LBC on the DAG of a general lower-triangular matrix (cholesky/InspectionDAG_03.h:14, call site
+    // examples/triangularTest_DAG_nonChordal.cpp:343-360: unit node costs) and lsolveParH2 on its schedule (:405)
+    int hLevels = 0, hParts = 0, *hLevelPtr = NULL, *hLevelSet = NULL, *hParPtr = NULL, *hPartition = NULL;
+    std::vector<double> nodeCost(n, 1.0);
+    int avgcc = getCoarseLevelSet_DAG_CSC03(n, Ap.data(), Ai.data(), hLevels, hLevelPtr, hLevelSet, hParts, hParPtr,
+                                            hPartition, costParam, levelParam, divRate, nodeCost.data());
+    int nparts = hLevelPtr[hLevels];
+    dump(dir, "dag_levelPtr.i32", hLevelPtr, (size_t)hLevels + 1); dump(dir, "dag_parPtr.i32", hParPtr, (size_t)nparts + 1);
+    dump(dir, "dag_partition.i32", hPartition, n);
+    for (size_t i2 = 0; i2 < n; ++i2) x[i2] = 1.0 + (double)i2 / (double)n;
+    lsolveParH2((int)n, Ap.data(), Ai.data(), Ax.data(), x.data(), hLevels, hLevelPtr, hLevelSet, hParts, hParPtr,
+                hPartition, chunk);
+    dump(dir, "tri_x_h2.f64", x.data(), n);
+    printf("{\"n\": %zu, \"nnz\": %zu, \"levels\": %d, \"dag_levels\": %d, \"dag_parts\": %d, \"dag_avg_cc\": %d}\n", n,
+           nnzA, levels, hLevels, nparts, avgcc);
     return 0;
   }
 

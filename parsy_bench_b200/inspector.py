@@ -179,6 +179,29 @@ def make_lower_half(in_path, out_path, tol=0.1):
         raise MatrixMarketError(rc, L.parsy_inspector_last_error().decode())
 
 
+def dag_lbc_csc(n, Lp, Li, innerParts, minLevelDist, divRate, nodeCost=None):
+    """``getCoarseLevelSet_DAG_CSC03`` (cholesky/InspectionDAG_03.h:14): LBC schedule over the COLUMNS of a general
+    lower-triangular CSC matrix, the input of ``lsolveParH2``.  Returns ``(nLevels, levelPtr, parPtr, partition)``."""
+    Lp = np.ascontiguousarray(Lp, np.int32)
+    Li = np.ascontiguousarray(Li, np.int32)
+    n = int(n)
+    lp, pp, part = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.int32), np.zeros(n, np.int32)
+    nl = ctypes.c_int(0)
+    cost = None if nodeCost is None else np.ascontiguousarray(nodeCost, np.float64)
+    f = lib().parsy_dag_lbc_csc
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
+                  ctypes.POINTER(ctypes.c_int), c_void_p, c_void_p, c_void_p]
+    rc = f(n, Lp.ctypes.data_as(c_void_p), Li.ctypes.data_as(c_void_p), int(innerParts), int(minLevelDist), int(divRate),
+           None if cost is None else cost.ctypes.data_as(c_void_p), ctypes.byref(nl), lp.ctypes.data_as(c_void_p),
+           pp.ctypes.data_as(c_void_p), part.ctypes.data_as(c_void_p))
+    if rc != 0:
+        raise ValueError(f"parsy_dag_lbc_csc: {lib().parsy_inspector_last_error().decode()}")
+    nl = int(nl.value)
+    nparts = int(lp[nl])
+    return nl, lp[:nl + 1].copy(), pp[:nparts + 1].copy(), part
+
+
 def build_level_set_csc(n, Lp, Li):
     """``buildLevelSet_CSC`` (triangularSolve/Inspection_Level.h:12): wavefront level sets of a lower-triangular CSC
     matrix (diagonal first per column) for ``lsolvePar``.  Returns ``(levels, levelPtr[levels+1], levelSet[n])``."""

@@ -602,11 +602,20 @@ def test_csc_solves_of_a_general_triangular_matrix(tmp_path, n, per_col, seed):
     x = b.copy()
     assert ex.lsolvePar(n, Lp, Li, Lx, x, levels, lptr, lset, 1) == 1
     assert rel_err(x, want) < 1e-11
+    # lsolveParH2 on the LBC schedule of the column DAG (restated getCoarseLevelSet_DAG_CSC03,
+    # examples/triangularTest_DAG_nonChordal.cpp:357,405)
+    nl, hlp, hpp, hpart = inspector.dag_lbc_csc(n, Lp, Li, 8, 2, 2)
+    xh = b.copy()
+    assert ex.lsolveParH2(n, Lp, Li, Lx, xh, nl, hlp, None, 0, hpp, hpart, 1) == 1
+    assert rel_err(xh, want) < 1e-11
     if refdump.have_ref():
         f = tmp_path / "tri.mtx"
         matrices.write_mtx(f, n, Lp, Li, Lx, symmetric=False)
         d = tmp_path / "dump"
         d.mkdir()
-        subprocess.run([refdump.REF_BIN, "--mtx", str(f), "--tri-only", "--dump", str(d)], check=True, capture_output=True)
+        subprocess.run([refdump.REF_BIN, "--mtx", str(f), "--tri-only", "--dump", str(d), "--cost", "8", "--level", "2",
+                        "--div", "2"], check=True, capture_output=True)
         assert rel_err(x, np.fromfile(d / "tri_x.f64", np.float64)) < 1e-11
         assert rel_err(x, np.fromfile(d / "tri_x_par.f64", np.float64)) < 1e-11
+        assert np.array_equal(hpart, np.fromfile(d / "dag_partition.i32", np.int32))      # same schedule ...
+        assert rel_err(xh, np.fromfile(d / "tri_x_h2.f64", np.float64)) < 1e-11           # ... same solution

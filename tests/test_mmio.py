@@ -222,3 +222,74 @@ def test_level_sets_match_the_reference(tmp_path, n, per_col, seed):
     levels, lptr, lset = inspector.build_level_set_csc(n, Lp, Li)
     assert np.array_equal(np.fromfile(d / "tri_levelPtr.i32", np.int32), lptr)
     assert np.array_equal(np.fromfile(d / "tri_levelSet.i32", np.int32), lset)
+
+
+# ---- LBC on the DAG of a general lower-triangular matrix (the inspector of lsolveParH2, InspectionDAG_03.h) ---------
+def check_h2_schedule(n, Lp, Li, nl, lp, pp, part):
+    """every column once; a column's producers sit in an earlier H-level or earlier in the same w-partition"""
+    assert lp[0] == 0 and len(lp) == nl + 1 and pp[0] == 0 and len(pp) == lp[-1] + 1 and pp[-1] == n
+    assert sorted(part.tolist()) == list(range(n))
+    pos, lev, par = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int64)
+    for H in range(nl):
+        for j1 in range(lp[H], lp[H + 1]):
+            for k in range(pp[j1], pp[j1 + 1]):
+                c = part[k]
+                pos[c], lev[c], par[c] = k, H, j1
+    for j in range(n):
+        for i in Li[Lp[j] + 1:Lp[j + 1]]:
+            assert lev[j] < lev[i] or (par[j] == par[i] and pos[j] < pos[i])
+
+
+@pytest.mark.parametrize("n,per_col,seed,params", [(1, 0, 0, (4, 2, 2)), (50, 0, 1, (4, 2, 2)), (300, 2, 2, (8, 2, 2)),
+                                                    (2000, 4, 3, (16, 1, 3)), (500, 40, 4, (3, 5, 2))])
+def test_dag_lbc_schedule_is_legal(n, per_col, seed, params):
+    n, Lp, Li, _ = random_lower_triangular(n, per_col, seed)
+    nl, lp, pp, part = inspector.dag_lbc_csc(n, Lp, Li, *params)
+    check_h2_schedule(n, Lp, Li, nl, lp, pp, part)
+
+
+def test_dag_lbc_rejects_bad_input():
+    with pytest.raises(ValueError):
+        inspector.dag_lbc_csc(2, [0, 1, 2], [1, 1], 4, 2, 2)           # column 0 does not start with its diagonal
+    with pytest.raises(ValueError):
+        inspector.dag_lbc_csc(2, [0, 1, 2], [0, 1], 0, 2, 2)           # no bins
+    with pytest.raises(ValueError):
+        inspector.dag_lbc_csc(2, [0, 1, 2], [0, 1], 4, 2, 0)           # the level cut would never advance
+
+
+def _ref_dag(tmp_path, n, Lp, Li, Lx, cost, level, div):
+    f = tmp_path / "tri.mtx"
+    matrices.write_mtx(f, n, Lp, Li, Lx, symmetric=False)
+    d = tmp_path / "dump"
+    d.mkdir(exist_ok=True)
+    subprocess.run([refdump.REF_BIN, "--mtx", str(f), "--tri-only", "--dump", str(d), "--cost", str(cost), "--level",
+                    str(level), "--div", str(div)], check=True, capture_output=True)
+    return {k: np.fromfile(d / f"dag_{k}.i32", np.int32) for k in ("levelPtr", "parPtr", "partition")}, d
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="compiled reference (oracle/_ref) not built")
+@pytest.mark.parametrize("n,per_col,seed,params", [(400, 3, 11, (8, 2, 2)), (1500, 6, 12, (16, 1, 2)), (64, 20, 13, (4, 2, 3)),
+                                                    (3000, 2, 5, (8, 3, 4)), (800, 10, 3, (2, 1, 1)), (6000, 2, 8, (148, 2, 2)),
+                                                    (300, 2, 2, (8, 40, 2)), (2500, 4, 9, (64, 2, 3))])
+def test_dag_lbc_matches_the_reference(tmp_path, n, per_col, seed, params):
+    """getCoarseLevelSet_DAG_CSC03 of the reference (cholesky/InspectionDAG_03.h:14, run through oracle/_ref/parsy_ref
+    --tri-only with unit node costs as examples/triangularTest_DAG_nonChordal.cpp:343-360 does) on random triangular
+    matrices that are not Cholesky factors: same levelPtr, parPtr and partition, bit for bit."""
+    n, Lp, Li, Lx = random_lower_triangular(n, per_col, seed)
+    R, _ = _ref_dag(tmp_path, n, Lp, Li, Lx, *params)
+    nl, lp, pp, part = inspector.dag_lbc_csc(n, Lp, Li, *params)
+    assert np.array_equal(lp, R["levelPtr"]) and np.array_equal(pp, R["parPtr"]) and np.array_equal(part, R["partition"])
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="compiled reference (oracle/_ref) not built")
+def test_dag_lbc_matches_the_reference_on_a_cholesky_factor(tmp_path):
+    """... and on the column form of a supernodal Cholesky factor (dense chains inside the supernodes, components that
+    meet and are merged): the golden 2D 30x30 case."""
+    from common import load_golden
+    G = load_golden("2d5_N30_c8_l1_d2")
+    n, Lp, Li, Lx = G.n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x
+    for params in ((8, 2, 2), (4, 3, 5), (16, 1, 7)):
+        R, _ = _ref_dag(tmp_path, n, Lp, Li, Lx, *params)
+        nl, lp, pp, part = inspector.dag_lbc_csc(n, Lp, Li, *params)
+        assert np.array_equal(lp, R["levelPtr"]) and np.array_equal(pp, R["parPtr"]) and np.array_equal(part, R["partition"])
+        check_h2_schedule(n, Lp, Li, nl, lp, pp, part)
