@@ -100,6 +100,26 @@ def test_resident_handle_and_block_sizes(nb):
     H2.close()
 
 
+def test_run_to_run_spread_is_bounded():
+    """Every update lands through red.global.add.f64, so the summation order — and with it the last bits of L — changes
+    from run to run.  The spread between factorizations of the same matrix on the same handle stays at rounding level,
+    three orders of magnitude inside the 1e-9 parity tolerance (wide separators: 3D 27-point, 22^3)."""
+    S = analyze("3d27", 22, 148, 1, 4)
+    H = ex.Solver(S.n, S.A2_p, S.A2_i, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.sParent, S.col2Sup, S.nLevels,
+                  S.levelPtr, S.parPtr, S.partition)
+    H.set_values(S.A2_x)
+    runs = []
+    for _ in range(4):
+        H.factor()
+        assert H.sync()
+        runs.append(H.get_factor())
+    H.close()
+    spread = max(rel_err(r, runs[0]) for r in runs[1:])
+    print(f"run-to-run spread of the factor: {spread:.2e}")
+    assert spread < 1e-12
+    assert all(np.array_equal(r == 0.0, runs[0] == 0.0) for r in runs[1:])
+
+
 def test_not_positive_definite_returns_false():
     G = load_golden("2d5_N30_c8_l1_d2")
     vals = G.A2_x.copy()
