@@ -82,6 +82,15 @@ int parsy_build_level_set_csc(int n, const int* Lp, const int* Li, int* levelPtr
 int parsy_dag_lbc_csc(int n, const int* Lp, const int* Li, int innerParts, int minLevelDist, int divRate,
                       const double* nodeCost, int* nLevels, int* levelPtr, int* parPtr, int* partition);
 
+/* The supernodal twin: LBC on the DAG of the BLOCKS of a BCSC factor — replaces getCoarseLevelSet_DAG_BCSC02
+ * (cholesky/Inspection_DAG_02.h:15; call site cholesky/LSparsity.h:1412 in analyze_DAG, the inspector behind
+ * examples/triangularTest_DAG.cpp).  Li_ptr / lR / blk2col (`super`) / col2blk (`col2Sup`) as in the BCSC structure;
+ * nodeCost: nblocks doubles or NULL for unit costs (analyze_DAG passes computeCostperBlock = width x rows).  Outputs as
+ * parsy_dag_lbc_csc over block ids: a schedule that cholesky_left_par_05 and H2LeveledBlockedLsolve accept. */
+int parsy_dag_lbc_bcsc(int nblocks, const size_t* Li_ptr, const int* lR, const int* blk2col, const int* col2blk,
+                       int innerParts, int minLevelDist, int divRate, const double* nodeCost, int* nLevels, int* levelPtr,
+                       int* parPtr, int* partition);
+
 /* BCSC -> CSC conversion of a supernodal factor (common/Util.h:311 bcsc2csc); Cp has n+1 entries; returns nnz.
  * Pass Ci = Cx = NULL to only count. */
 int64_t parsy_bcsc2csc(const parsy_symbolic* sym, const double* Lx, int* Cp, int* Ci, double* Cx);

@@ -36,6 +36,7 @@
 #include "Inspection_Level.h"
 #include "DFS.h"
 #include "InspectionDAG_03.h"
+#include "Inspection_DAG_02.h"
 #ifdef PARSY_GPU_FORWARD
 // The same driver with the reference's call sites forwarded to libparsy_cuda (include/parsy_cuda_dropin.h, the header
 // INTEGRATION.md gives to a maintainer): the reference's inspector and harness drive the CUDA executor — parsy_ref_gpu.
@@ -180,6 +181,19 @@ int main(int argc, char** argv) {
   dump(dir, "levelPtr.i32", levelPtr, nLevels + 1); dump(dir, "parPtr.i32", parPtr, nParts + 1);
   dump(dir, "partition.i32", partition, nsuper);
 
+  {
+    // DAG-based LBC over the factor's blocks (cholesky/Inspection_DAG_02.h:15; as analyze_DAG calls it,
+    // cholesky/LSparsity.h:1412, with computeCostperBlock = width x rows as node cost)
+    int dLevels = 0, dParts = 0, *dLevelPtr = NULL, *dLevelSet = NULL, *dParPtr = NULL, *dPartition = NULL;
+    std::vector<double> blockCost(nsuper);
+    for (size_t s2 = 0; s2 < nsuper; ++s2)
+      blockCost[s2] = (double)(L->super[s2 + 1] - L->super[s2]) * (double)(L->i_ptr[L->super[s2 + 1]] - L->i_ptr[L->super[s2]]);
+    getCoarseLevelSet_DAG_BCSC02(nsuper, L->p, L->i_ptr, L->s, L->super, L->col2Sup, dLevels, dLevelPtr, dLevelSet, dParts,
+                                 dParPtr, dPartition, costParam, levelParam, divRate, blockCost.data());
+    dump(dir, "dagb_levelPtr.i32", dLevelPtr, (size_t)dLevels + 1);
+    dump(dir, "dagb_parPtr.i32", dParPtr, (size_t)dLevelPtr[dLevels] + 1);
+    dump(dir, "dagb_partition.i32", dPartition, nsuper);
+  }
   CSC* A1 = ptranspose(Amat, 2, L->Perm, NULL, 0, status);   // triu(PAP') (choleskyTest01.cpp:190)
   CSC* A2 = ptranspose(A1, 2, NULL, NULL, 0, status);        // tril(PAP') (choleskyTest01.cpp:191)
   dump(dir, "A1_p.i32", A1->p, n + 1); dump(dir, "A1_i.i32", A1->i, nnzA); dump(dir, "A1_x.f64", A1->x, nnzA);

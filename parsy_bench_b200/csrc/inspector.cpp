@@ -407,6 +407,14 @@ void lbc_schedule(int n, const ivec& etree, const ivec& super, const std::vector
   }
 }
 
+}  // namespace
+// shared with dag_lbc.cpp (the block DAG coarsening cuts its levels with the same rule)
+int parsy_height_partitioning(int nwaves, const std::vector<int>& wptr, int H, int innerParts, int minLevelDist, int divRate,
+                              std::vector<int>& sizes, std::vector<int>& bounds) {
+  return height_partitioning(nwaves, wptr, H, innerParts, minLevelDist, divRate, sizes, bounds);
+}
+namespace {
+
 template <class T> T* dup(const std::vector<T>& v) {
   T* p = new T[std::max<size_t>(v.size(), 1)];
   if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));

@@ -202,6 +202,35 @@ def dag_lbc_csc(n, Lp, Li, innerParts, minLevelDist, divRate, nodeCost=None):
     return nl, lp[:nl + 1].copy(), pp[:nparts + 1].copy(), part
 
 
+def dag_lbc_bcsc(S, innerParts, minLevelDist, divRate, nodeCost="width_x_rows"):
+    """``getCoarseLevelSet_DAG_BCSC02`` (cholesky/Inspection_DAG_02.h:15): LBC on the DAG of the blocks of the factor
+    described by ``S`` (a Symbolic or anything with super / col2Sup / s / i_ptr / nsuper).  ``nodeCost``: array, None for
+    unit costs, or "width_x_rows" (what the reference's analyze_DAG passes).  Returns (nLevels, levelPtr, parPtr, partition)."""
+    sup = np.ascontiguousarray(S.super, np.int32)
+    c2s = np.ascontiguousarray(S.col2Sup, np.int32)
+    lR = np.ascontiguousarray(S.s, np.int32)
+    iptr = np.ascontiguousarray(S.i_ptr, np.uint64)
+    nb = int(S.nsuper)
+    if isinstance(nodeCost, str):
+        ip = iptr.astype(np.int64)
+        nodeCost = (np.diff(sup.astype(np.int64)) * (ip[sup[1:]] - ip[sup[:-1]])).astype(np.float64)
+    cost = None if nodeCost is None else np.ascontiguousarray(nodeCost, np.float64)
+    lp, pp, part = np.zeros(nb + 1, np.int32), np.zeros(nb + 1, np.int32), np.zeros(nb, np.int32)
+    nl = ctypes.c_int(0)
+    f = lib().parsy_dag_lbc_bcsc
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
+                  ctypes.POINTER(ctypes.c_int), c_void_p, c_void_p, c_void_p]
+    rc = f(nb, iptr.ctypes.data_as(c_void_p), lR.ctypes.data_as(c_void_p), sup.ctypes.data_as(c_void_p),
+           c2s.ctypes.data_as(c_void_p), int(innerParts), int(minLevelDist), int(divRate),
+           None if cost is None else cost.ctypes.data_as(c_void_p), ctypes.byref(nl), lp.ctypes.data_as(c_void_p),
+           pp.ctypes.data_as(c_void_p), part.ctypes.data_as(c_void_p))
+    if rc != 0:
+        raise ValueError(f"parsy_dag_lbc_bcsc: {lib().parsy_inspector_last_error().decode()}")
+    nl = int(nl.value)
+    return nl, lp[:nl + 1].copy(), pp[:int(lp[nl]) + 1].copy(), part
+
+
 def build_level_set_csc(n, Lp, Li):
     """``buildLevelSet_CSC`` (triangularSolve/Inspection_Level.h:12): wavefront level sets of a lower-triangular CSC
     matrix (diagonal first per column) for ``lsolvePar``.  Returns ``(levels, levelPtr[levels+1], levelSet[n])``."""

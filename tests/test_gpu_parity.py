@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import pytest
 
-from common import FULL_CASES, load_golden, rel_err, parse_case, full_matrix, View
+from common import FULL_CASES, load_golden, rel_err, parse_case, full_matrix, View, as_view
 from refdump import have_ref, ref_case
 from parsy_bench_b200 import executor as ex, inspector, matrices, _lib
 
@@ -98,6 +98,26 @@ def test_resident_handle_and_block_sizes(nb):
     assert H2.sync() and rel_err(H2.get_factor(), ref) < TOL
     H.close()
     H2.close()
+
+
+@pytest.mark.parametrize("case", [("2d5", 100, 8, 1, 2), ("3d27", 14, 16, 2, 2)])
+def test_factor_and_solve_on_the_dag_based_schedule(case):
+    """The DAG-based LBC schedule over the factor's blocks (restated getCoarseLevelSet_DAG_BCSC02,
+    cholesky/Inspection_DAG_02.h:15 — what analyze_DAG hands to cholesky_left_par_05 and H2LeveledBlockedLsolve in
+    examples/triangularTest_DAG.cpp:100-125,281) drives the CUDA executor like the tree-based one."""
+    S = analyze(*case)
+    nl, lp, pp, part = inspector.dag_lbc_bcsc(S, case[2], case[3], case[4])
+    V = View(as_view(S))
+    V["levelPtr"], V["parPtr"], V["partition"] = lp, pp, part
+    ok, lv = dropin_factor(V)
+    assert ok
+    ref = orc.cholesky_left_par_05(S)
+    assert rel_err(lv, ref) < TOL
+    b = orc.rhs_init_blocked(S, ref)
+    x = b.copy()
+    assert ex.H2LeveledBlockedLsolve(S.n, S.p, S.s, ref, int(S.xsize), S.i_ptr, S.col2Sup, S.super, S.nsuper, x, nl, lp,
+                                     None, 0, pp, part, 1) == 1
+    assert np.max(np.abs(x - 1.0)) < 1e-9
 
 
 def test_run_to_run_spread_is_bounded():

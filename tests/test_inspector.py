@@ -124,3 +124,23 @@ def test_bit_exact_vs_live_reference(case):
     for k in INT_ARRAYS:
         ref = R[k][:S.ssize] if k == "s" else R[k]
         assert np.array_equal(getattr(S, k), ref), k
+
+
+@pytest.mark.skipif(not have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("case", [("2d5", 30, 8, 1, 2), ("2d5", 64, 16, 2, 2), ("3d7", 12, 8, 1, 2), ("3d27", 10, 4, 0, 2),
+                                  ("2d5", 150, 592, 1, 4), ("3d7", 20, 37, 2, 3), ("3d27", 16, 8, -1, 4)])
+def test_dag_lbc_over_blocks_matches_the_reference(case):
+    """getCoarseLevelSet_DAG_BCSC02 (cholesky/Inspection_DAG_02.h:15, called as analyze_DAG does, LSparsity.h:1412, with
+    width x rows as node cost): the DAG-based LBC schedule over the factor's blocks, bit for bit; and the executor's
+    planner accepts it (every descendant in an earlier H-level or earlier in the same w-partition)."""
+    from parsy_bench_b200 import executor as ex
+    kind, N, c, l, d = case
+    R = ref_case(kind, N, cost=c, level=l, div=d, factor=False, solve=False)
+    n, Ap, Ai, Ax = matrices.laplacian(kind, N)
+    S = inspector.analyze(n, Ap, Ai, Ax, c, l, d)
+    nl, lp, pp, part = inspector.dag_lbc_bcsc(S, c, l, d)
+    assert np.array_equal(lp, R["dagb_levelPtr"]) and np.array_equal(pp, R["dagb_parPtr"])
+    assert np.array_equal(part, R["dagb_partition"])
+    assert sorted(part.tolist()) == list(range(S.nsuper))
+    rc, _ = ex.plan_check(n, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.col2Sup, nl, lp, pp, part)
+    assert rc == ex.OK
