@@ -1,3 +1,4 @@
+"""Dev tool (one GPU): the column-solve dataflow kernel on small structured matrices against scipy."""
 import sys, numpy as np
 sys.path.insert(0, "/root/repo")
 import scipy.sparse as sp, scipy.sparse.linalg as spl
