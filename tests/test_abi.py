@@ -97,6 +97,28 @@ def test_no_device_is_an_error_not_a_fallback():
     x = np.ones(G.n)
     assert ex.blockedLsolve(G.n, G.p, G.s, G.valL, 0, G.i_ptr, G.col2Sup, G.super, G.nsuper, x) == 0
     assert ex.blockedLsolve(G.n, None, G.s, G.valL, 0, G.i_ptr, G.col2Sup, G.super, G.nsuper, x) == 0  # NULL Lp
+    # the round-2 entry points fail just as loudly: sharded handle (emulated ranks need a device too), column solves
+    with pytest.raises(ex.ParsyCudaError) as e:
+        ex.Sharded(G.n, G.A2_p, G.A2_i, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.sParent, G.col2Sup,
+                   len(G.levelPtr) - 1, G.levelPtr, G.parPtr, G.partition, 0, 2, None)
+    assert e.value.code == ex.ERR_NO_DEVICE
+    with pytest.raises(ex.ParsyCudaError) as e:
+        ex.CscSolver(G.n, G.Lcsc_p, G.Lcsc_i)
+    assert e.value.code == ex.ERR_NO_DEVICE
+    y = np.ones(G.n)
+    assert ex.lsolve(G.n, G.Lcsc_p, G.Lcsc_i, G.Lcsc_x, y) == 0 and np.all(y == 1.0)
+
+
+def test_sharded_create_rejects_bad_arguments_before_touching_a_device():
+    G = load_golden("2d5_N12_c8_l1_d2")
+    args = (G.n, G.A2_p, G.A2_i, G.p, G.s, G.i_ptr, G.super, G.nsuper, G.sParent, G.col2Sup, len(G.levelPtr) - 1,
+            G.levelPtr, G.parPtr, G.partition)
+    for rank, world in ((0, 1), (2, 2), (-1, 4)):
+        with pytest.raises(ex.ParsyCudaError) as e:
+            ex.Sharded(*args, rank, world, None)
+        assert e.value.code == ex.ERR_BAD_ARG
+    with pytest.raises(ValueError):
+        ex.Sharded(*args, 0, 2, b"too short")
 
 
 @pytest.mark.parametrize("name", ["2d5_N30_c8_l1_d2", "2d5_N30_c64_l0_d4", "3d7_N7_c8_l1_d2", "3d27_N6_c4_l0_d2"])
