@@ -236,6 +236,13 @@ int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, const size_t* 
                           const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
                           const int* partition, const parsy_cuda_options* opt, parsy_cuda_stats* out);
 
+/* HOST-ONLY: 64-bit digest of everything the planner hands to the executor for these arrays and options (task lists,
+ * step table, sweep plan, ownership, broadcast lists): equal digests = the same launches on the same operands.  The CPU
+ * test-suite pins it for a set of matrices, so that planner changes that alter the device work are seen without a GPU. */
+int parsy_cuda_plan_digest(int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo,
+                           const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                           const int* partition, const parsy_cuda_options* opt, uint64_t* digest);
+
 /* Raw device pointers for callers that keep data on the GPU (e.g. bench.py with torch tensors). */
 double* parsy_cuda_device_factor(parsy_cuda_solver* s);   /* xsize doubles */
 double* parsy_cuda_device_rhs(parsy_cuda_solver* s);      /* n doubles     */

@@ -219,6 +219,9 @@ struct Plan {
 // Returns 0 on success, PARSY_CUDA_ERR_* otherwise (message in plan.error).
 // Number of places where the sweep task lists violate the ordering the spinning kernels rely on (0 = deadlock-free).
 int64_t sweep_order_violations(const Plan& P);
+// 64-bit FNV-1a over every list of the plan the executor reads (task lists, step table, sweep plan, ownership, runs):
+// two plans with the same digest launch the same work on the same operands.
+uint64_t plan_digest(const Plan& P);
 int build_plan(Plan& plan, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
                int supNo, const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
                const int* partition, const PlanOptions& opt);

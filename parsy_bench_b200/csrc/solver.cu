@@ -1048,11 +1048,9 @@ extern "C" int parsy_cuda_get_stats(parsy_cuda_solver* s, parsy_cuda_stats* o) {
   return PARSY_CUDA_OK;
 }
 
-extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
-                                     int supNo, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
-                                     const int* partition, const parsy_cuda_options* opt, parsy_cuda_stats* o) {
-  Plan P;
-  PlanOptions po;
+static int plan_only(Plan& P, PlanOptions& po, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
+                     int supNo, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                     const int* partition, const parsy_cuda_options* opt) {
   if (opt) {
     po.nb = opt->block_cols; po.ignore_hlevels = opt->ignore_hlevels != 0;
     po.rank = opt->rank; po.world = std::max(1, opt->world); po.phase = opt->reserved[2]; po.top_levels = std::max(1, opt->reserved[3]);
@@ -1067,6 +1065,16 @@ extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, con
   }
   const int rc = build_plan(P, n, lC, lR, Li_ptr, blockSet, supNo, nullptr, col2Sup, nLevels, levelPtr, parPtr, partition, po);
   if (rc) return fail(rc, P.error);
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
+                                     int supNo, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                                     const int* partition, const parsy_cuda_options* opt, parsy_cuda_stats* o) {
+  Plan P;
+  PlanOptions po;
+  const int rc = plan_only(P, po, n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition, opt);
+  if (rc) return rc;
   if (o) {
     memset(o, 0, sizeof(*o));
     o->n = P.n; o->nsuper = P.nsuper; o->xsize = P.xsize; o->ssize = P.ssize;
@@ -1085,6 +1093,18 @@ extern "C" int parsy_cuda_plan_check(int n, const size_t* lC, const int* lR, con
     o->reserved[5] = (int64_t)P.solve_ctas.size(); o->reserved[6] = P.n_narrow_prefix_ctas; o->reserved[7] = sweep_order_violations(P);
     for (int s2 = 0; s2 < P.nsuper; ++s2) { if (P.owner[s2] == po.rank) o->reserved[2]++; if (P.owner[s2] < 0) o->reserved[3]++; }
   }
+  return PARSY_CUDA_OK;
+}
+
+extern "C" int parsy_cuda_plan_digest(int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
+                                      int supNo, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
+                                      const int* partition, const parsy_cuda_options* opt, uint64_t* digest) {
+  if (!digest) return fail(PARSY_CUDA_ERR_BAD_ARG, "digest is NULL");
+  Plan P;
+  PlanOptions po;
+  const int rc = plan_only(P, po, n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition, opt);
+  if (rc) return rc;
+  *digest = plan_digest(P);
   return PARSY_CUDA_OK;
 }
 

@@ -274,6 +274,29 @@ def plan_check(n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, p
     return rc, st.as_dict()
 
 
+def plan_digest(n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition, block_cols=0,
+                ignore_hlevels=False, rank=0, world=1, phase=0, top_levels=1, top_chunk=0):
+    """Host-only: 64-bit digest of the plan the executor would run (parsy_cuda_plan_digest)."""
+    L = lib()
+    opt = Options()
+    opt.block_cols, opt.ignore_hlevels, opt.use_graph = int(block_cols), int(ignore_hlevels), 1
+    opt.rank, opt.world, opt.reserved[2], opt.reserved[3] = int(rank), int(world), int(phase), int(top_levels)
+    opt.reserved[7] = int(top_chunk)
+    out = ctypes.c_uint64(0)
+    f = L.parsy_cuda_plan_digest
+    f.restype = c_int
+    f.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                  POINTER(Options), POINTER(ctypes.c_uint64)]
+    keep = [_u64(lC, "lC"), _i32(lR, "lR"), _u64(Li_ptr, "Li_ptr"), _i32(blockSet, "blockSet"),
+            _i32(col2Sup, "col2Sup"), _i32(levelPtr, "levelPtr", True), _i32(parPtr, "parPtr", True),
+            _i32(partition, "partition", True)]
+    p = [k[1] for k in keep]
+    rc = f(int(n), p[0], p[1], p[2], p[3], int(supNo), p[4], int(nLevels), p[5], p[6], p[7], byref(opt), byref(out))
+    if rc != OK:
+        raise ParsyCudaError(rc, "parsy_cuda_plan_digest")
+    return int(out.value)
+
+
 def plan_owned_ranges(n, lC, lR, Li_ptr, blockSet, supNo, col2Sup, nLevels, levelPtr, parPtr, partition, world,
                       for_rank, top_levels=1):
     """Host-only: contiguous [begin, end) runs of lValues owned by `for_rank` when sharding over `world` ranks."""

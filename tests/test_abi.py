@@ -186,3 +186,21 @@ def test_planner_update_flops_are_conserved(case):
                 assert rc == ex.OK
                 tot += sp["reserved"][4]
         assert abs(tot - want) <= 1e-9 * want + 8 * world * 2
+
+
+def test_plan_digests_match_the_committed_table():
+    """tests/golden/plan_digests.json (tools/plan_digests.py): digests of the plans the GPU parity runs of round 2 were
+    made with.  A planner change that alters what the device executes — task order, operands, tile classes, sweep plan,
+    ownership — shows up here without a GPU; regenerate the table only together with a GPU parity run."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("plan_digests", os.path.join(root, "tools", "plan_digests.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(root, "tests", "golden", "plan_digests.json")) as f:
+        want = json.load(f)
+    got = mod.table(mod.SMALL)
+    assert set(got) == set(want)
+    bad = [k for k in want if got[k] != want[k]]
+    assert not bad, bad[:5]

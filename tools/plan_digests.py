@@ -1,0 +1,54 @@
+"""Digests of the executor plan (parsy_cuda_plan_digest) for a set of matrices, schedules and sharding options.
+Host only.  `python tools/plan_digests.py [--large] [--json out.json]` — used to check that a planner change leaves
+the device work untouched (compare the table before and after) and to (re)generate tests/golden/plan_digests.json."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from parsy_bench_b200 import executor as ex, inspector, matrices  # noqa: E402
+
+SMALL = [("2d5", 60, 64, 1, 2), ("2d5", 150, 8, 1, 2), ("3d7", 12, 16, 0, 2), ("3d7", 24, 592, 1, 4),
+         ("3d27", 10, 16, 1, 2), ("3d27", 16, 16, 0, 2), ("2d5", 200, 64, 1, 3), ("3d7", 30, 64, 1, 2)]
+LARGE = [("2d5", 1000, 64, 1, 2), ("3d7", 60, 64, 1, 2), ("3d27", 40, 64, 1, 2)]
+SHARD = [(0, 1, 0, 1, 0), (0, 2, 1, 1, 0), (1, 2, 1, 1, 0), (0, 2, 2, 1, 0), (1, 2, 2, 1, 0), (3, 8, 1, 1, 0),
+         (3, 8, 2, 1, 0), (5, 8, 2, 2, 2), (1, 4, 1, 2, 0), (2, 4, 2, 2, 1)]      # rank, world, phase, top_levels, top_chunk
+
+
+def table(cases):
+    out = {}
+    for kind, N, cost, level, div in cases:
+        n, Ap, Ai, Ax = matrices.laplacian(kind, N)
+        S = inspector.analyze(n, Ap, Ai, Ax, cost, level, div)
+        args = (n, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.col2Sup, S.nLevels, S.levelPtr, S.parPtr, S.partition)
+        for rank, world, phase, tl, tc in SHARD:
+            for nb, ign in ((0, False), (64, False), (0, True)):
+                if world > 1 and (nb or ign):
+                    continue
+                key = f"{kind}:{N}:{cost}:{level}:{div}|r{rank}w{world}p{phase}t{tl}c{tc}|nb{nb}i{int(ign)}"
+                t = time.time()
+                try:
+                    d = ex.plan_digest(*args, block_cols=nb, ignore_hlevels=ign, rank=rank, world=world, phase=phase,
+                                       top_levels=tl, top_chunk=tc)
+                    out[key] = f"{d:016x}"
+                except ex.ParsyCudaError as e:
+                    out[key] = f"error {e.code}"
+                if os.environ.get("PLAN_DIGEST_TIMES"):
+                    print(f"{key}  {out[key]}  {1e3 * (time.time() - t):.1f} ms", file=sys.stderr)
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--large", action="store_true")
+    ap.add_argument("--json")
+    a = ap.parse_args()
+    T = table(SMALL + (LARGE if a.large else []))
+    if a.json:
+        with open(a.json, "w") as f:
+            json.dump(T, f, indent=0, sort_keys=True)
+    else:
+        for k in sorted(T):
+            print(k, T[k])
