@@ -6,21 +6,41 @@
 #include <cstring>
 #include <chrono>
 #include <thread>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
+#include <sys/mman.h>
 
 namespace parsy {
 
-void enumerate_pairs(std::vector<PairDesc>& out, int supNo, const int* blockSet, const size_t* Li_ptr, const int* lR,
-                     const int* col2Sup) {
-  // For descendant d, every maximal run of its off-diagonal rows that falls into the columns of one
-  // supernode t is one update pair (t, d).  The reference finds the same [lb, ub] by a linear scan for each
-  // d returned by ereach_sn (parallel_PB_Cholesky_05.h:137-152); rows are sorted, so runs are contiguous.
-  out.clear();
-  for (int d = 0; d < supNo; ++d) {
+void* big_alloc(size_t bytes) {
+  constexpr size_t HP = (size_t)2 << 20;
+  if (bytes < 2 * HP) { void* p = malloc(std::max<size_t>(bytes, 1)); if (!p) throw std::bad_alloc(); return p; }
+  const size_t len = (bytes + HP - 1) / HP * HP;
+  char* raw = (char*)mmap(nullptr, len + HP, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (raw == (char*)MAP_FAILED) throw std::bad_alloc();
+  char* p = (char*)(((uintptr_t)raw + HP - 1) / HP * HP);
+  if (p > raw) munmap(raw, (size_t)(p - raw));                       // give the unaligned head and the tail back
+  if (p + len < raw + len + HP) munmap(p + len, (size_t)(raw + len + HP - (p + len)));
+  madvise(p, len, MADV_HUGEPAGE);                                    // advisory: without THP the list is simply 4 KB-paged
+  return p;
+}
+void big_free(void* p, size_t bytes) {
+  constexpr size_t HP = (size_t)2 << 20;
+  if (bytes < 2 * HP) { free(p); return; }
+  munmap(p, (bytes + HP - 1) / HP * HP);
+}
+
+// For descendant d, every maximal run of its off-diagonal rows that falls into the columns of one supernode t is one
+// update pair (t, d).  The reference finds the same [lb, ub] by a linear scan for each d returned by ereach_sn
+// (parallel_PB_Cholesky_05.h:137-152); rows are sorted, so runs are contiguous.  Appends the pairs of d0 <= d < d1.
+template <class Vec> static void pairs_of_range(Vec& out, int d0, int d1, const int* blockSet, const size_t* Li_ptr,
+                           const int* lR, const int* col2Sup, int64_t* count_of_src) {
+  for (int d = d0; d < d1; ++d) {
     const int col0 = blockSet[d], w = blockSet[d + 1] - col0;
     const size_t rp = Li_ptr[col0];
     const int r = (int)(Li_ptr[blockSet[d + 1]] - rp);
+    const size_t before = out.size();
     int i = w;
     while (i < r) {
       const int t = col2Sup[lR[rp + i]];
@@ -29,10 +49,38 @@ void enumerate_pairs(std::vector<PairDesc>& out, int supNo, const int* blockSet,
       out.push_back(PairDesc{t, d, i, e - i, r - i});
       i = e;
     }
+    if (count_of_src) count_of_src[d] = (int64_t)(out.size() - before);
   }
 }
 
+void enumerate_pairs(std::vector<PairDesc>& out, int supNo, const int* blockSet, const size_t* Li_ptr, const int* lR,
+                     const int* col2Sup) {
+  out.clear();
+  pairs_of_range(out, 0, supNo, blockSet, Li_ptr, lR, col2Sup, nullptr);
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Planner threads: PARSY_PLAN_THREADS, default min(8, hardware threads).  The lists are built by index ranges that do not
+// overlap, in an order fixed by prefix sums, so the plan does not depend on the number of threads.
+static int plan_threads() {
+  static const int nt = [] {
+    const char* e = getenv("PARSY_PLAN_THREADS");
+    int v = e ? atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    return std::max(1, std::min(v, 64));
+  }();
+  return nt;
+}
+// fn(begin, end, part) over `parts` contiguous pieces of [0, n); the caller's thread takes the last piece
+template <class F> static void par_ranges(size_t n, int parts, F fn) {
+  parts = (int)std::max<size_t>(1, std::min<size_t>(parts, n / 4096 + 1));
+  if (parts == 1) { fn((size_t)0, n, 0); return; }
+  std::vector<std::thread> th;
+  th.reserve(parts - 1);
+  for (int k = 0; k + 1 < parts; ++k) th.emplace_back([=] { fn(n * k / parts, n * (k + 1) / parts, k); });
+  fn(n * (parts - 1) / parts, n, parts - 1);
+  for (auto& t : th) t.join();
+}
 // tiles (mi, ni) of a TM x TN grid over the lower trapezoid: column tile ni needs row tiles from (ni*TN)/TM on
 static inline int lower_tiles(int M, int N, int TM, int TN) {
   const int MT = cdiv(M, TM), NT = cdiv(N, TN);
@@ -97,15 +145,34 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     for (int s = 0; s < supNo; ++s) if (hl[s] >= first_top_level) P.sup[s].flags = 0;
   // every update pair (target, descendant) must run the descendant first: an earlier H-level, or earlier in
   // the same w-partition (SURVEY.md Appendix E legality condition)
-  enumerate_pairs(P.pairs, supNo, blockSet, Li_ptr, lR, col2Sup);
-  P.n_pairs = (int64_t)P.pairs.size();
+  // the row scan, by ranges of descendants on several threads; each piece also checks its pairs (the first offence in
+  // pair order is the one reported, as a serial pass would)
   std::vector<int64_t> src_ptr(supNo + 1, 0);
-  for (const PairDesc& q : P.pairs) {
-    if (q.tgt <= q.src || q.tgt >= supNo) { P.error = "row structure is not lower triangular"; return PARSY_CUDA_ERR_BAD_ARG; }
-    const bool ok = hl[q.src] < hl[q.tgt] || (hl[q.src] == hl[q.tgt] && part[q.src] == part[q.tgt] && pos[q.src] < pos[q.tgt]);
-    if (!ok) { P.error = "schedule runs a supernode before one of its descendants"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
-    src_ptr[q.src + 1]++;
+  {
+    const int parts = plan_threads();
+    std::vector<BigVec<PairDesc>> loc(parts);
+    std::vector<int> bad(parts, 0);
+    par_ranges((size_t)supNo, parts, [&](size_t d0, size_t d1, int k) {
+      loc[k].reserve((d1 - d0) * 3);
+      pairs_of_range(loc[k], (int)d0, (int)d1, blockSet, Li_ptr, lR, col2Sup, src_ptr.data() + 1);
+      for (const PairDesc& q : loc[k]) {
+        if (q.tgt <= q.src || q.tgt >= supNo) { bad[k] = 1; break; }
+        const bool ok = hl[q.src] < hl[q.tgt] || (hl[q.src] == hl[q.tgt] && part[q.src] == part[q.tgt] && pos[q.src] < pos[q.tgt]);
+        if (!ok) { bad[k] = 2; break; }
+      }
+    });
+    for (int k = 0; k < parts; ++k) {
+      if (bad[k] == 1) { P.error = "row structure is not lower triangular"; return PARSY_CUDA_ERR_BAD_ARG; }
+      if (bad[k] == 2) { P.error = "schedule runs a supernode before one of its descendants"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
+    }
+    std::vector<size_t> base(parts + 1, 0);
+    for (int k = 0; k < parts; ++k) base[k + 1] = base[k] + loc[k].size();
+    P.pairs.resize(base[parts]);
+    par_ranges((size_t)parts, parts, [&](size_t k0, size_t k1, int) {
+      for (size_t k = k0; k < k1; ++k) if (!loc[k].empty()) memcpy(P.pairs.data() + base[k], loc[k].data(), loc[k].size() * sizeof(PairDesc));
+    });
   }
+  P.n_pairs = (int64_t)P.pairs.size();
   for (int s = 0; s < supNo; ++s) src_ptr[s + 1] += src_ptr[s];
   std::vector<int32_t> nblk(supNo), step0(supNo, 0), need(supNo, 0);
   for (int s = 0; s < supNo; ++s) nblk[s] = P.sup[s].flags ? 1 : cdiv(P.sup[s].w, NB);
@@ -246,18 +313,25 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   // GEMM-shaped tasks, generated with a sort key: step, then class (0 trsm, 1 tiles128, 2 tiles64, 3 small), then
   // group (0 = "A": the target is factored in the very next step, 1 = "R": the rest; the executor overlaps R with
   // the next step's POTRF/TRSM on a second stream)
-  struct Gen { GemmTask t; int32_t step; int8_t cls, grp; };
+  // Kept compact: a generated task is (step, class, group) plus a reference — the index of a real pair whose GemmTask
+  // is written straight into its final place after the sort (the warp-FMA pairs, 99 % of the list on 2-D problems), or
+  // ~index into `extra`, the tasks that exist in full already (TRSM, trailing updates, tiled and split pairs).
+  struct Gen { int32_t step; int32_t ref; int8_t cls, grp; };
+  BigVec<GemmTask> extra;
+  auto task_of = [&](const Gen& g) -> GemmTask& { return extra[~g.ref]; };
   // distributed top: does an update task of (step, group) read a panel that another rank factors (= must it wait for
   // that step's broadcasts)?  Set by the emitters below through `src_remote`.
   bool src_remote = false;
-  std::vector<Gen> gen;
+  BigVec<Gen> gen;
   gen.reserve(P.pairs.size() + 3 * (size_t)o_blk[nsteps]);
   // group of an update by the step its target is factored at: 0 = the very next step ("A", on the chain), 1 = soon
   // ("R"), 2 = at least FAR_STEPS later ("far": distributed top only — runs on its own low-priority stream and is
   // awaited FAR_STEPS steps later, so bursts of separator-to-separator updates do not stall the chain)
+  auto group_of = [&](int st, int tstep) { return tstep <= st + 1 ? 0 : ((dist_top && tstep >= st + FAR_STEPS) ? 2 : 1); };
   auto emit_update = [&](const GemmTask& t, int st, int tstep, bool real_pair) {
-    const int grp = tstep <= st + 1 ? 0 : ((dist_top && tstep >= st + FAR_STEPS) ? 2 : 1);
-    Gen g; g.t = t; g.step = st; g.grp = (int8_t)grp;
+    const int grp = group_of(st, tstep);
+    Gen g; g.ref = ~(int32_t)extra.size(); g.step = st; g.grp = (int8_t)grp;
+    extra.push_back(t);
     if (src_remote) P.steps[st].upd_remote[grp] = 1;
     const double fl = upd_flops(t);
     if (real_pair && is_small_pair(t.K, t.N)) { g.cls = 3; P.class_flops[5] += fl; P.n_pairs_small++; }
@@ -295,12 +369,12 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       P.class_flops[1] += (double)nb * nb * nb / 3.0;
       const int Mb = I.r - j0 - nb;
       if (Mb > 0) {
-        Gen g; memset(&g.t, 0, sizeof(g.t));
-        GemmTask& t = g.t;
+        GemmTask t; memset(&t, 0, sizeof(t));
         t.a_off = I.valptr + (int64_t)j0 * I.r + j0 + nb; t.b_off = (int64_t)bt.slot * NB_MAX * NB_MAX; t.c_off = t.a_off;
         t.rel_off = -1; t.lda = I.r; t.ldb = NB_MAX; t.ldc = I.r; t.M = Mb; t.N = nb; t.K = nb;
         t.flags = GF_OVERWRITE | GF_B_LINV;
-        g.step = st; g.cls = 0; g.grp = 0;
+        Gen g; g.ref = ~(int32_t)extra.size(); g.step = st; g.cls = 0; g.grp = 0;
+        extra.push_back(t);
         gen.push_back(g);
         P.class_flops[2] += (double)Mb * nb * nb;
       }
@@ -355,38 +429,112 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   P.n_slots = slot; P.n_block_cols = slot;
 
   // narrow supernodes first inside every step (the low-register kernel variant takes the leading part of the list)
+  std::vector<int32_t> sort_tmp;
   for (int st = 0; st < nsteps; ++st) {
     Step& S = P.steps[st];
-    std::stable_sort(P.small_list.begin() + S.small_sup.begin, P.small_list.begin() + S.small_sup.end,
-                     [&](int a2, int b2) { return P.sup[a2].w < P.sup[b2].w; });
-    S.small_narrow = 0;
-    for (int i = S.small_sup.begin; i < S.small_sup.end; ++i) if (P.sup[P.small_list[i]].w <= SMALL_W_NARROW) S.small_narrow++;
+    // stable counting sort by width (1 .. SMALL_W)
+    int32_t* L0 = P.small_list.data() + S.small_sup.begin;
+    const int cnt = S.small_sup.size();
+    int32_t at[SMALL_W + 2] = {0};
+    for (int i = 0; i < cnt; ++i) at[P.sup[L0[i]].w + 1]++;
+    for (int w2 = 0; w2 <= SMALL_W; ++w2) at[w2 + 1] += at[w2];
+    S.small_narrow = at[SMALL_W_NARROW + 1];
+    sort_tmp.assign(L0, L0 + cnt);
+    for (int i = 0; i < cnt; ++i) L0[at[P.sup[sort_tmp[i]].w]++] = sort_tmp[i];
   }
   // ---- dataflow sweeps: nodes, tasks in dependency order, target lists, counters ------------------------------
+  int64_t sweep_violations = -1;
   auto build_sweeps = [&]() {
+    const double t_sw0 = tnow();
+    struct SwLap { bool on; double t0; std::function<double()> now; ~SwLap() { if (on) fprintf(stderr, "[plan] (sweep thread)              %.1f ms\n", (now() - t0) * 1e3); } } swlap{timing_on, t_sw0, tnow};
     P.n_nodes = node_first[supNo];
-    auto node_of_row = [&](int row) {
-      const int t = col2Sup[row];
-      return P.sup[t].flags ? node_first[t] : node_first[t] + (row - P.sup[t].col0) / NB;
-    };
+    // node of every column, as one table: the target scans below look up every stored row index once
+    std::vector<int32_t> node_of_col(n);
+    for (int s = 0; s < supNo; ++s) {
+      const SupInfo& I = P.sup[s];
+      const int32_t nf = node_first[s];
+      if (I.flags) std::fill(node_of_col.begin() + I.col0, node_of_col.begin() + I.col0 + I.w, nf);
+      else for (int j = 0; j < I.w; ++j) node_of_col[I.col0 + j] = nf + j / NB;
+    }
+    auto node_of_row = [&](int row) { return node_of_col[row]; };
     P.node_need.assign(P.n_nodes, 0);
     P.node_tiles.assign(P.n_nodes, 1);
-    // per_tile: one target entry (and one unit of `need`) per node AND 64-row tile, so that a tile can be published
-    // as soon as its own atomics are out
-    auto add_targets = [&](SolveTask& t, const SupInfo& I, bool per_tile) {
-      t.tgt_begin = (int32_t)P.solve_targets.size();
-      int last = -1;
-      for (int i = t.row0; i < t.row0 + t.nrows; ++i) {
-        if (per_tile && i > t.row0 && (i - t.row0) % SOLVE_TILE_ROWS == 0) {
-          t.tile_tgt[(i - t.row0) / SOLVE_TILE_ROWS - 1] = (int32_t)P.solve_targets.size();
-          last = -1;
+    P.solve_ctas.reserve((size_t)supNo / 4 + 2 * P.block_tasks.size());
+    std::vector<uint8_t> is_wide(supNo);
+    for (int s = 0; s < supNo; ++s) is_wide[s] = P.sup[s].flags ? 0 : 1;
+
+    // Target list of one task: the nodes whose unknowns its rows touch, in row order.  Offsets are relative to `out`
+    // (one list per thread, joined below).
+    //   block-column slices: one entry (and one unit of `need`) per node AND 64-row tile, so that a tile can be published
+    //     as soon as its own atomics are out — a scan of the slice's row indices;
+    //   narrow supernodes: one entry per node — read off the update pairs of the supernode (one pair = one maximal run
+    //     of rows inside one target supernode = one node, unless the target is wide: then its rows are scanned for the
+    //     block-column boundaries).
+    // Row runs of the wide supernodes: maximal runs of rows (own columns included) inside one node, as (end row, node),
+    // found by one scan per supernode; the slices of its block columns — together they cover the rows of the
+    // supernode nblk/2 times over — then walk the runs instead of the rows.
+    std::vector<int32_t> wide_list, wide_id(supNo, -1);
+    for (int s = 0; s < supNo; ++s) if (is_wide[s]) { wide_id[s] = (int32_t)wide_list.size(); wide_list.push_back(s); }
+    std::vector<int64_t> run_ptr(wide_list.size() + 1, 0);
+    BigVec<int32_t> run_end, run_node;
+    {
+      const int parts = std::max(1, plan_threads() / 2);
+      std::vector<BigVec<int32_t>> le(parts), ln(parts);
+      std::vector<size_t> pb(parts, wide_list.size()), pe(parts, wide_list.size());
+      par_ranges(wide_list.size(), parts, [&](size_t w0, size_t w1, int k) {
+        pb[k] = w0; pe[k] = w1;
+        for (size_t wi = w0; wi < w1; ++wi) {
+          const SupInfo& I = P.sup[wide_list[wi]];
+          const size_t before = le[k].size();
+          int last = -1;
+          for (int i = 0; i < I.r; ++i) {
+            const int nd = node_of_row(lR[I.rowptr + i]);
+            if (nd != last) { if (last >= 0) le[k].push_back(i); ln[k].push_back(nd); last = nd; }
+          }
+          if (last >= 0) le[k].push_back(I.r);
+          run_ptr[wi + 1] = (int64_t)(le[k].size() - before);
         }
-        const int nd = node_of_row(lR[I.rowptr + i]);
-        if (nd != last) { P.solve_targets.push_back(nd); P.node_need[nd]++; last = nd; }
+      });
+      for (size_t wi = 0; wi < wide_list.size(); ++wi) run_ptr[wi + 1] += run_ptr[wi];
+      run_end.resize((size_t)run_ptr[wide_list.size()]); run_node.resize(run_end.size());
+      for (int k = 0; k < parts; ++k) {
+        if (le[k].empty()) continue;
+        memcpy(run_end.data() + run_ptr[pb[k]], le[k].data(), le[k].size() * sizeof(int32_t));
+        memcpy(run_node.data() + run_ptr[pb[k]], ln[k].data(), ln[k].size() * sizeof(int32_t));
       }
-      t.tgt_end = (int32_t)P.solve_targets.size();
-      for (int k = per_tile ? (t.nrows + SOLVE_TILE_ROWS - 1) / SOLVE_TILE_ROWS - 1 : 0; k < 4; ++k)
-        if (k >= 0) t.tile_tgt[k] = t.tgt_end;
+    }
+    auto slice_targets = [&](SolveTask& t, BigVec<int32_t>& out, int32_t* need_local) {
+      t.tgt_begin = (int32_t)out.size();
+      const int64_t r0 = run_ptr[wide_id[t.sup]], r1 = run_ptr[wide_id[t.sup] + 1];
+      const int32_t* re = run_end.data() + r0;
+      const int32_t* rn = run_node.data() + r0;
+      int k = (int)(std::upper_bound(re, re + (r1 - r0), t.row0) - re);      // the run holding row0
+      const int end = t.row0 + t.nrows;
+      for (int a = t.row0, tile = 0; a < end; a += SOLVE_TILE_ROWS, ++tile) {
+        if (tile > 0) t.tile_tgt[tile - 1] = (int32_t)out.size();
+        const int b2 = std::min(a + SOLVE_TILE_ROWS, end);
+        for (;; ++k) {                                                        // every run that meets [a, b2)
+          out.push_back(rn[k]); need_local[rn[k]]++;
+          if (re[k] >= b2) break;
+        }
+        if (re[k] == b2) ++k;
+      }
+      t.tgt_end = (int32_t)out.size();
+      for (int q = std::max(0, (t.nrows + SOLVE_TILE_ROWS - 1) / SOLVE_TILE_ROWS - 1); q < 4; ++q) t.tile_tgt[q] = t.tgt_end;
+    };
+    auto narrow_targets = [&](SolveTask& t, const SupInfo& I, BigVec<int32_t>& out, int32_t* need_local) {
+      t.tgt_begin = (int32_t)out.size();
+      for (int64_t e2 = src_ptr[t.sup]; e2 < src_ptr[t.sup + 1]; ++e2) {
+        const PairDesc& q = P.pairs[e2];
+        if (!is_wide[q.tgt]) { const int nd = node_first[q.tgt]; out.push_back(nd); need_local[nd]++; continue; }
+        int last = -1;
+        for (int i = q.lb; i < q.lb + q.nd1; ++i) {
+          const int nd = node_of_row(lR[I.rowptr + i]);
+          if (nd != last) { out.push_back(nd); need_local[nd]++; last = nd; }
+        }
+      }
+      t.tgt_end = (int32_t)out.size();
+      for (int k = 0; k < 4; ++k) t.tile_tgt[k] = t.tgt_end;
     };
     // Leaf region: narrow supernodes without a block-column supernode anywhere below them in the supernodal etree.
     // It is closed under descendants, so its tasks can run first, on the light narrow-only kernels (backward sweep:
@@ -399,17 +547,21 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       if (above_block[s] && I.r > I.w) above_block[col2Sup[lR[I.rowptr + I.w]]] = 1;   // etree parent: first row below the block
     }
     P.n_narrow_prefix_ctas = 0;
+    if (timing_on) fprintf(stderr, "[plan] (sweep: tables)   %.1f ms\n", (tnow() - t_sw0) * 1e3);
+    // First the ORDER of the tasks and their grouping into CTAs, as 16-byte descriptors (serial, cheap); the tasks
+    // themselves and their target lists are then written by ranges of that list on several threads.
+    struct TaskSrc { int32_t id; int32_t row0, nrows; int32_t kind; };   // id: supernode (kind 0) or block task (kind 1, 3 = first slice)
+    BigVec<TaskSrc> src;
+    src.reserve((size_t)supNo + 2 * P.block_tasks.size());
     for (int pass = 0; pass < 2; ++pass)
     for (int st = 0; st < nsteps; ++st) {
+      if (timing_on && st == 0) fprintf(stderr, "[plan] (sweep: pass %d at)   %.1f ms\n", pass, (tnow() - t_sw0) * 1e3);
       const Step& S = P.steps[st];
       const bool seen_block = pass == 1;
       // narrow supernodes: long panels get a CTA each (kind 2), the others go eight per CTA (kind 0)
       auto narrow_task = [&](int s) {
         const SupInfo& I = P.sup[s];
-        SolveTask t; memset(&t, 0, sizeof(t));
-        t.sup = s; t.node = node_first[s]; t.j0 = 0; t.nb = I.w; t.slot = -1; t.row0 = I.w; t.nrows = I.r - I.w; t.first = 1;
-        add_targets(t, I, false);
-        P.solve_tasks.push_back(t);
+        src.push_back(TaskSrc{s, I.w, I.r - I.w, 0});
       };
       auto is_tall = [&](int s) {
         const SupInfo& I = P.sup[s];
@@ -420,13 +572,13 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         const int s = P.small_list[i];
         if ((above_block[s] != 0) != (pass == 1)) continue;
         if (!is_tall(s)) { shortlist.push_back(s); continue; }
-        SolveCta c; c.kind = 2; c.first = (int32_t)P.solve_tasks.size(); c.count = 1; c.pad = 0;
+        SolveCta c; c.kind = 2; c.first = (int32_t)src.size(); c.count = 1; c.pad = 0;
         narrow_task(s);
         P.solve_ctas.push_back(c);
         if (!seen_block) P.n_narrow_prefix_ctas++;
       }
       for (size_t i0 = 0; i0 < shortlist.size(); i0 += 8) {
-        SolveCta c; c.kind = 0; c.first = (int32_t)P.solve_tasks.size(); c.count = (int32_t)std::min<size_t>(8, shortlist.size() - i0); c.pad = 0;
+        SolveCta c; c.kind = 0; c.first = (int32_t)src.size(); c.count = (int32_t)std::min<size_t>(8, shortlist.size() - i0); c.pad = 0;
         for (int i = 0; i < c.count; ++i) narrow_task(shortlist[i0 + i]);
         P.solve_ctas.push_back(c);
         if (!seen_block) P.n_narrow_prefix_ctas++;
@@ -448,18 +600,67 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         const int nd = node_first[b.sup] + b.j0 / NB;
         P.node_tiles[nd] = ntile;
         for (int k = 0; k < ntile; ++k) {
-          SolveTask t; memset(&t, 0, sizeof(t));
-          t.sup = b.sup; t.node = nd; t.j0 = b.j0; t.nb = b.nb; t.slot = b.slot;
-          t.row0 = b.j0 + b.nb + cut[k];
-          t.nrows = cut[k + 1] - cut[k];
-          t.first = k == 0;
-          add_targets(t, I, true);
-          SolveCta c; c.kind = 1; c.first = (int32_t)P.solve_tasks.size(); c.count = 1; c.pad = 0;
-          P.solve_tasks.push_back(t);
+          SolveCta c; c.kind = 1; c.first = (int32_t)src.size(); c.count = 1; c.pad = 0;
+          src.push_back(TaskSrc{i, b.j0 + b.nb + cut[k], cut[k + 1] - cut[k], k == 0 ? 3 : 1});
           P.solve_ctas.push_back(c);
         }
       }
     }
+    if (timing_on) fprintf(stderr, "[plan] (sweep: task order at) %.1f ms\n", (tnow() - t_sw0) * 1e3);
+    const size_t ntask = src.size();
+    P.solve_tasks.resize(ntask);
+    const int parts = std::max(1, plan_threads() / 2);
+    std::vector<BigVec<int32_t>> tg(parts);
+    std::vector<size_t> part_begin(parts + 1, ntask), part_end(parts + 1, ntask);
+    std::vector<std::vector<int32_t>> need_part(parts);      // counters per thread (the top separators are named by
+                                                             // thousands of tasks: a shared counter would bounce), summed below
+    par_ranges(ntask, parts, [&](size_t t0, size_t t1, int part) {
+      part_begin[part] = t0; part_end[part] = t1;
+      BigVec<int32_t>& out = tg[part];
+      out.reserve((t1 - t0) * 3);
+      need_part[part].assign(P.n_nodes, 0);
+      int32_t* need_local = need_part[part].data();
+      for (size_t ti = t0; ti < t1; ++ti) {
+        const TaskSrc& d = src[ti];
+        SolveTask& t = P.solve_tasks[ti];
+        memset(&t, 0, sizeof(t));
+        if (d.kind == 0) {
+          const SupInfo& I = P.sup[d.id];
+          t.sup = d.id; t.node = node_first[d.id]; t.j0 = 0; t.nb = I.w; t.slot = -1; t.row0 = d.row0; t.nrows = d.nrows; t.first = 1;
+          t.rowptr = I.rowptr; t.valptr = I.valptr; t.col0 = I.col0; t.r = I.r;
+          narrow_targets(t, I, out, need_local);
+        } else {
+          const BlockTask& bk = P.block_tasks[d.id];
+          const SupInfo& I = P.sup[bk.sup];
+          t.sup = bk.sup; t.node = node_first[bk.sup] + bk.j0 / NB; t.j0 = bk.j0; t.nb = bk.nb; t.slot = bk.slot;
+          t.row0 = d.row0; t.nrows = d.nrows; t.first = d.kind == 3;
+          t.rowptr = I.rowptr; t.valptr = I.valptr; t.col0 = I.col0; t.r = I.r;
+          slice_targets(t, out, need_local);
+        }
+      }
+    });
+    for (int k = 0; k < parts; ++k)
+      if (!need_part[k].empty()) for (int v = 0; v < P.n_nodes; ++v) P.node_need[v] += need_part[k][v];
+    size_t total = 0;
+    std::vector<size_t> base(parts + 1, 0);
+    for (int k = 0; k < parts; ++k) { base[k] = total; total += tg[k].size(); }
+    P.solve_targets.resize(total);
+    // join the lists, shift the tasks' offsets, and hand every task its node's input count (complete now)
+    par_ranges((size_t)parts, parts, [&](size_t k0, size_t k1, int) {
+      for (size_t k = k0; k < k1; ++k) {
+        if (!tg[k].empty()) memcpy(P.solve_targets.data() + base[k], tg[k].data(), tg[k].size() * sizeof(int32_t));
+        const int32_t off = (int32_t)base[k];
+        for (size_t ti = part_begin[k]; ti < part_end[k]; ++ti) {
+          SolveTask& t = P.solve_tasks[ti];
+          t.tgt_begin += off; t.tgt_end += off;
+          for (int q = 0; q < 4; ++q) t.tile_tgt[q] += off;
+          t.need = P.node_need[t.node];
+        }
+      }
+    });
+    if (timing_on) fprintf(stderr, "[plan] (sweep: targets at) %.1f ms\n", (tnow() - t_sw0) * 1e3);
+    // the sweep kernels spin on counters: a task list that is not a topological order would hang the device
+    sweep_violations = sweep_order_violations(P);
   };
   // the sweep plan only depends on the factor-side lists above: built on a second thread next to the update lists
   std::thread sweep_thread(build_sweeps);
@@ -473,13 +674,21 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     const PairDesc& q = P.pairs[pi];
     const SupInfo& D = P.sup[q.src]; const SupInfo& T = P.sup[q.tgt];
     const int st = step0[q.src] + nblk[q.src] - 1;
-    GemmTask t; memset(&t, 0, sizeof(t));
-    t.a_off = D.valptr + q.lb; t.b_off = t.a_off; t.c_off = T.valptr; t.rel_off = rel;
-    t.lda = t.ldb = D.r; t.ldc = T.r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
     P.rel_prefix[pi] = rel; P.rel_pair_src[pi] = q.src; P.rel_pair_tgt[pi] = q.tgt; P.rel_pair_lb[pi] = q.lb;
+    const int64_t rel_here = rel;
     rel += q.m;
     if (!pair_active(q.src, q.tgt)) continue;
     src_remote = false;
+    if (!dist_top && is_small_pair(D.w, q.nd1)) {      // the common case: no GemmTask yet, see pair_task below
+      Gen g; g.step = st; g.ref = (int32_t)pi; g.cls = 3; g.grp = (int8_t)group_of(st, step0[q.tgt]);
+      const double k = D.w, nd1 = q.nd1, nd3 = q.m - q.nd1;
+      P.class_flops[5] += nd1 * nd1 * k + 2.0 * nd3 * nd1 * k; P.n_pairs_small++;
+      gen.push_back(g);
+      continue;
+    }
+    GemmTask t; memset(&t, 0, sizeof(t));
+    t.a_off = D.valptr + q.lb; t.b_off = t.a_off; t.c_off = T.valptr; t.rel_off = rel_here;
+    t.lda = t.ldb = D.r; t.ldc = T.r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
     if (!dist_top) { emit_update(t, st, step0[q.tgt], true); continue; }
     // Distributed top.  (i) The pair's columns are split by the target block column they fall into; a rank keeps what
     // it owns.  (ii) A wide source is applied in K-chunks of PAIR_KBLK block columns as they are finished instead of
@@ -520,14 +729,15 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     std::vector<int32_t> tdef(3 * (size_t)nsteps, 0), t64(3 * (size_t)nsteps, 0);
     for (const Gen& g : gen) {
       if (g.cls != 1 && g.cls != 2) continue;
-      tdef[3 * g.step + g.grp] += g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : lower_tiles(g.t.M, g.t.N, 64, 64);
-      t64[3 * g.step + g.grp] += lower_tiles(g.t.M, g.t.N, 64, 64);
+      const GemmTask& t = task_of(g);
+      tdef[3 * g.step + g.grp] += g.cls == 1 ? lower_tiles(t.M, t.N, 128, 64) : lower_tiles(t.M, t.N, 64, 64);
+      t64[3 * g.step + g.grp] += lower_tiles(t.M, t.N, 64, 64);
     }
     for (Gen& g : gen) {
       if (g.cls != 1 && g.cls != 2) continue;
       const int k = 3 * g.step + g.grp;
       if (tdef[k] >= SMS) continue;
-      const double fl = upd_flops(g.t);
+      const double fl = upd_flops(task_of(g));
       const int ncls = t64[k] >= SMS ? 2 : 4;
       if (ncls == g.cls) continue;
       if (g.cls == 1) { P.class_flops[3] -= fl; P.class_flops[4] += fl; }
@@ -540,70 +750,91 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     constexpr int FILL = 2 * 148;
     std::vector<int32_t> tl(3 * (size_t)nsteps, 0);
     auto ntiles = [&](const Gen& g) {
-      return g.cls == 1 ? lower_tiles(g.t.M, g.t.N, 128, 64) : g.cls == 2 ? lower_tiles(g.t.M, g.t.N, 64, 64) : lower_tiles(g.t.M, g.t.N, 32, 32);
+      const GemmTask& t = task_of(g);
+      return g.cls == 1 ? lower_tiles(t.M, t.N, 128, 64) : g.cls == 2 ? lower_tiles(t.M, t.N, 64, 64) : lower_tiles(t.M, t.N, 32, 32);
     };
     for (const Gen& g : gen) if (g.cls == 1 || g.cls == 2 || g.cls == 4) tl[3 * g.step + g.grp] += ntiles(g);
     const size_t n0 = gen.size();
     for (size_t i = 0; i < n0; ++i) {
-      if ((gen[i].cls != 1 && gen[i].cls != 2 && gen[i].cls != 4) || gen[i].t.K < 128) continue;
+      if ((gen[i].cls != 1 && gen[i].cls != 2 && gen[i].cls != 4) || task_of(gen[i]).K < 128) continue;
       const int total = tl[3 * gen[i].step + gen[i].grp];
       if (total >= FILL) continue;
-      const int K = gen[i].t.K;
+      const int K = task_of(gen[i]).K;
       const int f = std::min(std::min(cdiv(K, 64), cdiv(FILL, std::max(total, 1))), 8);
       if (f <= 1) continue;
       const int chunk = cdiv(cdiv(K, f), 16) * 16;
       for (int k0 = chunk; k0 < K; k0 += chunk) {
         Gen g = gen[i];
-        g.t.a_off += (int64_t)k0 * g.t.lda; g.t.b_off += (int64_t)k0 * g.t.ldb; g.t.K = std::min(chunk, K - k0);
+        GemmTask t = task_of(gen[i]);
+        t.a_off += (int64_t)k0 * t.lda; t.b_off += (int64_t)k0 * t.ldb; t.K = std::min(chunk, K - k0);
+        g.ref = ~(int32_t)extra.size();
+        extra.push_back(t);
         gen.push_back(g);
       }
-      gen[i].t.K = chunk;
+      task_of(gen[i]).K = chunk;
     }
   }
   lap("tile classes + split-K");
   if (gen.size() > (size_t)INT32_MAX) { P.error = "task list too large"; return PARSY_CUDA_ERR_BAD_ARG; }
   // stable counting sort by (step, class, group): the key space is small (15 buckets per step)
-  std::vector<int32_t> ord(gen.size());
+  BigVec<int32_t> ord(gen.size());
+  std::vector<int32_t> bucket_begin;
   {
     auto bucket = [&](const Gen& g) { return (size_t)g.step * 15 + (size_t)g.cls * 3 + (size_t)g.grp; };
     std::vector<int32_t> start((size_t)nsteps * 15 + 1, 0);
     for (const Gen& g : gen) start[bucket(g) + 1]++;
     for (size_t b2 = 0; b2 + 1 < start.size(); ++b2) start[b2 + 1] += start[b2];
+    bucket_begin = start;
     for (size_t i = 0; i < gen.size(); ++i) ord[start[bucket(gen[i])]++] = (int32_t)i;
   }
+  lap("counting sort");
   P.gemm_tasks.resize(gen.size());
-  {
-    size_t i = 0;
-    for (int st = 0; st < nsteps; ++st) {
-      Step& S = P.steps[st];
-      auto take = [&](int cls, int grp) {
-        const int32_t b0 = (int32_t)i;
-        while (i < ord.size() && gen[ord[i]].step == st && gen[ord[i]].cls == cls && gen[ord[i]].grp == grp) {
-          P.gemm_tasks[i] = gen[ord[i]].t;
-          ++i;
-        }
-        return Range{b0, (int32_t)i};
-      };
-      S.trsm = take(0, 0);
-      for (int g = 0; g < 3; ++g) S.upd[g].u128 = take(1, g);
-      for (int g = 0; g < 3; ++g) S.upd[g].u64 = take(2, g);
-      for (int g = 0; g < 3; ++g) S.upd[g].small_pairs = take(3, g);
-      for (int g = 0; g < 3; ++g) S.upd[g].u32 = take(4, g);
+  lap("resize");
+  // the sorted list, written in place by index ranges (threads); the per-step ranges are the bucket boundaries
+  BigVec<uint32_t> shape(ord.size());      // per task: M, bit 31 = K <= 4 (all the small-task pass below needs)
+  par_ranges(ord.size(), plan_threads(), [&](size_t i0, size_t i1, int) {
+    for (size_t i = i0; i < i1; ++i) {
+      const Gen& g = gen[ord[i]];
+      if (g.ref < 0) { const GemmTask& e = extra[~g.ref]; P.gemm_tasks[i] = e; shape[i] = (uint32_t)e.M | (e.K <= 4 ? 0x80000000u : 0u); continue; }
+      const PairDesc& q = P.pairs[g.ref];              // a warp-FMA pair, described by the pair table alone
+      const SupInfo& D = P.sup[q.src];
+      GemmTask& t = P.gemm_tasks[i];
+      t.a_off = D.valptr + q.lb; t.b_off = t.a_off; t.c_off = P.sup[q.tgt].valptr; t.rel_off = P.rel_prefix[g.ref];
+      t.lda = t.ldb = D.r; t.ldc = P.sup[q.tgt].r; t.M = q.m; t.N = q.nd1; t.K = D.w; t.flags = GF_LOWER | GF_ATOMIC;
+      t.tile0 = 0;
+      shape[i] = (uint32_t)t.M | (t.K <= 4 ? 0x80000000u : 0u);
     }
+  });
+  for (int st = 0; st < nsteps; ++st) {
+    Step& S = P.steps[st];
+    auto take = [&](int cls, int grp) { const size_t b2 = (size_t)st * 15 + cls * 3 + grp; return Range{bucket_begin[b2], bucket_begin[b2 + 1]}; };
+    S.trsm = take(0, 0);
+    for (int g = 0; g < 3; ++g) S.upd[g].u128 = take(1, g);
+    for (int g = 0; g < 3; ++g) S.upd[g].u64 = take(2, g);
+    for (int g = 0; g < 3; ++g) S.upd[g].small_pairs = take(3, g);
+    for (int g = 0; g < 3; ++g) S.upd[g].u32 = take(4, g);
   }
-  std::vector<Gen>().swap(gen);
+  BigVec<Gen>().swap(gen);
   lap("sort + take");
   // row chunks of the small pairs, narrow (K <= 4) first inside every (step, group)
+  {
+    size_t total = 0;
+    for (int st = 0; st < nsteps; ++st)
+      for (int g = 0; g < 3; ++g)
+        for (int gi = P.steps[st].upd[g].small_pairs.begin; gi < P.steps[st].upd[g].small_pairs.end; ++gi) total += cdiv((int)(shape[gi] & 0x7fffffffu), 256);
+    P.small_tasks.reserve(total);
+  }
   for (int st = 0; st < nsteps; ++st)
     for (int g = 0; g < 3; ++g) {
       UpdGroup& U = P.steps[st].upd[g];
       U.small.begin = (int32_t)P.small_tasks.size();
       for (int pass = 0; pass < 2; ++pass) {
         for (int gi = U.small_pairs.begin; gi < U.small_pairs.end; ++gi) {
-          const GemmTask& t = P.gemm_tasks[gi];
-          if ((t.K <= 4) != (pass == 0)) continue;
-          for (int r0 = 0; r0 < t.M; r0 += 256) {
-            SmallTask stt; stt.pair = gi; stt.row0 = r0; stt.nrows = std::min(256, t.M - r0); stt.pad = 0;
+          const bool narrow = (shape[gi] & 0x80000000u) != 0;
+          const int M = (int)(shape[gi] & 0x7fffffffu);
+          if (narrow != (pass == 0)) continue;
+          for (int r0 = 0; r0 < M; r0 += 256) {
+            SmallTask stt; stt.pair = gi; stt.row0 = r0; stt.nrows = std::min(256, M - r0); stt.pad = 0;
             P.small_tasks.push_back(stt);
           }
         }
@@ -611,6 +842,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       }
       U.small.end = (int32_t)P.small_tasks.size();
     }
+  lap("small tasks");
 
   // tile prefixes per launch segment
   for (int st = 0; st < nsteps; ++st) {
@@ -668,7 +900,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       P.bcast_ptr[st + 1] = (int32_t)(P.bcast.size() / 3);
     }
   }
-  lap("small tasks + prefixes");
+  lap("prefixes + bcast");
   sweep_thread.join();
   lap("sweep plan");
   // ---- what a factorization zeroes / assembles, what the ranks sum, which columns the sweeps solve ---------------
@@ -701,15 +933,8 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       else if (cb >= 0) { P.col_runs.push_back(cb); P.col_runs.push_back(ce); cb = -1; }
     }
   }
-  for (SolveTask& t : P.solve_tasks) {
-    const SupInfo& I = P.sup[t.sup];
-    t.rowptr = I.rowptr; t.valptr = I.valptr; t.col0 = I.col0; t.r = I.r; t.need = P.node_need[t.node]; t.pad2 = 0;
-  }
   lap("runs");
-  // the sweep kernels spin on counters: a task list that is not a topological order would hang the device
-  const int64_t viol = sweep_order_violations(P);
-  lap("sweep order check");
-  if (viol != 0) { P.error = "internal error: sweep task order is not a topological order"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
+  if (sweep_violations != 0) { P.error = "internal error: sweep task order is not a topological order"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
   return PARSY_CUDA_OK;
 }
 
@@ -724,7 +949,7 @@ struct Fnv {
     for (; i < nbytes; ++i) h = (h ^ c[i]) * 1099511628211ull;
   }
   template <class T> void pod(const T& v) { bytes(&v, sizeof(T)); }
-  template <class T> void vec(const std::vector<T>& v) { pod((uint64_t)v.size()); if (!v.empty()) bytes(v.data(), v.size() * sizeof(T)); }
+  template <class V> void vec(const V& v) { pod((uint64_t)v.size()); if (!v.empty()) bytes(v.data(), v.size() * sizeof(typename V::value_type)); }
 };
 }  // namespace
 

@@ -14,8 +14,29 @@
 #include <cstddef>
 #include <vector>
 #include <string>
+#include <new>
+#include <utility>
 
 namespace parsy {
+
+// Allocator of the planner's long lists.  First-touch page faults are the largest single cost of building a plan for
+// a 2-D problem (about 100 MB of lists; ~1.7 us per 4 KB page on the hosts measured, three times the cost of the writes
+// themselves), so lists of 4 MB and more are mapped directly, 2 MB-aligned, with MADV_HUGEPAGE; smaller ones come from
+// malloc.  resize(n) leaves new elements uninitialised (no second pass over the list): every user fills what it sizes.
+void* big_alloc(size_t bytes);
+void big_free(void* p, size_t bytes);
+template <class T> struct BigAlloc {
+  using value_type = T;
+  BigAlloc() = default;
+  template <class U> BigAlloc(const BigAlloc<U>&) {}
+  T* allocate(size_t n) { return (T*)big_alloc(n * sizeof(T)); }
+  void deallocate(T* p, size_t n) { big_free(p, n * sizeof(T)); }
+  template <class U> void construct(U* p) { ::new ((void*)p) U; }
+  template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+  template <class U> bool operator==(const BigAlloc<U>&) const { return true; }
+  template <class U> bool operator!=(const BigAlloc<U>&) const { return false; }
+};
+template <class T> using BigVec = std::vector<T, BigAlloc<T>>;
 
 constexpr int SMALL_W = 32;       // widest supernode handled by the warp-cooperative path
 constexpr int SMALL_R = 1024;     // ... and its largest row count
@@ -169,20 +190,20 @@ struct Plan {
   int32_t n = 0, nsuper = 0, nlevels = 0;
   int64_t xsize = 0, ssize = 0, nnzA = 0;
   int nb = 128;
-  std::vector<SupInfo> sup;
+  BigVec<SupInfo> sup;
   std::vector<int32_t> small_list;
   std::vector<BlockTask> block_tasks;
-  std::vector<GemmTask> gemm_tasks;
-  std::vector<SmallTask> small_tasks;
+  BigVec<GemmTask> gemm_tasks;
+  BigVec<SmallTask> small_tasks;
   std::vector<Step> steps;
   std::vector<int32_t> hlevel_first_step;   // nlevels+1
   // relative indices: rel_src_row[e] = global row index to look up, rel_tgt[e] = target supernode;
   // filled on the device from (pair prefix) — here only the per-pair prefix and descriptors
-  std::vector<PairDesc> pairs;              // all pairs, in GemmTask order for the first pairs.size() real pairs
-  std::vector<int64_t> rel_prefix;          // per real pair with a map: start in the rel array (size npairs+1)
-  std::vector<int32_t> rel_pair_src;        // per rel-pair: source supernode
-  std::vector<int32_t> rel_pair_tgt;        // per rel-pair: target supernode
-  std::vector<int32_t> rel_pair_lb;         // per rel-pair: lb
+  BigVec<PairDesc> pairs;                   // all pairs, in GemmTask order for the first pairs.size() real pairs
+  BigVec<int64_t> rel_prefix;               // per real pair with a map: start in the rel array (size npairs+1)
+  BigVec<int32_t> rel_pair_src;             // per rel-pair: source supernode
+  BigVec<int32_t> rel_pair_tgt;             // per rel-pair: target supernode
+  BigVec<int32_t> rel_pair_lb;              // per rel-pair: lb
   int64_t rel_entries = 0;
   std::vector<int32_t> owner;               // per supernode: owning rank, -1 = shared top (world > 1 only)
   std::vector<int32_t> node_owner;          // per node (narrow supernode / block column) of the top: owning rank
@@ -200,11 +221,11 @@ struct Plan {
   int32_t first_top_step = 0;
   // dataflow sweeps
   int32_t n_nodes = 0;
-  std::vector<SolveTask> solve_tasks;      // forward order (dependency steps ascending)
+  BigVec<SolveTask> solve_tasks;           // forward order (dependency steps ascending)
   std::vector<SolveCta> solve_ctas;        // forward order; the backward sweep walks it in reverse
   int32_t n_narrow_prefix_ctas = 0;        // leading CTAs (all of kind 0) that come before the first block-column task:
                                            // the leaf region of the tree, run by the light narrow-only sweep kernels
-  std::vector<int32_t> solve_targets;      // node ids
+  BigVec<int32_t> solve_targets;           // node ids
   std::vector<int32_t> node_need;          // forward: number of tasks that add into the node's right-hand side
   std::vector<int32_t> node_tiles;         // backward: number of slices of the node (narrow supernodes: 1)
   int32_t n_slots = 0;

@@ -689,9 +689,9 @@ static int create_impl(parsy_cuda_solver** out, int n, const int* c, const int* 
     cudaFree(d_prefix); cudaFree(d_src); cudaFree(d_tgt); cudaFree(d_lb);
   }
   // host copies of the per-pair bookkeeping are no longer needed
-  std::vector<int64_t>().swap(P.rel_prefix); std::vector<int32_t>().swap(P.rel_pair_src);
-  std::vector<int32_t>().swap(P.rel_pair_tgt); std::vector<int32_t>().swap(P.rel_pair_lb);
-  std::vector<PairDesc>().swap(P.pairs);
+  decltype(P.rel_prefix)().swap(P.rel_prefix); decltype(P.rel_pair_src)().swap(P.rel_pair_src);
+  decltype(P.rel_pair_tgt)().swap(P.rel_pair_tgt); decltype(P.rel_pair_lb)().swap(P.rel_pair_lb);
+  decltype(P.pairs)().swap(P.pairs);
   if (c && r) {
     const int64_t nnz = c[n];
     P.nnzA = nnz;
