@@ -6,7 +6,6 @@
 #include <cstring>
 #include <chrono>
 #include <thread>
-#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <sys/mman.h>
@@ -145,6 +144,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     for (int s = 0; s < supNo; ++s) if (hl[s] >= first_top_level) P.sup[s].flags = 0;
   // every update pair (target, descendant) must run the descendant first: an earlier H-level, or earlier in
   // the same w-partition (SURVEY.md Appendix E legality condition)
+  lap("schedule arrays");
   // the row scan, by ranges of descendants on several threads; each piece also checks its pairs (the first offence in
   // pair order is the one reported, as a serial pass would)
   std::vector<int64_t> src_ptr(supNo + 1, 0);
@@ -174,6 +174,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   }
   P.n_pairs = (int64_t)P.pairs.size();
   for (int s = 0; s < supNo; ++s) src_ptr[s + 1] += src_ptr[s];
+  lap("pair scan");
   std::vector<int32_t> nblk(supNo), step0(supNo, 0), need(supNo, 0);
   for (int s = 0; s < supNo; ++s) nblk[s] = P.sup[s].flags ? 1 : cdiv(P.sup[s].w, NB);
   P.hlevel_first_step.assign(nLevels + 1, 0);
@@ -446,7 +447,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   int64_t sweep_violations = -1;
   auto build_sweeps = [&]() {
     const double t_sw0 = tnow();
-    struct SwLap { bool on; double t0; std::function<double()> now; ~SwLap() { if (on) fprintf(stderr, "[plan] (sweep thread)              %.1f ms\n", (now() - t0) * 1e3); } } swlap{timing_on, t_sw0, tnow};
+    auto sw_at = [&](const char* what) { if (timing_on) fprintf(stderr, "[plan] (sweep thread: %s at) %.1f ms\n", what, (tnow() - t_sw0) * 1e3); };
     P.n_nodes = node_first[supNo];
     // node of every column, as one table: the target scans below look up every stored row index once
     std::vector<int32_t> node_of_col(n);
@@ -470,8 +471,25 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     //   narrow supernodes: one entry per node — read off the update pairs of the supernode (one pair = one maximal run
     //     of rows inside one target supernode = one node, unless the target is wide: then its rows are scanned for the
     //     block-column boundaries).
+    // Runs of one update pair, as fn(end row, node): its rows lie inside ONE target supernode, so a narrow target is a
+    // single run; inside a wide target the (sorted) rows are cut at the block-column boundaries by bisection.
+    auto pair_walk = [&](const PairDesc& q, const SupInfo& I, auto&& fn) {
+      if (!is_wide[q.tgt]) { fn(q.lb + q.nd1, node_first[q.tgt]); return; }
+      const int* rows = lR + I.rowptr;
+      const int c0 = P.sup[q.tgt].col0, nf = node_first[q.tgt];
+      int pos = q.lb;
+      const int end = q.lb + q.nd1;
+      while (pos < end) {
+        const int blk = (rows[pos] - c0) / NB;
+        // a block column has NB columns and the rows are distinct: its last row is less than NB entries away
+        const int lim = std::min(end, pos + NB);
+        const int next = rows[lim - 1] < c0 + (blk + 1) * NB ? lim : (int)(std::lower_bound(rows + pos, rows + lim, c0 + (blk + 1) * NB) - rows);
+        fn(next, nf + blk);
+        pos = next;
+      }
+    };
     // Row runs of the wide supernodes: maximal runs of rows (own columns included) inside one node, as (end row, node),
-    // found by one scan per supernode; the slices of its block columns — together they cover the rows of the
+    // from the block columns and the update pairs of the supernode; the slices of its block columns — together they cover the rows of the
     // supernode nblk/2 times over — then walk the runs instead of the rows.
     std::vector<int32_t> wide_list, wide_id(supNo, -1);
     for (int s = 0; s < supNo; ++s) if (is_wide[s]) { wide_id[s] = (int32_t)wide_list.size(); wide_list.push_back(s); }
@@ -484,14 +502,12 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       par_ranges(wide_list.size(), parts, [&](size_t w0, size_t w1, int k) {
         pb[k] = w0; pe[k] = w1;
         for (size_t wi = w0; wi < w1; ++wi) {
-          const SupInfo& I = P.sup[wide_list[wi]];
+          const int s = wide_list[wi];
+          const SupInfo& I = P.sup[s];
           const size_t before = le[k].size();
-          int last = -1;
-          for (int i = 0; i < I.r; ++i) {
-            const int nd = node_of_row(lR[I.rowptr + i]);
-            if (nd != last) { if (last >= 0) le[k].push_back(i); ln[k].push_back(nd); last = nd; }
-          }
-          if (last >= 0) le[k].push_back(I.r);
+          for (int b2 = 0; b2 < nblk[s]; ++b2) { le[k].push_back(std::min(I.w, (b2 + 1) * NB)); ln[k].push_back(node_first[s] + b2); }   // own columns
+          for (int64_t e2 = src_ptr[s]; e2 < src_ptr[s + 1]; ++e2)
+            pair_walk(P.pairs[e2], I, [&](int end_row, int nd) { le[k].push_back(end_row); ln[k].push_back(nd); });
           run_ptr[wi + 1] = (int64_t)(le[k].size() - before);
         }
       });
@@ -503,6 +519,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         memcpy(run_node.data() + run_ptr[pb[k]], ln[k].data(), ln[k].size() * sizeof(int32_t));
       }
     }
+    sw_at("row runs");
     auto slice_targets = [&](SolveTask& t, BigVec<int32_t>& out, int32_t* need_local) {
       t.tgt_begin = (int32_t)out.size();
       const int64_t r0 = run_ptr[wide_id[t.sup]], r1 = run_ptr[wide_id[t.sup] + 1];
@@ -524,15 +541,8 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     };
     auto narrow_targets = [&](SolveTask& t, const SupInfo& I, BigVec<int32_t>& out, int32_t* need_local) {
       t.tgt_begin = (int32_t)out.size();
-      for (int64_t e2 = src_ptr[t.sup]; e2 < src_ptr[t.sup + 1]; ++e2) {
-        const PairDesc& q = P.pairs[e2];
-        if (!is_wide[q.tgt]) { const int nd = node_first[q.tgt]; out.push_back(nd); need_local[nd]++; continue; }
-        int last = -1;
-        for (int i = q.lb; i < q.lb + q.nd1; ++i) {
-          const int nd = node_of_row(lR[I.rowptr + i]);
-          if (nd != last) { out.push_back(nd); need_local[nd]++; last = nd; }
-        }
-      }
+      for (int64_t e2 = src_ptr[t.sup]; e2 < src_ptr[t.sup + 1]; ++e2)
+        pair_walk(P.pairs[e2], I, [&](int, int nd) { out.push_back(nd); need_local[nd]++; });
       t.tgt_end = (int32_t)out.size();
       for (int k = 0; k < 4; ++k) t.tile_tgt[k] = t.tgt_end;
     };
@@ -547,7 +557,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
       if (above_block[s] && I.r > I.w) above_block[col2Sup[lR[I.rowptr + I.w]]] = 1;   // etree parent: first row below the block
     }
     P.n_narrow_prefix_ctas = 0;
-    if (timing_on) fprintf(stderr, "[plan] (sweep: tables)   %.1f ms\n", (tnow() - t_sw0) * 1e3);
+    sw_at("tables");
     // First the ORDER of the tasks and their grouping into CTAs, as 16-byte descriptors (serial, cheap); the tasks
     // themselves and their target lists are then written by ranges of that list on several threads.
     struct TaskSrc { int32_t id; int32_t row0, nrows; int32_t kind; };   // id: supernode (kind 0) or block task (kind 1, 3 = first slice)
@@ -555,7 +565,6 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     src.reserve((size_t)supNo + 2 * P.block_tasks.size());
     for (int pass = 0; pass < 2; ++pass)
     for (int st = 0; st < nsteps; ++st) {
-      if (timing_on && st == 0) fprintf(stderr, "[plan] (sweep: pass %d at)   %.1f ms\n", pass, (tnow() - t_sw0) * 1e3);
       const Step& S = P.steps[st];
       const bool seen_block = pass == 1;
       // narrow supernodes: long panels get a CTA each (kind 2), the others go eight per CTA (kind 0)
@@ -606,7 +615,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         }
       }
     }
-    if (timing_on) fprintf(stderr, "[plan] (sweep: task order at) %.1f ms\n", (tnow() - t_sw0) * 1e3);
+    sw_at("task order");
     const size_t ntask = src.size();
     P.solve_tasks.resize(ntask);
     const int parts = std::max(1, plan_threads() / 2);
@@ -658,9 +667,10 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
         }
       }
     });
-    if (timing_on) fprintf(stderr, "[plan] (sweep: targets at) %.1f ms\n", (tnow() - t_sw0) * 1e3);
+    sw_at("targets");
     // the sweep kernels spin on counters: a task list that is not a topological order would hang the device
     sweep_violations = sweep_order_violations(P);
+    sw_at("order check, end");
   };
   // the sweep plan only depends on the factor-side lists above: built on a second thread next to the update lists
   std::thread sweep_thread(build_sweeps);
@@ -901,7 +911,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     }
   }
   lap("prefixes + bcast");
-  sweep_thread.join();
+  if (sweep_thread.joinable()) sweep_thread.join();
   lap("sweep plan");
   // ---- what a factorization zeroes / assembles, what the ranks sum, which columns the sweeps solve ---------------
   {
