@@ -146,7 +146,8 @@ void parsy_cuda_options_default(parsy_cuda_options* opt);
  *   blockSet, supNo   supernode partition;  aTree = sParent;  col2Sup
  *   nLevels, levelPtr, parPtr, partition    LBC schedule (cholesky/InspectionLevel_06.h:18)
  * The derived task lists (descendant pairs with (lb, ndrow1, ndrow3), relative row indices, per-level
- * batches) are computed here once per structure. */
+ * batches) are computed here once per structure, on up to PARSY_PLAN_THREADS host threads (environment; default
+ * min(8, hardware threads); the lists do not depend on the count).  PARSY_PLAN_TIMING=1 prints the planner's laps. */
 int parsy_cuda_create(parsy_cuda_solver** out, int n, const int* c, const int* r, const size_t* lC, const int* lR,
                       const size_t* Li_ptr, const int* blockSet, int supNo, const int* aTree, const int* col2Sup,
                       int nLevels, const int* levelPtr, const int* parPtr, const int* partition,

@@ -204,3 +204,23 @@ def test_plan_digests_match_the_committed_table():
     assert set(got) == set(want)
     bad = [k for k in want if got[k] != want[k]]
     assert not bad, bad[:5]
+
+
+def test_plan_does_not_depend_on_the_number_of_planner_threads(tmp_path):
+    """The planner splits its long lists over PARSY_PLAN_THREADS threads by index ranges whose order is fixed by prefix
+    sums: the digests of two medium-size problems (several ranges per list) must agree between 1, 3 and 8 threads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tables = []
+    for nt in (1, 3, 8):
+        out = tmp_path / f"d{nt}.json"
+        env = dict(os.environ, PARSY_PLAN_THREADS=str(nt))
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "plan_digests.py"), "--medium", "--json", str(out)],
+                           env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        with open(out) as f:
+            tables.append(json.load(f))
+    assert len(tables[0]) >= 20 and not any(v.startswith("error") for v in tables[0].values())
+    assert tables[0] == tables[1] == tables[2]

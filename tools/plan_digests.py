@@ -12,6 +12,7 @@ from parsy_bench_b200 import executor as ex, inspector, matrices  # noqa: E402
 
 SMALL = [("2d5", 60, 64, 1, 2), ("2d5", 150, 8, 1, 2), ("3d7", 12, 16, 0, 2), ("3d7", 24, 592, 1, 4),
          ("3d27", 10, 16, 1, 2), ("3d27", 16, 16, 0, 2), ("2d5", 200, 64, 1, 3), ("3d7", 30, 64, 1, 2)]
+MEDIUM = [("2d5", 300, 64, 1, 2), ("3d7", 40, 64, 1, 2)]      # large enough for the planner to split its lists over threads
 LARGE = [("2d5", 1000, 64, 1, 2), ("3d7", 60, 64, 1, 2), ("3d27", 40, 64, 1, 2)]
 SHARD = [(0, 1, 0, 1, 0), (0, 2, 1, 1, 0), (1, 2, 1, 1, 0), (0, 2, 2, 1, 0), (1, 2, 2, 1, 0), (3, 8, 1, 1, 0),
          (3, 8, 2, 1, 0), (5, 8, 2, 2, 2), (1, 4, 1, 2, 0), (2, 4, 2, 2, 1)]      # rank, world, phase, top_levels, top_chunk
@@ -43,9 +44,10 @@ def table(cases):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--large", action="store_true")
+    ap.add_argument("--medium", action="store_true", help="only the MEDIUM cases (thread-independence check)")
     ap.add_argument("--json")
     a = ap.parse_args()
-    T = table(SMALL + (LARGE if a.large else []))
+    T = table(MEDIUM if a.medium else SMALL + (LARGE if a.large else []))
     if a.json:
         with open(a.json, "w") as f:
             json.dump(T, f, indent=0, sort_keys=True)
