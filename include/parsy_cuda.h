@@ -32,6 +32,7 @@ extern "C" {
 #define PARSY_CUDA_ERR_NO_DEVICE 4      /* no CUDA device / driver                                       */
 #define PARSY_CUDA_ERR_CUDA 5           /* a CUDA runtime call failed (see parsy_cuda_last_error)        */
 #define PARSY_CUDA_ERR_STATE 6          /* call order violated (e.g. solve before factor)                */
+#define PARSY_CUDA_ERR_NO_MEMORY 7      /* host memory exhausted while building the plan                 */
 
 const char* parsy_cuda_last_error(void);
 int parsy_cuda_device_count(void);

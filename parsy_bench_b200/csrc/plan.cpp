@@ -6,6 +6,8 @@
 #include <cstring>
 #include <chrono>
 #include <thread>
+#include <exception>
+#include <stdexcept>
 #include <cstdio>
 #include <cstdlib>
 #include <sys/mman.h>
@@ -71,14 +73,24 @@ static int plan_threads() {
   return nt;
 }
 // fn(begin, end, part) over `parts` contiguous pieces of [0, n); the caller's thread takes the last piece
+// An exception in any piece (std::bad_alloc, in practice) is rethrown in the caller once every thread has finished.
 template <class F> static void par_ranges(size_t n, int parts, F fn) {
   parts = (int)std::max<size_t>(1, std::min<size_t>(parts, n / 4096 + 1));
   if (parts == 1) { fn((size_t)0, n, 0); return; }
   std::vector<std::thread> th;
-  th.reserve(parts - 1);
-  for (int k = 0; k + 1 < parts; ++k) th.emplace_back([=] { fn(n * k / parts, n * (k + 1) / parts, k); });
-  fn(n * (parts - 1) / parts, n, parts - 1);
+  std::vector<std::exception_ptr> err(parts);
+  auto piece = [&](int k) {
+    try { fn(n * k / parts, n * (k + 1) / parts, k); } catch (...) { err[k] = std::current_exception(); }
+  };
+  try {
+    th.reserve(parts - 1);
+    for (int k = 0; k + 1 < parts; ++k) th.emplace_back(piece, k);
+  } catch (...) {                                   // no more threads to be had: the caller does the rest itself
+    for (int k = (int)th.size(); k + 1 < parts; ++k) piece(k);
+  }
+  piece(parts - 1);
   for (auto& t : th) t.join();
+  for (int k = 0; k < parts; ++k) if (err[k]) std::rethrow_exception(err[k]);
 }
 // tiles (mi, ni) of a TM x TN grid over the lower trapezoid: column tile ni needs row tiles from (ni*TN)/TM on
 static inline int lower_tiles(int M, int N, int TM, int TN) {
@@ -88,9 +100,29 @@ static inline int lower_tiles(int M, int N, int TM, int TN) {
   return cnt;
 }
 
+static int build_plan_impl(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
+                           int supNo, const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr,
+                           const int* parPtr, const int* partition, const PlanOptions& opt);
+
+// The planner allocates a few hundred bytes per supernode and pair on the host; running out of memory is reported, not
+// thrown through the C ABI.
 int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet, int supNo,
                const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr, const int* parPtr,
                const int* partition, const PlanOptions& opt) {
+  try {
+    return build_plan_impl(P, n, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition, opt);
+  } catch (const std::bad_alloc&) {
+    P.error = "out of host memory while building the plan";
+    return PARSY_CUDA_ERR_NO_MEMORY;
+  } catch (const std::exception& e) {
+    P.error = std::string("planner failed: ") + e.what();
+    return PARSY_CUDA_ERR_NO_MEMORY;
+  }
+}
+
+static int build_plan_impl(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li_ptr, const int* blockSet,
+                           int supNo, const int* aTree, const int* col2Sup, int nLevels, const int* levelPtr,
+                           const int* parPtr, const int* partition, const PlanOptions& opt) {
   const bool timing_on = getenv("PARSY_PLAN_TIMING") != nullptr;
   auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double tlast = tnow();
@@ -673,7 +705,8 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
     sw_at("order check, end");
   };
   // the sweep plan only depends on the factor-side lists above: built on a second thread next to the update lists
-  std::thread sweep_thread(build_sweeps);
+  std::exception_ptr sweep_error;
+  std::thread sweep_thread([&] { try { build_sweeps(); } catch (...) { sweep_error = std::current_exception(); } });
   struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } sweep_joiner{sweep_thread};
   lap("factor-side lists + trailing");
   // real pairs (+ relative-index bookkeeping)
@@ -912,6 +945,7 @@ int build_plan(Plan& P, int n, const size_t* lC, const int* lR, const size_t* Li
   }
   lap("prefixes + bcast");
   if (sweep_thread.joinable()) sweep_thread.join();
+  if (sweep_error) std::rethrow_exception(sweep_error);
   lap("sweep plan");
   // ---- what a factorization zeroes / assembles, what the ranks sum, which columns the sweeps solve ---------------
   {

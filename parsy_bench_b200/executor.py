@@ -14,7 +14,7 @@ import numpy as np
 from ._lib import lib, last_error, Options, Stats
 
 SOLVE_FWD, SOLVE_BWD = 1, 2
-OK, ERR_NOT_SPD, ERR_BAD_ARG, ERR_BAD_SCHEDULE, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE = range(7)
+OK, ERR_NOT_SPD, ERR_BAD_ARG, ERR_BAD_SCHEDULE, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_NO_MEMORY = range(8)
 
 
 class ParsyCudaError(RuntimeError):

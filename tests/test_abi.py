@@ -224,3 +224,4 @@ def test_plan_does_not_depend_on_the_number_of_planner_threads(tmp_path):
             tables.append(json.load(f))
     assert len(tables[0]) >= 20 and not any(v.startswith("error") for v in tables[0].values())
     assert tables[0] == tables[1] == tables[2]
+
