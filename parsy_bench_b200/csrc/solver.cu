@@ -1271,7 +1271,10 @@ extern "C" int parsy_cuda_cholesky_left_sn_07(int n, int* c, int* r, double* val
                                               size_t* Li_ptr, double* lValues, int* blockSet, int supNo, double* timing,
                                               int* prunePtr, int* pruneSet, int* map, double* contribs) {
   (void)map; (void)contribs;
-  if (!c || !r || !values || !lValues || !blockSet) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  if (!c || !r || !values || !lValues || !blockSet || !lC || !lR || !Li_ptr || n < 0 || supNo < 0) { fail(PARSY_CUDA_ERR_BAD_ARG, "NULL argument"); return 0; }
+  if (supNo > 0 && (blockSet[0] != 0 || blockSet[supNo] != n)) { fail(PARSY_CUDA_ERR_BAD_ARG, "blockSet does not cover 0..n"); return 0; }
+  for (int s = 0; s < supNo; ++s)
+    if (blockSet[s] >= blockSet[s + 1]) { fail(PARSY_CUDA_ERR_BAD_ARG, "empty supernode"); return 0; }
   // col2sup is not an argument of the serial twin: rebuild it from blockSet
   std::vector<int> c2s((size_t)std::max(n, 0));
   for (int s = 0; s < supNo; ++s) for (int j = blockSet[s]; j < blockSet[s + 1]; ++j) c2s[j] = s;

@@ -225,3 +225,24 @@ def test_plan_does_not_depend_on_the_number_of_planner_threads(tmp_path):
     assert len(tables[0]) >= 20 and not any(v.startswith("error") for v in tables[0].values())
     assert tables[0] == tables[1] == tables[2]
 
+
+
+def test_serial_twin_rejects_broken_supernode_partitions_before_touching_them():
+    """parsy_cuda_cholesky_left_sn_07 rebuilds col2sup from blockSet on the host (PB_Cholesky.h:16 has no such argument):
+    NULL structure arrays and partitions that do not cover 0..n in increasing order are refused, not indexed."""
+    L = _lib.lib()
+    f = L.parsy_cuda_cholesky_left_sn_07
+    f.restype = ctypes.c_int
+    n = 4
+    I = lambda a: np.asarray(a, np.int32)     # noqa: E731
+    U = lambda a: np.asarray(a, np.uint64)    # noqa: E731
+    c, r, v = I([0, 1, 2, 3, 4]), I([0, 1, 2, 3]), np.ones(4)
+    lC, lR, Lip, lv = U([0, 1, 2, 3, 4]), I([0, 1, 2, 3]), U([0, 1, 2, 3, 4]), np.zeros(4)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    f.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 8 + [ctypes.c_int] + [ctypes.c_void_p] * 5
+    for bad in (I([0, 1, 2, 3, 5]), I([1, 2, 3, 4, 4]), I([0, 3, 2, 3, 4]), I([0, 1, 1, 3, 4])):
+        assert f(n, P(c), P(r), P(v), P(lC), P(lR), P(Lip), P(lv), P(bad), 4, None, None, None, None, None) == 0
+        assert "blockSet" in ex.last_error() or "supernode" in ex.last_error()
+    good = I([0, 1, 2, 3, 4])
+    assert f(n, P(c), P(r), P(v), None, P(lR), P(Lip), P(lv), P(good), 4, None, None, None, None, None) == 0
+    assert "NULL" in ex.last_error()
