@@ -186,6 +186,10 @@ static int build_plan_impl(Plan& P, int n, const size_t* lC, const int* lR, cons
     std::vector<int> bad(parts, 0);
     par_ranges((size_t)supNo, parts, [&](size_t d0, size_t d1, int k) {
       loc[k].reserve((d1 - d0) * 3);
+      // every stored row index is looked up in col2Sup (here) and in the panels (device): refuse what lies outside
+      if (d1 > d0)
+        for (size_t e2 = Li_ptr[blockSet[d0]]; e2 < Li_ptr[blockSet[d1]]; ++e2)
+          if ((unsigned)lR[e2] >= (unsigned)n) { bad[k] = 3; return; }
       pairs_of_range(loc[k], (int)d0, (int)d1, blockSet, Li_ptr, lR, col2Sup, src_ptr.data() + 1);
       for (const PairDesc& q : loc[k]) {
         if (q.tgt <= q.src || q.tgt >= supNo) { bad[k] = 1; break; }
@@ -194,6 +198,7 @@ static int build_plan_impl(Plan& P, int n, const size_t* lC, const int* lR, cons
       }
     });
     for (int k = 0; k < parts; ++k) {
+      if (bad[k] == 3) { P.error = "row index outside the matrix"; return PARSY_CUDA_ERR_BAD_ARG; }
       if (bad[k] == 1) { P.error = "row structure is not lower triangular"; return PARSY_CUDA_ERR_BAD_ARG; }
       if (bad[k] == 2) { P.error = "schedule runs a supernode before one of its descendants"; return PARSY_CUDA_ERR_BAD_SCHEDULE; }
     }

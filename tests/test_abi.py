@@ -246,3 +246,14 @@ def test_serial_twin_rejects_broken_supernode_partitions_before_touching_them():
     good = I([0, 1, 2, 3, 4])
     assert f(n, P(c), P(r), P(v), None, P(lR), P(Lip), P(lv), P(good), 4, None, None, None, None, None) == 0
     assert "NULL" in ex.last_error()
+
+
+def test_planner_refuses_row_indices_outside_the_matrix():
+    from parsy_bench_b200 import matrices
+    n, Ap, Ai, Ax = matrices.laplacian("2d5", 12)
+    S = inspector.analyze(n, Ap, Ai, Ax)
+    for where, val in ((int(S.i_ptr[n]) - 1, n + 7), (int(S.i_ptr[n]) // 2, -1), (0, 2 ** 31 - 1)):
+        s2 = np.array(S.s, np.int32, copy=True)
+        s2[where] = val
+        rc, _ = ex.plan_check(n, S.p, s2, S.i_ptr, S.super, S.nsuper, S.col2Sup, S.nLevels, S.levelPtr, S.parPtr, S.partition)
+        assert rc == ex.ERR_BAD_ARG and "row index" in ex.last_error()
