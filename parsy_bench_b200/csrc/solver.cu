@@ -559,6 +559,7 @@ static int create_impl(parsy_cuda_solver** out, int n, const int* c, const int* 
                        const parsy_cuda_options* opt, parsy_cuda_solver* parent, bool share_buffers) {
   if (!out) return fail(PARSY_CUDA_ERR_BAD_ARG, "out is NULL");
   *out = nullptr;
+  if (n < 0 || supNo < 0) return fail(PARSY_CUDA_ERR_BAD_ARG, "negative size");
   if (parsy_cuda_device_count() <= 0) return fail(PARSY_CUDA_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
   parsy_cuda_options o;
   parsy_cuda_options_default(&o);
@@ -592,6 +593,13 @@ static int create_impl(parsy_cuda_solver** out, int n, const int* c, const int* 
   }
   rc = build_plan(s->plan, n, lC, lR, Li_ptr, blockSet, supNo, aTree, col2Sup, nLevels, levelPtr, parPtr, partition, po);
   if (rc) { g_err = s->plan.error; delete s; return rc; }
+  if (c && r) {
+    // pattern of A: the assembly kernels index the panels with it, so it is checked once here, on the host
+    bool ok = c[0] == 0;
+    for (int j = 0; ok && j < n; ++j) ok = c[j] <= c[j + 1];
+    for (int64_t e = 0; ok && e < (int64_t)c[n]; ++e) ok = (unsigned)r[e] < (unsigned)n;
+    if (!ok) { delete s; return fail(PARSY_CUDA_ERR_BAD_ARG, "pattern of A: column pointers must start at 0 and not decrease, row indices must lie in 0..n-1"); }
+  }
   Plan& P = s->plan;
 #define TRY(x) do { rc = (x); if (rc) { parsy_cuda_destroy(s); return rc; } } while (0)
 #define TRYCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { parsy_cuda_destroy(s); return fail(PARSY_CUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
