@@ -11,19 +11,44 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from parsy_bench_b200 import executor as ex, inspector, matrices  # noqa: E402
 
 SMALL = [("2d5", 60, 64, 1, 2), ("2d5", 150, 8, 1, 2), ("3d7", 12, 16, 0, 2), ("3d7", 24, 592, 1, 4),
-         ("3d27", 10, 16, 1, 2), ("3d27", 16, 16, 0, 2), ("2d5", 200, 64, 1, 3), ("3d7", 30, 64, 1, 2)]
+         ("3d27", 10, 16, 1, 2), ("3d27", 16, 16, 0, 2), ("2d5", 200, 64, 1, 3), ("3d7", 30, 64, 1, 2),
+         ("2d5+dag", 120, 16, 1, 2), ("3d27+dag", 16, 16, 0, 2), ("rnd", 6000, 16, 1, 2)]
 MEDIUM = [("2d5", 300, 64, 1, 2), ("3d7", 40, 64, 1, 2)]      # large enough for the planner to split its lists over threads
 LARGE = [("2d5", 1000, 64, 1, 2), ("3d7", 60, 64, 1, 2), ("3d27", 40, 64, 1, 2)]
 SHARD = [(0, 1, 0, 1, 0), (0, 2, 1, 1, 0), (1, 2, 1, 1, 0), (0, 2, 2, 1, 0), (1, 2, 2, 1, 0), (3, 8, 1, 1, 0),
          (3, 8, 2, 1, 0), (5, 8, 2, 2, 2), (1, 4, 1, 2, 0), (2, 4, 2, 2, 1)]      # rank, world, phase, top_levels, top_chunk
 
 
+def random_pattern(n, extra_per_col, seed):
+    """Lower half of a symmetric, strictly diagonally dominant matrix with a random pattern plus a path."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    cols = [sorted({j + 1} | {int(i) for i in rng.integers(j + 1, n, size=extra_per_col)}) for j in range(n - 1)] + [[]]
+    deg = np.zeros(n)
+    for j, rows in enumerate(cols):
+        deg[j] += len(rows)
+        for i in rows:
+            deg[i] += 1
+    Ap, Ai, Ax = [0], [], []
+    for j, rows in enumerate(cols):
+        Ai += [j] + rows
+        Ax += [deg[j] + 1.0] + [-1.0] * len(rows)
+        Ap.append(len(Ai))
+    return n, np.array(Ap, np.int32), np.array(Ai, np.int32), np.array(Ax)
+
+
 def table(cases):
     out = {}
     for kind, N, cost, level, div in cases:
-        n, Ap, Ai, Ax = matrices.laplacian(kind, N)
+        if kind == "rnd":
+            n, Ap, Ai, Ax = random_pattern(N, 2, 11)
+        else:
+            n, Ap, Ai, Ax = matrices.laplacian(kind.split("+")[0], N)
         S = inspector.analyze(n, Ap, Ai, Ax, cost, level, div)
         args = (n, S.p, S.s, S.i_ptr, S.super, S.nsuper, S.col2Sup, S.nLevels, S.levelPtr, S.parPtr, S.partition)
+        if kind.endswith("+dag"):      # the DAG-based LBC schedule over the factor's blocks instead of the tree-based one
+            nl, lp, pp, part = inspector.dag_lbc_bcsc(S, cost, level, div)
+            args = args[:7] + (nl, lp, pp, part)
         for rank, world, phase, tl, tc in SHARD:
             for nb, ign in ((0, False), (64, False), (0, True)):
                 if world > 1 and (nb or ign):
