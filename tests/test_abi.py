@@ -257,3 +257,23 @@ def test_planner_refuses_row_indices_outside_the_matrix():
         s2[where] = val
         rc, _ = ex.plan_check(n, S.p, s2, S.i_ptr, S.super, S.nsuper, S.col2Sup, S.nLevels, S.levelPtr, S.parPtr, S.partition)
         assert rc == ex.ERR_BAD_ARG and "row index" in ex.last_error()
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both public headers (and the forwarding header under C++) must compile on their own."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "h.c"
+    src.write_text('#include "parsy_cuda.h"\n#include "parsy_inspector.h"\nint main(void) { return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "h.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if shutil.which("g++"):
+        src2 = tmp_path / "h.cpp"
+        src2.write_text('#include <cstddef>\n#include "parsy_cuda_dropin.h"\nint main() { return 0; }\n')
+        r = subprocess.run(["g++", "-std=c++11", "-Wall", "-I", os.path.join(root, "include"), "-c", str(src2), "-o",
+                            str(tmp_path / "h2.o")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
