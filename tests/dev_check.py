@@ -1,4 +1,6 @@
-"""Developer smoke: factor + solves on one synthetic case through the C ABI, compared with oracle/_ref."""
+"""Developer check (not collected by pytest; run by hand on a GPU box: python tests/dev_check.py 2d5 200): factor + solves
+on one synthetic case through the C ABI, compared with the compiled reference.  Lives under tests/ because it executes
+oracle/_ref, which only the tests, smoke() and bench.py's CPU legs may do."""
 import os
 import sys
 import time
@@ -6,7 +8,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from refdump import ref_case, rel_err  # noqa: E402
 from parsy_bench_b200 import executor as ex  # noqa: E402
 
